@@ -1,0 +1,127 @@
+/* vdb200 — C ABI of the B200-native Versatile-Diffusion sampling hot path (libvdb200.so).
+ *
+ * The reference (SHI-Labs/Versatile-Diffusion) has no FFI/operator boundary: its hot path is eager
+ * PyTorch inside lib/model_zoo.  This header is the boundary a maintainer binds
+ * instead: every entry point replaces the arithmetic of one reference call site (cited per function),
+ * takes raw device pointers + explicit sizes + a cudaStream_t (passed as void*), allocates nothing,
+ * keeps no global state besides a thread-local error string and a launch counter, and returns an
+ * int status (0 = ok).  Python binding: versatile-diffusion_b200/vdb200/_lib.py (ctypes); the
+ * reference-side stubs are shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - activations: bf16, NHWC / token-major ([B, H, W, C] == [B*H*W, C]); latents/images fp32.
+ *   - weights: bf16 [N, K] row-major (K contiguous); conv weights repacked to [Cout, (ky,kx,ci)].
+ *   - all device pointers 16-byte aligned; leading dimensions in ELEMENTS.
+ *   - `stream` is a cudaStream_t; kernels are stream-ordered and CUDA-graph capturable.
+ */
+#ifndef VDB200_H_
+#define VDB200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { VDB_OK = 0, VDB_ERR_INVALID = 1, VDB_ERR_CUDA = 2, VDB_ERR_UNSUPPORTED = 3 };
+enum { VDB_ACT_NONE = 0, VDB_ACT_SILU = 1, VDB_ACT_GELU = 2, VDB_ACT_QUICK_GELU = 3, VDB_ACT_GEGLU = 4 };
+
+/* ---- library state ------------------------------------------------------------------------- */
+const char* vdb_version(void);
+const char* vdb_last_error(void);        /* message of the last non-zero status on this thread */
+long long vdb_launch_count(void);        /* kernels launched by this library since the last reset */
+void vdb_reset_launch_count(void);
+int vdb_num_sms(void);
+
+/* ---- K4: CFG mix + DDIM update — DDIMSampler.p_sample_ddim, lib/model_zoo/ddim.py:144-171 ------
+ * e = e_u + scale*(e_c - e_u); pred_x0 = (x - sqrt(1-a_t) e)/sqrt(a_t);
+ * x_prev = sqrt(a_prev) pred_x0 + sqrt(1 - a_prev - sigma^2) e + sigma*noise*temperature.
+ * coef: device fp32 {a_t, a_prev, sigma_t, sqrt_one_minus_a_t}[, more rows]; step_idx (device int,
+ * may be NULL) selects the row, so one captured CUDA graph serves every step. e_uncond/noise/pred_x0
+ * may be NULL (scale==1 path, eta==0, no pred_x0 wanted). fp32, bit-identical to the reference ops. */
+int vdb_ddim_cfg_step(const float* e_uncond, const float* e_cond, const float* x, const float* noise,
+                      const float* coef, const int* step_idx, float scale, float temperature, float* x_prev,
+                      float* pred_x0, long long n, void* stream);
+int vdb_add_int(int* p, int delta, void* stream); /* device-side step counter update */
+
+/* ---- tcgen05 GEMM — nn.Linear / 1x1 conv call sites: attention.py:37-64,161-193,237,249;
+ *      autokl_modules.py:150-202; HF CLIP q/k/v/out/fc1/fc2 (clip.py:58-61,92-100) ----------------
+ * out[M,N] = act(alpha * [A | A2] @ W^T + bias) + resid.   A [M,K] (lda), optional A2 [M,K2] (lda2)
+ * concatenated along K, W [N, K+K2] (ldw).  bias fp32 [N] (bias_bstride==0) or per-batch rows
+ * [.., N] selected by row / rows_per_batch.  act = VDB_ACT_*; VDB_ACT_GEGLU expects W/bias rows packed
+ * per 256-column tile as 128 value rows then their 128 gate rows and writes N/2 columns
+ * (GEGLU.forward, attention.py:42-44).  out bf16 (out_f32==0) or fp32.  bn: 0 = auto, else force
+ * tile N in {64,128,160,256}.  ksplit: 0 = auto, 1 = off; split-K needs workspace >= ksplit*M*N*4 B. */
+int vdb_gemm_bf16(const void* A, long long M, long long K, long long lda, const void* A2, long long K2,
+                  long long lda2, const void* W, long long N, long long ldw, const float* bias,
+                  long long bias_bstride, long long rows_per_batch, const void* resid, long long ldr, void* out,
+                  long long ldo, int out_f32, int act, float alpha, int bn, int ksplit, void* workspace,
+                  size_t ws_bytes, void* stream);
+
+/* ---- tcgen05 implicit-GEMM 3x3 conv on NHWC — ResBlock convs openaimodel.py:203,229; Downsample
+ *      :150-152; Upsample.conv :105; VAE autokl_modules.py:48-76,93-111 ---------------------------
+ * mode 0: stride 1 pad 1; mode 1: stride 2 pad 1; mode 2: stride 2 with pad (0,1,0,1) (VAE).
+ * Wt [N, 9*C + Cs1 + Cs2], K order (ky,kx,c) then the 1x1 skip_connection columns whose inputs
+ * skip1/skip2 (raw NHWC at output resolution; the two halves of torch.cat([h, hs.pop()]),
+ * vd.py:372) are accumulated into the same TMEM tile (ResBlock.skip_connection, openaimodel.py:240).
+ * bias/resid/out/act as vdb_gemm_bf16 with rows_per_batch = Hout*Wout. C, Cs1, Cs2 multiples of 64. */
+int vdb_conv3x3_bf16(const void* X, int B, int H, int W, int C, int mode, const void* Wt, int N, long long ldw,
+                     const void* skip1, int Cs1, const void* skip2, int Cs2, const float* bias,
+                     long long bias_bstride, const void* resid, long long ldr, void* out, long long ldo,
+                     int out_f32, int act, int bn, int ksplit, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- tcgen05/TMEM flash attention — CrossAttention.forward, attention.py:178-192 -----------------
+ * O = softmax(Q K^T * scale) V per (batch, head), fp32 online softmax, nothing materialised.
+ * Q [B*Nq, ldq] head h at columns q_col0 + h*DK; K [B*Nk, ldk] at k_col0 + h*DK;
+ * Vt [H*DVP, ldv] row h*DVP + c, column b*Nk + j; out [B*Nq, ldo] head h at columns h*d_head.
+ * DK = vdb_attention_dk_pad(d_head), DVP = vdb_attention_dv_pad(d_head); pad columns/rows must be
+ * zero (the projection weights are zero-padded at pack time). causal != 0: CLIP text mask. */
+int vdb_attention_dk_pad(int d_head);
+int vdb_attention_dv_pad(int d_head);
+int vdb_attention_bf16(const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0,
+                       const void* Vt, long long ldv, void* out, long long ldo, int B, int H, int Nq, int Nk,
+                       int d_head, float scale, int causal, void* stream);
+
+/* ---- GroupNorm(32) [+SiLU] [+channel concat] on NHWC — normalization()/Normalize():
+ *      diffusion_utils.py:168-191 (eps 1e-5), attention.py:76-77 & autokl_modules.py:38-39 (1e-6) ----
+ * y[B,HW,C1+C2] = act(GN32(cat(x1,x2))) ; partial: scratch of B*vdb_groupnorm_nsplit(B,HW)*64 floats. */
+int vdb_groupnorm_nsplit(int B, int HW);
+int vdb_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int B, int HW, int groups, const float* gamma,
+                       const float* beta, float eps, int act, float* partial, void* y, void* stream);
+
+/* ---- LayerNorm over the last dim — BasicTransformerBlock.norm1/2/3 attention.py:206-208 ---------- */
+int vdb_layernorm(const void* x, long long rows, int C, const float* gamma, const float* beta, float eps, void* y,
+                  void* stream);
+
+/* ---- nearest 2x upsample NHWC — Upsample.forward openaimodel.py:114, autokl_modules.py:54 -------- */
+int vdb_upsample2x_nhwc(const void* x, int B, int H, int W, int C, void* y, void* stream);
+
+/* ---- im2col for tiny-Cin 3x3 convs (latent 4ch / RGB 3ch inputs): fp32 NHWC -> bf16 [B*H*W, Kpad]
+ *      (x*in_scale + in_shift applied first: AutoencoderKL.encode's x*2-1, autokl.py:34) ----------- */
+int vdb_im2col3x3_small(const float* x, int B, int H, int W, int Cin, int Kpad, float in_scale, float in_shift,
+                        void* y, void* stream);
+
+/* ---- fp32 NCHW <-> NHWC permute with y = x*mul + add [clamped to [0,1]] (autokl.py:47) ------------ */
+int vdb_permute_f32(const float* x, int B, int C, long long HW, int to_nhwc, float mul, float add, int clamp01,
+                    float* y, void* stream);
+int vdb_cast_f32_bf16(const float* x, void* y, long long n, void* stream);
+int vdb_cast_bf16_f32(const void* x, float* y, long long n, void* stream);
+
+/* ---- timestep_embedding [cos|sin] — diffusion_utils.py:131-151 ---------------------------------
+ * ts: device int64 [B], or a table indexed by *step_idx (broadcast to all B rows) when step_idx != NULL.
+ * neg_log_period = (float)(-ln(max_period)). */
+int vdb_timestep_embedding(const long long* ts, const int* step_idx, int B, int dim, float neg_log_period,
+                           float* out, void* stream);
+
+/* ---- skinny linear (M <= 16) — time_embed openaimodel.py:2629-2633, ResBlock.emb_layers :217-223 --
+ * out[M,N] = act_out(act_in(x)[M,K] @ W[N,K]^T + bias); x/out fp32, W bf16; act 0 none, 1 SiLU. */
+int vdb_linear_small(const float* x, int M, int K, const void* Wt, int N, const float* bias, int act_in, int act_out,
+                     float* out, void* stream);
+
+/* ---- row softmax (VAE AttnBlock, autokl_modules.py:186-188) ------------------------------------- */
+int vdb_softmax_rows(const void* x, long long rows, int n, long long ld, float scale, void* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDB200_H_ */

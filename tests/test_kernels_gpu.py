@@ -1,0 +1,319 @@
+"""Per-kernel numerics: every vdb200 kernel against a plain torch fp32 restatement of the same op
+(the reference's own arithmetic for that call site), on bf16-rounded inputs.
+
+Tolerances: bf16 tensor-core kernels  max|err| <= 2e-2 * max|ref| and cosine >= 0.999;
+fp32 elementwise kernels bit-exact or <= 1e-6 relative as stated per test.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from vdb200 import ops
+    return ops
+
+
+def rnd(*shape, scale=1.0, seed=0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+def assert_close(out, ref, tol=2e-2, cos_min=0.999, what=""):
+    out = out.float().flatten()
+    ref = ref.float().flatten()
+    assert torch.isfinite(out).all(), f"{what}: non-finite output"
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-12
+    cos = F.cosine_similarity(out, ref, dim=0).item()
+    assert err <= tol * scale and cos >= cos_min, f"{what}: max err {err:.4g} vs scale {scale:.4g}, cos {cos:.6f}"
+
+
+# ----------------------------------------------------------------------------------------------
+def test_ddim_cfg_step_bit_exact():
+    ops = _ops()
+    n = (4, 64, 64, 4)
+    eu, ec, x = (rnd(*n, seed=s, dtype=torch.float32) for s in (1, 2, 3))
+    a_t, a_prev, sigma = 0.5312, 0.6123, 0.0
+    coef = torch.tensor([[a_t, a_prev, sigma, math.sqrt(1 - a_t)]], dtype=torch.float32, device=DEV)
+    p0 = torch.empty_like(x)
+    xp, _ = ops.ddim_cfg_step(eu, ec, x, coef, 7.5, pred_x0=p0)
+    # reference op order of ddim.py:150,165-170 (separate fp32 ATen ops)
+    e = eu + 7.5 * (ec - eu)
+    c = coef[0]
+    px0 = (x - c[3] * e) / c[0].sqrt()
+    d = (1.0 - c[1] - c[2] ** 2).sqrt() * e
+    ref = c[1].sqrt() * px0 + d + c[2] * torch.zeros_like(x) * 1.0
+    assert torch.equal(p0, px0)
+    assert torch.equal(xp, ref)
+
+
+def test_ddim_cfg_step_table_and_noise():
+    ops = _ops()
+    x, ec, nz = (rnd(2, 33, seed=s, dtype=torch.float32) for s in (1, 2, 3))  # n = 66: tail path
+    coef = torch.tensor([[0.9, 0.95, 0.0, 0.3], [0.4, 0.5, 0.2, 0.77]], dtype=torch.float32, device=DEV)
+    idx = torch.tensor([1], dtype=torch.int32, device=DEV)
+    xp, _ = ops.ddim_cfg_step(None, ec, x, coef, 1.0, noise=nz, temperature=0.7, step_idx=idx)
+    c = coef[1]
+    px0 = (x - c[3] * ec) / c[0].sqrt()
+    ref = c[1].sqrt() * px0 + (1.0 - c[1] - c[2] ** 2).sqrt() * ec + c[2] * nz * 0.7
+    assert torch.equal(xp, ref)
+    ops.add_int(idx, -1)
+    assert idx.item() == 0
+
+
+GEMM_CASES = [
+    # M, N, K, bias, resid, act, bn, ksplit, f32out
+    (128, 64, 64, False, False, 0, 0, 1, False),
+    (256, 160, 320, True, False, 0, 0, 1, False),
+    (1000, 320, 320, True, True, 0, 0, 1, False),
+    (4096, 1280, 640, True, True, 0, 0, 1, False),
+    (77, 768, 768, True, False, 3, 0, 1, False),
+    (300, 256, 128, True, False, 1, 128, 1, False),
+    (512, 1280, 2880, True, True, 0, 0, 0, False),     # auto split-K
+    (512, 1280, 11520, True, True, 0, 0, 8, False),    # forced split-K
+    (640, 200, 192, True, False, 2, 0, 1, True),       # fp32 out, N tail
+    (8192, 320, 1280, False, True, 0, 160, 1, False),
+    (20000, 640, 640, True, False, 0, 0, 1, False),    # many tiles per CTA (persistent loop, TMEM double buffer)
+]
+
+
+@pytest.mark.parametrize("M,N,K,bias,resid,act,bn,ksplit,f32", GEMM_CASES)
+def test_gemm(M, N, K, bias, resid, act, bn, ksplit, f32):
+    ops = _ops()
+    a = rnd(M, K, seed=1)
+    w = rnd(N, K, seed=2, scale=K ** -0.5)
+    b = rnd(N, seed=3, dtype=torch.float32) if bias else None
+    r = rnd(M, N, seed=4) if resid else None
+    out = ops.gemm(a, w, bias=b, resid=r, act=act, bn=bn, ksplit=ksplit,
+                   out_dtype=torch.float32 if f32 else torch.bfloat16)
+    ref = a.float() @ w.float().t()
+    if bias:
+        ref = ref + b
+    ref = {0: lambda t: t, 1: F.silu, 2: F.gelu, 3: lambda t: t * torch.sigmoid(1.702 * t)}[act](ref)
+    if resid:
+        ref = ref + r.float()
+    assert_close(out, ref, what=f"gemm {M}x{N}x{K}")
+
+
+def test_gemm_two_source_and_batched_bias():
+    ops = _ops()
+    M, K1, K2, N, B = 512, 640, 320, 320, 4
+    a1, a2 = rnd(M, K1, seed=1), rnd(M, K2, seed=2)
+    w = rnd(N, K1 + K2, seed=3, scale=(K1 + K2) ** -0.5)
+    bias = rnd(B, N, seed=4, dtype=torch.float32)
+    out = ops.gemm(a1, w, a2=a2, bias=bias, bias_bstride=N, rows_per_batch=M // B)
+    ref = torch.cat([a1, a2], 1).float() @ w.float().t() + bias.repeat_interleave(M // B, 0)
+    assert_close(out, ref, what="gemm two-source")
+
+
+def pack_geglu(w, b, bn=256):
+    """rows [0,4C) value, [4C,8C) gate -> per 256-col tile: 128 value rows then their 128 gate rows"""
+    n2 = w.shape[0] // 2
+    half = bn // 2
+    idx = []
+    for t in range(n2 // half):
+        idx += list(range(t * half, (t + 1) * half)) + list(range(n2 + t * half, n2 + (t + 1) * half))
+    idx = torch.tensor(idx, device=w.device)
+    return w[idx].contiguous(), (b[idx].contiguous() if b is not None else None)
+
+
+@pytest.mark.parametrize("M,C", [(256, 320), (1024, 640)])
+def test_gemm_geglu(M, C):
+    ops = _ops()
+    x = rnd(M, C, seed=1)
+    w = rnd(8 * C, C, seed=2, scale=C ** -0.5)
+    b = rnd(8 * C, seed=3, dtype=torch.float32)
+    wp, bp = pack_geglu(w, b)
+    out = ops.gemm(x, wp, bias=bp, act=ops.ACT_GEGLU)
+    h = x.float() @ w.float().t() + b
+    val, gate = h.chunk(2, dim=-1)
+    ref = val * F.gelu(gate)
+    assert out.shape == (M, 4 * C)
+    assert_close(out, ref, what="geglu")
+
+
+def pack_conv_w(w, skip_ws=()):
+    """[N,C,3,3] -> [N, (ky,kx,c)] (+ 1x1 skip columns)"""
+    cols = [w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)]
+    cols += [s.reshape(s.shape[0], -1) for s in skip_ws]
+    return torch.cat(cols, 1).contiguous()
+
+
+CONV_CASES = [
+    # B, H, W, C, N, mode
+    (2, 64, 64, 64, 128, 0),
+    (2, 16, 16, 128, 160, 0),
+    (3, 8, 8, 64, 64, 0),
+    (1, 32, 32, 320, 320, 0),
+    (2, 32, 32, 64, 64, 1),
+    (3, 16, 16, 128, 128, 1),
+    (2, 32, 32, 64, 64, 2),
+    (1, 256, 256, 64, 64, 0),
+    (2, 8, 8, 1280, 1280, 0),   # split-K regime
+]
+
+
+@pytest.mark.parametrize("B,H,W,C,N,mode", CONV_CASES)
+def test_conv3x3(B, H, W, C, N, mode):
+    ops = _ops()
+    x = rnd(B, H, W, C, seed=1)
+    w = rnd(N, C, 3, 3, seed=2, scale=(9 * C) ** -0.5)
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    out = ops.conv3x3(x, pack_conv_w(w), bias=bias, mode=mode)
+    xin = x.float().permute(0, 3, 1, 2)
+    if mode == 0:
+        ref = F.conv2d(xin, w.float(), bias, padding=1)
+    elif mode == 1:
+        ref = F.conv2d(xin, w.float(), bias, stride=2, padding=1)
+    else:
+        ref = F.conv2d(F.pad(xin, (0, 1, 0, 1)), w.float(), bias, stride=2)
+    assert_close(out, ref.permute(0, 2, 3, 1), what=f"conv {B}x{H}x{W}x{C}->{N} mode {mode}")
+
+
+def test_conv3x3_resblock_tail():
+    """conv2 of a channel-changing ResBlock: 3x3 conv + 1x1 skip over cat(h, skip) + per-batch bias + residual"""
+    ops = _ops()
+    B, H, W, C, N, C1, C2 = 2, 16, 16, 128, 128, 128, 64
+    a = rnd(B, H, W, C, seed=1)
+    s1, s2 = rnd(B, H, W, C1, seed=2), rnd(B, H, W, C2, seed=3)
+    w = rnd(N, C, 3, 3, seed=4, scale=(9 * C) ** -0.5)
+    ws = rnd(N, C1 + C2, 1, 1, seed=5, scale=(C1 + C2) ** -0.5)
+    bias = rnd(B, N, seed=6, dtype=torch.float32)
+    resid = rnd(B, H, W, N, seed=7)
+    out = ops.conv3x3(a, pack_conv_w(w, [ws]), bias=bias, bias_bstride=N, skip1=s1, skip2=s2, resid=resid)
+    ref = F.conv2d(a.float().permute(0, 3, 1, 2), w.float(), padding=1)
+    ref = ref + F.conv2d(torch.cat([s1, s2], -1).float().permute(0, 3, 1, 2), ws.float())
+    ref = ref + bias[:, :, None, None] + resid.float().permute(0, 3, 1, 2)
+    assert_close(out, ref.permute(0, 2, 3, 1), what="conv resblock tail")
+
+
+def build_attention_inputs(ops, q, k, v):
+    """q [B,H,Nq,d], k/v [B,H,Nk,d] fp32 -> padded kernel layouts"""
+    B, H, Nq, d = q.shape
+    Nk = k.shape[2]
+    dk, dv = ops.attention_pads(d)
+    Q = torch.zeros(B * Nq, H * dk, dtype=torch.bfloat16, device=DEV)
+    K = torch.zeros(B * Nk, H * dk, dtype=torch.bfloat16, device=DEV)
+    ldv = (B * Nk + 7) // 8 * 8
+    Vt = torch.zeros(H * dv, ldv, dtype=torch.bfloat16, device=DEV)
+    Q.view(B, Nq, H, dk)[..., :d] = q.permute(0, 2, 1, 3).to(torch.bfloat16)
+    K.view(B, Nk, H, dk)[..., :d] = k.permute(0, 2, 1, 3).to(torch.bfloat16)
+    Vt.view(H, dv, ldv)[:, :d, :B * Nk] = v.permute(1, 3, 0, 2).reshape(H, d, B * Nk).to(torch.bfloat16)
+    return Q, K, Vt
+
+
+ATT_CASES = [
+    # B, H, Nq, Nk, d, causal
+    (1, 2, 128, 128, 40, False),
+    (2, 8, 256, 256, 40, False),
+    (1, 2, 4096, 4096, 40, False),
+    (2, 8, 1024, 77, 80, False),
+    (2, 8, 64, 64, 160, False),
+    (2, 8, 256, 257, 160, False),
+    (2, 8, 1024, 1028, 80, False),
+    (2, 12, 77, 77, 64, True),
+    (2, 16, 257, 257, 64, False),
+    (1, 8, 4096, 77, 40, False),
+]
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk,d,causal", ATT_CASES)
+def test_attention(B, H, Nq, Nk, d, causal):
+    ops = _ops()
+    q, k, v = (rnd(B, H, n, d, seed=s, dtype=torch.float32) for s, n in ((1, Nq), (2, Nk), (3, Nk)))
+    q = q * 2.0  # make the softmax peaky enough to exercise the rescale path
+    Q, K, Vt = build_attention_inputs(ops, q, k, v)
+    out = torch.empty(B * Nq, H * d, dtype=torch.bfloat16, device=DEV)
+    ops.attention(Q, K, Vt, out, B, H, Nq, Nk, d, causal=causal)
+    qb, kb, vb = (t.to(torch.bfloat16).float() for t in (q, k, v))
+    sim = torch.einsum("bhid,bhjd->bhij", qb, kb) * d ** -0.5
+    if causal:
+        sim = sim + torch.full((Nq, Nk), float("-inf"), device=DEV).triu(1)
+    ref = torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), vb).permute(0, 2, 1, 3).reshape(B * Nq, H * d)
+    assert_close(out, ref, what=f"attention B{B} H{H} {Nq}x{Nk} d{d}")
+
+
+@pytest.mark.parametrize("B,HW,C1,C2,act,eps", [(2, 4096, 320, 0, 1, 1e-5), (2, 1024, 640, 320, 1, 1e-5),
+                                              (3, 64, 1280, 1280, 1, 1e-5), (2, 256, 1280, 640, 0, 1e-6),
+                                              (1, 65536, 128, 0, 1, 1e-6), (2, 4096, 512, 0, 0, 1e-6)])
+def test_groupnorm(B, HW, C1, C2, act, eps):
+    ops = _ops()
+    x1 = rnd(B, HW, C1, seed=1) + 0.5
+    x2 = rnd(B, HW, C2, seed=2, scale=2.0) if C2 else None
+    C = C1 + C2
+    g, b = rnd(C, seed=3, dtype=torch.float32), rnd(C, seed=4, dtype=torch.float32)
+    out = ops.groupnorm(x1, g, b, eps, act=act, x2=x2)
+    x = torch.cat([x1, x2], -1) if C2 else x1
+    ref = F.group_norm(x.float().permute(0, 2, 1), 32, g, b, eps)
+    if act:
+        ref = F.silu(ref)
+    assert_close(out, ref.permute(0, 2, 1), tol=1.5e-2, what="groupnorm")
+    out2 = ops.groupnorm(x1, g, b, eps, act=act, x2=x2)
+    assert torch.equal(out, out2), "groupnorm must be run-to-run deterministic"
+
+
+@pytest.mark.parametrize("rows,C", [(4096, 320), (1000, 640), (512, 1280), (154, 768), (514, 1024)])
+def test_layernorm(rows, C):
+    ops = _ops()
+    x = rnd(rows, C, seed=1) * 3 + 1
+    g, b = rnd(C, seed=3, dtype=torch.float32), rnd(C, seed=4, dtype=torch.float32)
+    out = ops.layernorm(x, g, b, 1e-5)
+    ref = F.layer_norm(x.float(), (C,), g, b, 1e-5)
+    assert_close(out, ref, tol=1.5e-2, what="layernorm")
+
+
+def test_upsample_im2col_permute_cast():
+    ops = _ops()
+    x = rnd(2, 8, 8, 64, seed=1)
+    up = ops.upsample2x(x)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(up.float(), ref)
+    z = rnd(2, 4, 16, 16, seed=2, dtype=torch.float32)
+    zh = ops.nchw_to_nhwc(z)
+    assert torch.equal(zh, z.permute(0, 2, 3, 1).contiguous())
+    back = ops.nhwc_to_nchw(zh, mul=0.5, add=0.5, clamp01=True)
+    assert torch.equal(back, torch.clamp(z * 0.5 + 0.5, 0, 1))
+    col = ops.im2col3x3_small(zh, kpad=64)
+    unf = F.unfold(z, 3, padding=1)  # [B, C*9, L] with (c, ky, kx) order
+    unf = unf.view(2, 4, 9, 256).permute(0, 3, 2, 1).reshape(2 * 256, 36)  # -> (tap, c)
+    assert torch.equal(col[:, :36].float(), unf.to(torch.bfloat16).float())
+    assert (col[:, 36:] == 0).all()
+    assert torch.equal(ops.to_f32(ops.to_bf16(z)), z.to(torch.bfloat16).float())
+
+
+def test_timestep_embedding_and_linear_small():
+    ops = _ops()
+    ts = torch.tensor([1, 21, 501, 981, 999, 0, 7, 333], dtype=torch.int64, device=DEV)
+    emb = ops.timestep_embedding(ts, 320)
+    half = 160
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half).to(DEV)
+    args = ts[:, None].float() * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], -1)
+    assert (emb - ref).abs().max().item() <= 2e-5   # fp32 sin/cos of arguments up to 1e3
+    table = torch.tensor([981, 961, 941], dtype=torch.int64, device=DEV)
+    idx = torch.tensor([1], dtype=torch.int32, device=DEV)
+    emb2 = ops.timestep_embedding(table, 320, step_idx=idx, batch=4)
+    assert torch.equal(emb2, ops.timestep_embedding(torch.full((4,), 961, dtype=torch.int64, device=DEV), 320))
+    w = rnd(1280, 320, seed=5, scale=320 ** -0.5)
+    b = rnd(1280, seed=6, dtype=torch.float32)
+    h = ops.linear_small(emb, w, b, act_out=ops.ACT_SILU)
+    refh = F.silu(emb @ w.float().t() + b)
+    assert_close(h, refh, tol=1e-4, cos_min=0.99999, what="linear_small")
+    w2 = rnd(5000, 1280, seed=7, scale=1280 ** -0.5)
+    o = ops.linear_small(h, w2, None, act_in=ops.ACT_SILU)
+    assert_close(o, F.silu(h) @ w2.float().t(), tol=1e-4, cos_min=0.99999, what="linear_small silu-in")
+
+
+def test_softmax_rows():
+    ops = _ops()
+    x = rnd(300, 4096, seed=1, scale=4.0)
+    out = ops.softmax_rows(x, scale=0.044)
+    ref = (x.float() * 0.044).softmax(-1)
+    assert_close(out, ref, tol=1e-2, what="softmax_rows")

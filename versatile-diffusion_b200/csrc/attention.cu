@@ -1,0 +1,356 @@
+// vdb200 — flash-style scaled-dot-product attention on tcgen05/TMEM (sm_100a).
+//
+// Replaces the reference's materialised  sim = q k^T * d^-1/2 ; softmax ; attn v  of
+// CrossAttention.forward (lib/model_zoo/attention.py:178-192) — self-attention N = M in
+// {4096,1024,256,64}, d_head in {40,80,160}; cross-attention M = 77 (text) / 257 (image) /
+// n*257 (multi-image) — and the CLIP encoder attention (d_head 64, optional causal mask).
+//
+// One CTA = one (q-tile of 128 rows, head, batch).  192 threads:
+//   warp 0    : TMA producer (Q once; K and V^T tiles through two independent 2-stage rings)
+//   warp 1    : MMA issuer   (S_j = Q K_j^T into double-buffered TMEM; O += P_j V_j into TMEM)
+//   warps 2-5 : online softmax in fp32 registers (one query row per thread), P_j -> bf16 ->
+//               128B-swizzled shared memory (double buffered), lazy O rescale in TMEM, final
+//               normalise + store.
+// Operand layouts (all K-major, 128B swizzle, written by the projection GEMMs):
+//   Q  [B*Nq, ldq]  head h at columns q_col0 + h*DK .. (+DK, zero padded beyond d_head)
+//   K  [B*Nk, ldk]  head h at columns k_col0 + h*DK ..
+//   Vt [H*DVP, >=B*Nk]  row h*DVP + c = channel c of head h (zero rows beyond d_head), column b*Nk + j
+//   O  [B*Nq, ldo]  head h at columns h*dv .. (+dv)   (dense, feeds to_out)
+#include "common.cuh"
+#include "host_util.h"
+
+namespace vdb {
+
+constexpr int kAttThreads = 192;
+constexpr int kBQ = 128;   // query rows per CTA
+constexpr int kBKV = 128;  // kv columns per tile
+constexpr float kRescaleThreshold = 8.0f;  // in log2 units (P stays <= 2^8)
+
+struct alignas(64) AttnParams {
+  CUtensorMap tmQ;   // 2D (cols, rows) box (64, 128)
+  CUtensorMap tmK;   // 2D (cols, rows) box (64, 128)
+  CUtensorMap tmV;   // 2D (kv, H*DVP) box (64, DVP)
+  int Nq, Nk;        // per-batch query / key counts
+  int q_col0, k_col0;
+  int dv;            // valid head channels (<= DVP)
+  int causal;
+  float scale_log2;  // d^-1/2 * log2(e)
+  __nv_bfloat16* out;
+  long long ldo;
+};
+
+template <int DK, int DVP, int KV_STAGES>
+__global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
+  constexpr int KA = DK / 64;                      // 64-wide K atoms of the QK^T reduction
+  constexpr uint32_t kQBytes = KA * kBQ * 128;     // Q tile
+  constexpr uint32_t kKBytes = KA * kBKV * 128;    // one K stage
+  constexpr uint32_t kVAtom = DVP * 128;           // one 64-kv atom of V^T
+  constexpr uint32_t kVBytes = 2 * kVAtom;         // one V stage (128 kv)
+  constexpr uint32_t kPBytes = 2 * kBQ * 128;      // one P buffer (128 x 128 bf16)
+  static_assert(kVAtom % 1024 == 0, "V atom must keep 1024B alignment");
+  static_assert(DVP % 16 == 0 && DVP <= 256, "invalid UMMA N for PV");
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kQBytes;
+  uint8_t* sV = sK + KV_STAGES * kKBytes;
+  uint8_t* sP = sV + KV_STAGES * kVBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // [2]
+  uint64_t* k_empty = bars + 3;       // [2]
+  uint64_t* v_full = bars + 5;        // [2]
+  uint64_t* v_empty = bars + 7;       // [2]
+  uint64_t* s_full = bars + 9;        // [2]
+  uint64_t* p_full = bars + 11;       // 1 (count 4: one arrive per softmax warp)
+  uint64_t* pv_done = bars + 12;      // 1
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kBQ;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+
+  int ntiles = (p.Nk + kBKV - 1) / kBKV;
+  if (p.causal) ntiles = min(ntiles, (q0 + kBQ + kBKV - 1) / kBKV);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+    }
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t tmem_S = tmem_base;        // 2 x 128 columns
+  const uint32_t tmem_O = tmem_base + 256;  // DVP columns
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // Q tile
+      mbar_arrive_expect_tx(q_full, kQBytes);
+      for (int a = 0; a < KA; ++a)
+        tma_load_2d(sQ + a * kBQ * 128, &p.tmQ, q_full, p.q_col0 + head * DK + a * 64, b * p.Nq + q0);
+      // K / V rings
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], kKBytes);
+        for (int a = 0; a < KA; ++a)
+          tma_load_2d(sK + st * kKBytes + a * kBKV * 128, &p.tmK, &k_full[st], p.k_col0 + head * DK + a * 64,
+                      b * p.Nk + j * kBKV);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], kVBytes);
+        for (int a = 0; a < 2; ++a)
+          tma_load_2d(sV + st * kVBytes + a * kVAtom, &p.tmV, &v_full[st], b * p.Nk + j * kBKV + a * 64, head * DVP);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(kBQ, kBKV);
+      constexpr uint32_t idesc_o = make_idesc_bf16(kBQ, DVP);
+      auto issue_S = [&](int j) {
+        const int st = j % KV_STAGES;
+        mbar_wait(&k_full[st], (j / KV_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t d = tmem_S + (j & 1) * 128;
+#pragma unroll
+        for (int a = 0; a < KA; ++a) {
+          const uint64_t qd = make_desc_sw128(smem_u32(sQ + a * kBQ * 128));
+          const uint64_t kd = make_desc_sw128(smem_u32(sK + st * kKBytes + a * kBKV * 128));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(d, qd + 2 * k, kd + 2 * k, idesc_s, (a > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_S(0);
+      // with a single KV stage, S_{j+1} can only be issued once K_{j+1} has landed, which needs S_j retired
+      if (ntiles > 1) issue_S(1);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % KV_STAGES;
+        mbar_wait(p_full, j & 1);
+        mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
+        tc_fence_after();
+        const uint8_t* pb = sP + (j & 1) * kPBytes;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const uint64_t pd = make_desc_sw128(smem_u32(pb + a * kBQ * 128));
+          const uint64_t vd = make_desc_sw128(smem_u32(sV + st * kVBytes + a * kVAtom));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(tmem_O, pd + 2 * k, vd + 2 * k, idesc_o, (j > 0 || a > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&v_empty[st]);
+        umma_commit(pv_done);
+        if (j + 2 < ntiles) issue_S(j + 2);
+      }
+    }
+  } else {
+    // ------------------------------ softmax / correction / epilogue ------------------------------
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;           // query row inside the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const int q_idx = q0 + r;
+    float m_ref = -INFINITY;  // reference max (raw score units)
+    float l_sum = 0.f;
+    for (int j = 0; j < ntiles; ++j) {
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t ts = tmem_S + (j & 1) * 128 + lane_off;
+      const int kv0 = j * kBKV;
+      const bool need_mask = (kv0 + kBKV > p.Nk) || p.causal;
+      const int kv_lim = p.causal ? min(p.Nk, q_idx + 1) : p.Nk;  // valid kv indices are < kv_lim
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(ts + c * 32, v);
+        tmem_wait_ld();
+        if (need_mask) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (kv0 + c * 32 + i < kv_lim) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      // lazy rescale decision (warp-uniform because tcgen05.ld/st are warp collectives)
+      const float m_new = fmaxf(m_ref, mx);
+      bool rescale = false;
+      float factor = 1.f;
+      if (j == 0) {
+        m_ref = m_new;
+      } else {
+        const bool want = (m_new - m_ref) * p.scale_log2 > kRescaleThreshold;
+        rescale = __any_sync(0xffffffffu, want);
+        if (rescale) {
+          factor = exp2f((m_ref - m_new) * p.scale_log2);  // m_ref finite for j > 0
+          m_ref = m_new;
+          l_sum *= factor;
+        }
+      }
+      const float m_scaled = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;
+      // pass 2: P = exp2(s*scale - m), row sum, bf16 -> swizzled smem
+      uint8_t* prow = sP + (j & 1) * kPBytes + r * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(ts + c * 32, v);
+        tmem_wait_ld();
+        float pf[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float e = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_scaled));
+          if (need_mask && !(kv0 + c * 32 + i < kv_lim)) e = 0.f;
+          pf[i] = e;
+          l_sum += e;
+        }
+        uint8_t* patom = prow + (c >> 1) * (kBQ * 128);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = (c & 1) * 4 + q;  // 16-byte chunk inside the 128-byte row
+          const uint4 pk = make_uint4(pack_bf16x2(pf[q * 8], pf[q * 8 + 1]), pack_bf16x2(pf[q * 8 + 2], pf[q * 8 + 3]),
+                                      pack_bf16x2(pf[q * 8 + 4], pf[q * 8 + 5]), pack_bf16x2(pf[q * 8 + 6], pf[q * 8 + 7]));
+          *reinterpret_cast<uint4*>(patom + ((chunk ^ (r & 7)) << 4)) = pk;
+        }
+      }
+      // O must be settled (PV_{j-1} retired) before it is rescaled / accumulated into again
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+        if (rescale) {
+#pragma unroll 1
+          for (int c = 0; c < DVP / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld16(tmem_O + lane_off + c * 16, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+            tmem_st16(tmem_O + lane_off + c * 16, o);
+          }
+          tmem_wait_st();
+        }
+      }
+      fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the MMA's async-proxy reads
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // epilogue: O / l -> bf16
+    mbar_wait(pv_done, (ntiles - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l_sum;
+    const bool row_ok = q_idx < p.Nq;
+    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.Nq + q_idx) * p.ldo + head * p.dv;
+#pragma unroll 1
+    for (int c = 0; c < DVP / 16; ++c) {
+      uint32_t o[16];
+      tmem_ld16(tmem_O + lane_off + c * 16, o);
+      tmem_wait_ld();
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int col = c * 16 + q * 8;
+          if (col + 8 <= p.dv) {
+            const uint4 pk = make_uint4(
+                pack_bf16x2(__uint_as_float(o[q * 8]) * inv_l, __uint_as_float(o[q * 8 + 1]) * inv_l),
+                pack_bf16x2(__uint_as_float(o[q * 8 + 2]) * inv_l, __uint_as_float(o[q * 8 + 3]) * inv_l),
+                pack_bf16x2(__uint_as_float(o[q * 8 + 4]) * inv_l, __uint_as_float(o[q * 8 + 5]) * inv_l),
+                pack_bf16x2(__uint_as_float(o[q * 8 + 6]) * inv_l, __uint_as_float(o[q * 8 + 7]) * inv_l));
+            *reinterpret_cast<uint4*>(orow + col) = pk;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+template <int DK, int DVP, int KV_STAGES>
+static int launch_attention(const AttnParams& p, int B, int H, cudaStream_t stream) {
+  constexpr int KA = DK / 64;
+  constexpr size_t smem = KA * kBQ * 128 + KV_STAGES * (KA * kBKV * 128 + 2 * DVP * 128) + 2 * (2 * kBQ * 128) +
+                          13 * 8 + 16 + 1024;
+  static_assert(smem <= 227 * 1024, "attention smem budget");
+  static bool configured = false;
+  if (!configured) {
+    VDB_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<DK, DVP, KV_STAGES>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = true;
+  }
+  dim3 grid((p.Nq + kBQ - 1) / kBQ, H, B);
+  attention_kernel<DK, DVP, KV_STAGES><<<grid, kAttThreads, smem, stream>>>(p);
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+}  // namespace vdb
+
+using namespace vdb;
+
+extern "C" {
+
+// Padded head sizes the projection GEMMs must produce for a given d_head (see include/vdb200.h).
+int vdb_attention_dk_pad(int d_head) { return d_head <= 64 ? 64 : (d_head <= 128 ? 128 : (d_head <= 192 ? 192 : -1)); }
+int vdb_attention_dv_pad(int d_head) {
+  if (d_head <= 48) return 48;
+  if (d_head <= 64) return 64;
+  if (d_head <= 80) return 80;
+  if (d_head <= 160) return 160;
+  return -1;
+}
+
+int vdb_attention_bf16(const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0,
+                       const void* Vt, long long ldv, void* out, long long ldo, int B, int H, int Nq, int Nk,
+                       int d_head, float scale, int causal, void* stream) {
+  if (!Q || !K || !Vt || !out || B <= 0 || H <= 0 || Nq <= 0 || Nk <= 0)
+    return set_error(VDB_ERR_INVALID, "attention: null/empty argument");
+  const int DK = vdb_attention_dk_pad(d_head), DVP = vdb_attention_dv_pad(d_head);
+  if (DK < 0 || DVP < 0) return set_error(VDB_ERR_UNSUPPORTED, "attention: d_head %d not supported (<= 160)", d_head);
+  if ((d_head % 8) || (ldo % 8) || (ldq % 8) || (ldk % 8) || (ldv % 8))
+    return set_error(VDB_ERR_INVALID, "attention: d_head and leading dims must be multiples of 8");
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = make_tmap_2d(&p.tmQ, Q, static_cast<uint64_t>(ldq), static_cast<uint64_t>(B) * Nq, ldq * 2, 64, kBQ);
+  if (rc) return rc;
+  rc = make_tmap_2d(&p.tmK, K, static_cast<uint64_t>(ldk), static_cast<uint64_t>(B) * Nk, ldk * 2, 64, kBKV);
+  if (rc) return rc;
+  rc = make_tmap_2d(&p.tmV, Vt, static_cast<uint64_t>(B) * Nk, static_cast<uint64_t>(H) * DVP, ldv * 2, 64, DVP);
+  if (rc) return rc;
+  p.Nq = Nq; p.Nk = Nk; p.q_col0 = q_col0; p.k_col0 = k_col0; p.dv = d_head; p.causal = causal;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (DK == 64 && DVP == 48) return launch_attention<64, 48, 2>(p, B, H, st);
+  if (DK == 64 && DVP == 64) return launch_attention<64, 64, 2>(p, B, H, st);
+  if (DK == 128 && DVP == 80) return launch_attention<128, 80, 2>(p, B, H, st);
+  if (DK == 192 && DVP == 160) return launch_attention<192, 160, 1>(p, B, H, st);
+  return set_error(VDB_ERR_UNSUPPORTED, "attention: no kernel for d_head %d", d_head);
+}
+
+}  // extern "C"

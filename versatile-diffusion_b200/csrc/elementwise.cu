@@ -1,0 +1,618 @@
+// vdb200 — HBM-bound kernels of the sampling path (sm_100a): DDIM/CFG update, GroupNorm statistics
+// and apply(+SiLU, +channel concat), LayerNorm, nearest 2x upsample, small-Cin im2col, skinny
+// (M <= 16) linears for the timestep-embedding MLP, sinusoidal timestep embedding, row softmax,
+// layout permutes. All vectorised to 16-byte accesses on NHWC / token-major bf16 tensors.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace vdb {
+
+// ---------------------------------------------------------------------------------------------
+// K4: classifier-free-guidance mix + DDIM x_{t-1} update        (reference ddim.py:144-171)
+//   e      = e_u + s * (e_c - e_u)
+//   pred_x0= (x - sqrt(1-a_t) * e) / sqrt(a_t)
+//   dir    = sqrt(1 - a_prev - sigma^2) * e
+//   x_prev = sqrt(a_prev) * pred_x0 + dir + sigma * noise * temperature
+// Explicit _rn intrinsics keep the op order / rounding of the reference's separate ATen ops
+// (no FMA contraction), so fp32 results are bit-identical to the CPU oracle.
+// coef = {a_t, a_prev, sigma_t, sqrt_one_minus_at}; if step_idx != null, row *step_idx of coef.
+// ---------------------------------------------------------------------------------------------
+__global__ void ddim_cfg_step_kernel(const float* __restrict__ e_uncond, const float* __restrict__ e_cond,
+                                     const float* __restrict__ x, const float* __restrict__ noise,
+                                     const float* __restrict__ coef, const int* __restrict__ step_idx,
+                                     float scale, float temperature, float* __restrict__ x_prev,
+                                     float* __restrict__ pred_x0, long long n) {
+  const float* c = coef + (step_idx ? 4 * (*step_idx) : 0);
+  const float a_t = c[0], a_prev = c[1], sigma = c[2], s1m = c[3];
+  const float sqrt_at = __fsqrt_rn(a_t);
+  const float sqrt_aprev = __fsqrt_rn(a_prev);
+  const float dir_c = __fsqrt_rn(__fsub_rn(__fsub_rn(1.0f, a_prev), __fmul_rn(sigma, sigma)));
+  for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
+    float ec[4], eu[4], xv[4], nz[4] = {0.f, 0.f, 0.f, 0.f}, xp[4], p0[4];
+    if (i + 3 < n) {
+      *reinterpret_cast<float4*>(ec) = __ldg(reinterpret_cast<const float4*>(e_cond + i));
+      if (e_uncond) *reinterpret_cast<float4*>(eu) = __ldg(reinterpret_cast<const float4*>(e_uncond + i));
+      *reinterpret_cast<float4*>(xv) = __ldg(reinterpret_cast<const float4*>(x + i));
+      if (noise) *reinterpret_cast<float4*>(nz) = __ldg(reinterpret_cast<const float4*>(noise + i));
+    } else {
+      for (int q = 0; q < 4; ++q)
+        if (i + q < n) {
+          ec[q] = e_cond[i + q];
+          if (e_uncond) eu[q] = e_uncond[i + q];
+          xv[q] = x[i + q];
+          if (noise) nz[q] = noise[i + q];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float e = ec[q];
+      if (e_uncond) e = __fadd_rn(eu[q], __fmul_rn(scale, __fsub_rn(ec[q], eu[q])));
+      const float px0 = __fdiv_rn(__fsub_rn(xv[q], __fmul_rn(s1m, e)), sqrt_at);
+      const float dir = __fmul_rn(dir_c, e);
+      const float nn = __fmul_rn(__fmul_rn(sigma, nz[q]), temperature);
+      xp[q] = __fadd_rn(__fadd_rn(__fmul_rn(sqrt_aprev, px0), dir), nn);
+      p0[q] = px0;
+    }
+    if (i + 3 < n) {
+      *reinterpret_cast<float4*>(x_prev + i) = *reinterpret_cast<float4*>(xp);
+      if (pred_x0) *reinterpret_cast<float4*>(pred_x0 + i) = *reinterpret_cast<float4*>(p0);
+    } else {
+      for (int q = 0; q < 4; ++q)
+        if (i + q < n) {
+          x_prev[i + q] = xp[q];
+          if (pred_x0) pred_x0[i + q] = p0[q];
+        }
+    }
+  }
+}
+
+__global__ void add_int_kernel(int* p, int delta) { *p += delta; }
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm(32) statistics over NHWC bf16, optional two-source channel concat.
+// grid (nsplit, B), block 512. Thread t owns channel-vector v = t % V (8 channels) and pixel lane
+// t / V; per-thread fp32 sum / sum-of-squares, then shared-memory atomics into the 32 groups.
+// partial[b][split][g][2] = {sum, sumsq} over this CTA's pixel range (no global atomics: the
+// result is deterministic, which the N-rank == 1-rank bit-reproducibility test relies on).
+// ---------------------------------------------------------------------------------------------
+constexpr int kGnThreads = 512;
+
+__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1,
+                                                              const __nv_bfloat16* __restrict__ x2, int C2,
+                                                              int HW, int groups, float* __restrict__ partial) {
+  const int C = C1 + C2;
+  const int V = C / 8;
+  const int cpg = C / groups;
+  const int b = blockIdx.y, split = blockIdx.x, nsplit = gridDim.x;
+  const int pix_per = (HW + nsplit - 1) / nsplit;
+  const int p_begin = split * pix_per;
+  const int p_end = min(HW, p_begin + pix_per);
+  // deterministic two-level reduction (no atomics): [pixel lane][channel][sum|sumsq] -> channel -> group
+  __shared__ float part[kGnThreads * 16];
+  const int lanes = kGnThreads / V;  // pixel lanes (>= 1 because V <= 512)
+  const int v = threadIdx.x % V;
+  const int pl = threadIdx.x / V;
+  if (pl < lanes) {
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+    const bool first = v * 8 < C1;
+    const __nv_bfloat16* src = first ? x1 + static_cast<long long>(b) * HW * C1 + v * 8
+                                     : x2 + static_cast<long long>(b) * HW * C2 + (v * 8 - C1);
+    const int Cs = first ? C1 : C2;
+    for (int p = p_begin + pl; p < p_end; p += lanes) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(p) * Cs));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16x2(w[i]);
+        s[2 * i] += f.x; q[2 * i] += f.x * f.x;
+        s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+      }
+    }
+    float* dst = part + (static_cast<size_t>(pl) * V + v) * 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { dst[i] = s[i]; dst[8 + i] = q[i]; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kGnThreads) {
+    float s = 0.f, q = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      const float* src = part + (static_cast<size_t>(l) * V + c / 8) * 16 + (c & 7);
+      s += src[0]; q += src[8];
+    }
+    float* own = part + (static_cast<size_t>(c / 8)) * 16 + (c & 7);  // lane-0 slot of this channel (only this thread touches it)
+    own[0] = s; own[8] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    float s = 0.f, q = 0.f;
+    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
+      const float* src = part + (static_cast<size_t>(c / 8)) * 16 + (c & 7);
+      s += src[0]; q += src[8];
+    }
+    float* o = partial + (static_cast<long long>(b) * nsplit + split) * 2 * groups + 2 * threadIdx.x;
+    o[0] = s; o[1] = q;
+  }
+}
+
+// y = act((x - mean) * rstd * gamma + beta), written as one concatenated NHWC bf16 tensor.
+// grid (nblk, B), block 256; dynamic smem = 2*C floats (per-channel scale/shift).
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int C1,
+                                                       const __nv_bfloat16* __restrict__ x2, int C2, int HW,
+                                                       int groups, const float* __restrict__ partial, int nsplit,
+                                                       const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float eps, int act,
+                                                       __nv_bfloat16* __restrict__ y) {
+  extern __shared__ float sm[];
+  const int C = C1 + C2;
+  const int cpg = C / groups;
+  float* scale = sm;
+  float* shift = sm + C;
+  __shared__ float gmean[32], grstd[32];
+  const int b = blockIdx.y;
+  if (threadIdx.x < groups) {
+    float s = 0.f, q = 0.f;
+    for (int i = 0; i < nsplit; ++i) {
+      const float* pp = partial + (static_cast<long long>(b) * nsplit + i) * 2 * groups + 2 * threadIdx.x;
+      s += pp[0]; q += pp[1];
+    }
+    const float inv_n = 1.0f / (static_cast<float>(HW) * cpg);
+    const float mean = s * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    gmean[threadIdx.x] = mean;
+    grstd[threadIdx.x] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float sc = grstd[g] * __ldg(gamma + c);
+    scale[c] = sc;
+    shift[c] = __ldg(beta + c) - gmean[g] * sc;
+  }
+  __syncthreads();
+  const int V = C / 8;
+  const long long total = static_cast<long long>(HW) * V;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % V);
+    const long long p = i / V;
+    const int c0 = v * 8;
+    const uint4 u = (c0 < C1)
+                        ? __ldg(reinterpret_cast<const uint4*>(x1 + (static_cast<long long>(b) * HW + p) * C1 + c0))
+                        : __ldg(reinterpret_cast<const uint4*>(x2 + (static_cast<long long>(b) * HW + p) * C2 + (c0 - C1)));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16x2(w[k]);
+      float a = f.x * scale[c0 + 2 * k] + shift[c0 + 2 * k];
+      float bb = f.y * scale[c0 + 2 * k + 1] + shift[c0 + 2 * k + 1];
+      if (act == 1) { a = silu_f(a); bb = silu_f(bb); }
+      o[k] = pack_bf16x2(a, bb);
+    }
+    *reinterpret_cast<uint4*>(y + (static_cast<long long>(b) * HW + p) * C + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over the last dim of [rows, C] bf16 (one warp per row, two-pass in registers).
+// ---------------------------------------------------------------------------------------------
+template <int MAXV>  // max 16-byte vectors per lane
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps,
+                                                        __nv_bfloat16* __restrict__ y) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int V = C / 8;
+  for (long long r = warp; r < rows; r += nwarps) {
+    float f[MAXV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      if (v < V) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + r * C + v * 8));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 t = unpack_bf16x2(w[k]);
+          f[i][2 * k] = t.x; f[i][2 * k + 1] = t.y;
+          s += t.x + t.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      if (lane + i * 32 < V) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float d = f[i][k] - mean; q += d * d; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / C + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      if (v < V) {
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = v * 8 + 2 * k;
+          const float a = (f[i][2 * k] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+          const float b2 = (f[i][2 * k + 1] - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
+          o[k] = pack_bf16x2(a, b2);
+        }
+        *reinterpret_cast<uint4*>(y + r * C + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
+// nearest-neighbour 2x upsample of NHWC bf16           (openaimodel.py:114, autokl_modules.py:54)
+__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C,
+                                  __nv_bfloat16* __restrict__ y) {
+  const int V = C / 8;
+  const long long total = static_cast<long long>(B) * 2 * H * 2 * W * V;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % V);
+    long long p = i / V;
+    const int xo = static_cast<int>(p % (2 * W)); p /= 2 * W;
+    const int yo = static_cast<int>(p % (2 * H));
+    const int b = static_cast<int>(p / (2 * H));
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(
+        x + ((static_cast<long long>(b) * H + (yo >> 1)) * W + (xo >> 1)) * C + v * 8));
+    *reinterpret_cast<uint4*>(y + ((static_cast<long long>(b) * 2 * H + yo) * 2 * W + xo) * C + v * 8) = u;
+  }
+}
+
+// im2col for 3x3/pad-1/stride-1 convs with tiny Cin (latent 4ch, RGB 3ch): fp32 NHWC in,
+// bf16 [B*H*W, Kpad] out with column (ky*3+kx)*Cin + c, zero padded to Kpad.
+__global__ void im2col3x3_small_kernel(const float* __restrict__ x, int B, int H, int W, int Cin, int Kpad,
+                                       float in_scale, float in_shift, __nv_bfloat16* __restrict__ y) {
+  const long long total = static_cast<long long>(B) * H * W * Kpad;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % Kpad);
+    long long p = i / Kpad;
+    float val = 0.f;
+    if (k < 9 * Cin) {
+      const int c = k % Cin, t = k / Cin;
+      const int xo = static_cast<int>(p % W);
+      const int yo = static_cast<int>((p / W) % H);
+      const int b = static_cast<int>(p / (static_cast<long long>(W) * H));
+      const int xi = xo + t % 3 - 1, yi = yo + t / 3 - 1;
+      if (xi >= 0 && xi < W && yi >= 0 && yi < H)
+        val = x[((static_cast<long long>(b) * H + yi) * W + xi) * Cin + c] * in_scale + in_shift;
+    }
+    y[i] = __float2bfloat16(val);
+  }
+}
+
+// fp32 NCHW <-> NHWC permutes for the latent / image boundaries; optional affine + clamp on the way out
+__global__ void permute_f32_kernel(const float* __restrict__ x, int B, int C, int HW, int to_nhwc, float mul,
+                                   float add, int clamp01, float* __restrict__ y) {
+  const long long total = static_cast<long long>(B) * C * HW;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long src;
+    if (to_nhwc) {  // i indexes NHWC output
+      const int c = static_cast<int>(i % C);
+      const long long p = (i / C) % HW;
+      const long long b = i / (static_cast<long long>(C) * HW);
+      src = (b * C + c) * HW + p;
+    } else {        // i indexes NCHW output
+      const long long p = i % HW;
+      const int c = static_cast<int>((i / HW) % C);
+      const long long b = i / (static_cast<long long>(C) * HW);
+      src = (b * HW + p) * C + c;
+    }
+    float v = x[src] * mul + add;
+    if (clamp01) v = fminf(fmaxf(v, 0.f), 1.f);
+    y[i] = v;
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    y[i] = __float2bfloat16(x[i]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    y[i] = __bfloat162float(x[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sinusoidal timestep embedding [cos | sin]              (diffusion_utils.py:131-151)
+// t from ts[b] (int64), or ts_table[*step_idx] broadcast to all rows when step_idx != null.
+// ---------------------------------------------------------------------------------------------
+__global__ void timestep_embedding_kernel(const long long* __restrict__ ts, const int* __restrict__ step_idx,
+                                          int B, int dim, float neg_log_period, float* __restrict__ out) {
+  const int half = dim / 2;
+  const int total = B * half;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / half, k = i % half;
+    const float t = static_cast<float>(step_idx ? ts[*step_idx] : ts[b]);
+    // freqs = exp(-ln(max_period) * k / half) in fp32, as torch does (host passes fp32(-ln(max_period)))
+    const float fr = expf(__fdiv_rn(__fmul_rn(neg_log_period, static_cast<float>(k)), static_cast<float>(half)));
+    const float a = t * fr;
+    out[b * dim + k] = cosf(a);
+    out[b * dim + half + k] = sinf(a);
+    if ((dim & 1) && k == 0) out[b * dim + dim - 1] = 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Skinny linear for M <= 16 rows (time-embedding MLP, ResBlock.emb_layers): weight-bandwidth bound.
+//   out[m, n] = act_out( sum_k act_in(x[m, k]) * W[n, k] + bias[n] )          fp32 x/out, bf16 W
+// One warp per output column; x staged (activated) in shared memory.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) linear_small_kernel(const float* __restrict__ x, int M, int K,
+                                                           const __nv_bfloat16* __restrict__ Wt, int N,
+                                                           const float* __restrict__ bias, int act_in, int act_out,
+                                                           float* __restrict__ out) {
+  extern __shared__ float xs[];  // [M, K]
+  for (int i = threadIdx.x; i < M * K; i += blockDim.x) {
+    float v = x[i];
+    if (act_in == 1) v = silu_f(v);
+    xs[i] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  for (int n = blockIdx.x * nwarps + warp; n < N; n += gridDim.x * nwarps) {
+    float acc[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) acc[m] = 0.f;
+    const __nv_bfloat16* wr = Wt + static_cast<long long>(n) * K;
+    for (int k = lane * 8; k < K; k += 256) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(wr + k));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      float wf[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const float2 t = unpack_bf16x2(w[q]); wf[2 * q] = t.x; wf[2 * q + 1] = t.y; }
+#pragma unroll
+      for (int m = 0; m < 16; ++m) {
+        if (m < M) {
+          const float* xr = xs + m * K + k;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[m] += xr[q] * wf[q];
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      if (m < M) {
+        float v = acc[m];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) {
+          v += bias ? bias[n] : 0.f;
+          if (act_out == 1) v = silu_f(v);
+          out[static_cast<long long>(m) * N + n] = v;
+        }
+      }
+    }
+  }
+}
+
+// row softmax over [rows, n] bf16 with scale, fp32 math, bf16 out (VAE AttnBlock, autokl_modules.py:186-188)
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const __nv_bfloat16* __restrict__ x, long long rows,
+                                                           int n, long long ld, float scale,
+                                                           __nv_bfloat16* __restrict__ y) {
+  __shared__ float red[32];
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const __nv_bfloat16* xr = x + r * ld;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, __bfloat162float(xr[i]) * scale);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < (blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += __expf(__bfloat162float(xr[i]) * scale - mx);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    s = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) s += red[w];
+    __syncthreads();
+    const float inv = 1.f / s;
+    __nv_bfloat16* yr = y + r * ld;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      yr[i] = __float2bfloat16(__expf(__bfloat162float(xr[i]) * scale - mx) * inv);
+  }
+}
+
+static int ew_blocks(long long work_items, int threads) {
+  long long b = (work_items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace vdb
+
+using namespace vdb;
+
+extern "C" {
+
+int vdb_ddim_cfg_step(const float* e_uncond, const float* e_cond, const float* x, const float* noise,
+                      const float* coef, const int* step_idx, float scale, float temperature, float* x_prev,
+                      float* pred_x0, long long n, void* stream) {
+  if (!e_cond || !x || !coef || !x_prev || n <= 0) return set_error(VDB_ERR_INVALID, "ddim_cfg_step: null/empty argument");
+  if ((reinterpret_cast<uintptr_t>(e_cond) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_prev) |
+       reinterpret_cast<uintptr_t>(e_uncond) | reinterpret_cast<uintptr_t>(noise) | reinterpret_cast<uintptr_t>(pred_x0)) & 15)
+    return set_error(VDB_ERR_INVALID, "ddim_cfg_step: pointers must be 16-byte aligned");
+  const int threads = 256;
+  ddim_cfg_step_kernel<<<ew_blocks((n + 3) / 4, threads), threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      e_uncond, e_cond, x, noise, coef, step_idx, scale, temperature, x_prev, pred_x0, n);
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_add_int(int* p, int delta, void* stream) {
+  if (!p) return set_error(VDB_ERR_INVALID, "add_int: null");
+  add_int_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, delta);
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+// partial must hold B * nsplit * 2 * groups floats; returns nsplit through *nsplit_out when partial == null
+int vdb_groupnorm_nsplit(int B, int HW) {
+  int ns = (HW + 255) / 256;
+  const int want = std::max(1, (2 * num_sms()) / std::max(B, 1));
+  ns = std::min(ns, want);
+  ns = std::min(ns, 256);
+  return std::max(ns, 1);
+}
+
+int vdb_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int B, int HW, int groups, const float* gamma,
+                       const float* beta, float eps, int act, float* partial, void* y, void* stream) {
+  const int C = C1 + (x2 ? C2 : 0);
+  if (!x1 || !gamma || !beta || !partial || !y) return set_error(VDB_ERR_INVALID, "groupnorm: null argument");
+  if (groups != 32 || (C % groups) || (C1 % 8) || (x2 && (C2 % 8)) || C / 8 > kGnThreads)
+    return set_error(VDB_ERR_UNSUPPORTED, "groupnorm: need 32 groups, C %% 32 == 0, C/8 <= 512 (C=%d)", C);
+  if (!x2) C2 = 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int nsplit = vdb_groupnorm_nsplit(B, HW);
+  gn_stats_kernel<<<dim3(nsplit, B), kGnThreads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x1), C1,
+                                                         reinterpret_cast<const __nv_bfloat16*>(x2), C2, HW, groups,
+                                                         partial);
+  VDB_CUDA_CHECK(cudaGetLastError());
+  const long long work = static_cast<long long>(HW) * (C / 8);
+  int nblk = static_cast<int>(std::min<long long>((work + 255) / 256, std::max(1, (num_sms() * 8) / std::max(B, 1))));
+  gn_apply_kernel<<<dim3(nblk, B), 256, 2 * C * sizeof(float), st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x1), C1, reinterpret_cast<const __nv_bfloat16*>(x2), C2, HW, groups,
+      partial, nsplit, gamma, beta, eps, act, reinterpret_cast<__nv_bfloat16*>(y));
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch(2);
+  return VDB_OK;
+}
+
+int vdb_layernorm(const void* x, long long rows, int C, const float* gamma, const float* beta, float eps, void* y,
+                  void* stream) {
+  if (!x || !gamma || !beta || !y || rows <= 0) return set_error(VDB_ERR_INVALID, "layernorm: null/empty argument");
+  if ((C % 8) || C > 8 * 32 * 8) return set_error(VDB_ERR_UNSUPPORTED, "layernorm: C must be a multiple of 8, <= 2048");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int threads = 256;
+  const int blocks = static_cast<int>(std::min<long long>((rows + 7) / 8, num_sms() * 8LL));
+  const int V = C / 8;
+  if (V <= 64)
+    layernorm_kernel<2><<<blocks, threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, C, gamma, beta, eps,
+                                                    reinterpret_cast<__nv_bfloat16*>(y));
+  else if (V <= 160)
+    layernorm_kernel<5><<<blocks, threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, C, gamma, beta, eps,
+                                                    reinterpret_cast<__nv_bfloat16*>(y));
+  else
+    layernorm_kernel<8><<<blocks, threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, C, gamma, beta, eps,
+                                                    reinterpret_cast<__nv_bfloat16*>(y));
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_upsample2x_nhwc(const void* x, int B, int H, int W, int C, void* y, void* stream) {
+  if (!x || !y || (C % 8)) return set_error(VDB_ERR_INVALID, "upsample2x: null argument or C %% 8 != 0");
+  const long long total = static_cast<long long>(B) * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<ew_blocks(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, reinterpret_cast<__nv_bfloat16*>(y));
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_im2col3x3_small(const float* x, int B, int H, int W, int Cin, int Kpad, float in_scale, float in_shift,
+                        void* y, void* stream) {
+  if (!x || !y || 9 * Cin > Kpad || (Kpad % 8)) return set_error(VDB_ERR_INVALID, "im2col3x3_small: bad argument");
+  const long long total = static_cast<long long>(B) * H * W * Kpad;
+  im2col3x3_small_kernel<<<ew_blocks(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, B, H, W, Cin, Kpad, in_scale, in_shift, reinterpret_cast<__nv_bfloat16*>(y));
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_permute_f32(const float* x, int B, int C, long long HW, int to_nhwc, float mul, float add, int clamp01,
+                    float* y, void* stream) {
+  if (!x || !y) return set_error(VDB_ERR_INVALID, "permute_f32: null argument");
+  const long long total = static_cast<long long>(B) * C * HW;
+  permute_f32_kernel<<<ew_blocks(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, B, C, static_cast<int>(HW), to_nhwc, mul, add, clamp01, y);
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_cast_f32_bf16(const float* x, void* y, long long n, void* stream) {
+  if (!x || !y) return set_error(VDB_ERR_INVALID, "cast: null argument");
+  cast_f32_bf16_kernel<<<ew_blocks(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(y), n);
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+int vdb_cast_bf16_f32(const void* x, float* y, long long n, void* stream) {
+  if (!x || !y) return set_error(VDB_ERR_INVALID, "cast: null argument");
+  cast_bf16_f32_kernel<<<ew_blocks(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), y, n);
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_timestep_embedding(const long long* ts, const int* step_idx, int B, int dim, float neg_log_period, float* out,
+                           void* stream) {
+  if (!ts || !out || B <= 0 || dim <= 1) return set_error(VDB_ERR_INVALID, "timestep_embedding: bad argument");
+  timestep_embedding_kernel<<<ew_blocks(static_cast<long long>(B) * (dim / 2), 128), 128, 0,
+                              reinterpret_cast<cudaStream_t>(stream)>>>(ts, step_idx, B, dim, neg_log_period, out);
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_linear_small(const float* x, int M, int K, const void* Wt, int N, const float* bias, int act_in, int act_out,
+                     float* out, void* stream) {
+  if (!x || !Wt || !out || M <= 0 || M > 16 || (K % 8)) return set_error(VDB_ERR_INVALID, "linear_small: need 1 <= M <= 16, K %% 8 == 0");
+  const size_t smem = static_cast<size_t>(M) * K * sizeof(float);
+  if (smem > 200 * 1024) return set_error(VDB_ERR_UNSUPPORTED, "linear_small: M*K too large for shared memory");
+  static bool configured = false;
+  if (!configured) {
+    VDB_CUDA_CHECK(cudaFuncSetAttribute(linear_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  const int blocks = std::min((N + 7) / 8, num_sms() * 2);
+  linear_small_kernel<<<blocks, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, M, K, reinterpret_cast<const __nv_bfloat16*>(Wt), N, bias, act_in, act_out, out);
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_softmax_rows(const void* x, long long rows, int n, long long ld, float scale, void* y, void* stream) {
+  if (!x || !y || rows <= 0 || n <= 0) return set_error(VDB_ERR_INVALID, "softmax_rows: bad argument");
+  const int blocks = static_cast<int>(std::min<long long>(rows, num_sms() * 8LL));
+  softmax_rows_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), rows, n, ld, scale, reinterpret_cast<__nv_bfloat16*>(y));
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+}  // extern "C"

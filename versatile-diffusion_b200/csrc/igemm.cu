@@ -1,0 +1,625 @@
+// vdb200 — persistent tcgen05 implicit-GEMM mainloop (sm_100a).
+//
+// One kernel family serves every GEMM-shaped stage of the Versatile-Diffusion sampling path:
+//   * Linear layers and 1x1 convs on NHWC activations (CrossAttention.to_q/k/v/to_out,
+//     FeedForward/GEGLU, SpatialTransformer.proj_in/out — reference lib/model_zoo/attention.py:37-64,
+//     152-193, 221-266; AutoencoderKL AttnBlock q/k/v/proj_out — autokl_modules.py:150-202),
+//   * 3x3 convolutions as implicit GEMM over 9 filter taps (ResBlock in_layers[2]/out_layers[3],
+//     Downsample.op, Upsample.conv — openaimodel.py:89-274; VAE ResnetBlock/Downsample/Upsample —
+//     autokl_modules.py:42-141), with the 1x1 skip_connection of a channel-changing ResBlock folded
+//     in as extra K segments of the same accumulator.
+//
+// Structure: grid = #SMs (persistent, static round-robin over output tiles), 192 threads:
+//   warp 0   : TMA producer  (cp.async.bulk.tensor 4D box loads of A, 2D box loads of W)
+//   warp 1   : MMA issuer    (tcgen05.mma cta_group::1 kind::f16, 128 x BN x 16, fp32 accum in TMEM)
+//   warps 2-5: epilogue      (tcgen05.ld -> bias/act/residual -> bf16/fp32 global stores)
+// smem ring of STAGES x (A 128x64 bf16 | W BNx64 bf16), both 128B-swizzled K-major; TMEM holds two
+// accumulator stages (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace vdb {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // bf16 elements = 128 B = one swizzle row
+constexpr int kMaxA = 6;     // A tensor maps per launch
+constexpr int kMaxSeg = 12;  // K segments per launch
+constexpr int kNumThreads = 192;
+constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
+
+struct ASeg {
+  int16_t tmap;  // which A tensor map
+  int16_t dw;    // W-coordinate shift of this segment (filter tap / parity lattice)
+  int16_t dh;    // H-coordinate shift
+  int16_t nkb;   // number of 64-channel k-blocks
+  int32_t c0;    // first channel coordinate
+};
+
+struct alignas(64) IgemmParams {
+  CUtensorMap tmA[kMaxA];  // 4D (C, W, H, B) bf16, box (64, TW, TH, TB), SWIZZLE_128B
+  CUtensorMap tmB;         // 2D (Ktot, N) bf16, box (64, BN), SWIZZLE_128B
+  ASeg seg[kMaxSeg];
+  int nseg;
+  int kb_total;      // total k-blocks over all segments
+  int ksplit;        // split-K factor (>=1); >1 => fp32 partial output
+  int kb_per_split;  // ceil(kb_total / ksplit)
+  int TW, TH, TB;    // M tile = TW*TH*TB = 128 output pixels
+  int Wo, Ho, Bo;    // output pixel grid (GEMM view: Wo = M, Ho = Bo = 1)
+  int tilesW, tilesH, tilesB, tilesN;
+  int N;             // valid output columns (GEGLU: packed columns, output has N/2)
+  // epilogue
+  const float* bias;          // [bias_rows, N] fp32 or null
+  long long bias_bstride;     // 0: shared bias row; else stride between per-batch rows
+  int rows_per_batch;         // output pixels per batch element (for bias_bstride != 0)
+  const __nv_bfloat16* resid; // [M, ldr] bf16 or null (added after activation)
+  long long ldr;
+  void* out;                  // bf16 or fp32 [M, ldo]
+  long long ldo;
+  int out_f32;                // 1: fp32 output
+  int act;                    // 0 none, 1 silu, 2 gelu(erf), 3 quick_gelu, 4 geglu (packed halves)
+  float alpha;                // accumulator scale applied before bias
+  float* partial;             // split-K: [ksplit, M, N] fp32
+};
+
+enum { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_QGELU = 3, ACT_GEGLU = 4 };
+
+VDB_DEVINL float apply_act(float v, int act) {
+  switch (act) {
+    case ACT_SILU: return silu_f(v);
+    case ACT_GELU: return gelu_erf_f(v);
+    case ACT_QGELU: return quick_gelu_f(v);
+    default: return v;
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+  constexpr uint32_t kBBytes = BN * kBlockK * 2;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static_assert(kBBytes % 1024 == 0, "B stage must keep 1024B alignment");
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smemA = smem;
+  uint8_t* smemB = smem + STAGES * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < kMaxA; ++i) tma_prefetch_desc(&p.tmA[i]);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int tilesM = p.tilesW * p.tilesH * p.tilesB;
+  const int num_tiles = tilesM * p.tilesN * p.ksplit;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_idx = t % tilesM;
+        const int rest = t / tilesM;
+        const int n_idx = rest % p.tilesN;
+        const int ks = rest / p.tilesN;
+        const int wt = m_idx % p.tilesW;
+        const int ht = (m_idx / p.tilesW) % p.tilesH;
+        const int bt = m_idx / (p.tilesW * p.tilesH);
+        const int w0 = wt * p.TW, h0 = ht * p.TH, b0 = bt * p.TB;
+        const int n0 = n_idx * BN;
+        const int kb_begin = ks * p.kb_per_split;
+        const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
+        int kb = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const ASeg sg = p.seg[s];
+          if (kb + sg.nkb <= kb_begin) { kb += sg.nkb; continue; }
+          for (int j = 0; j < sg.nkb; ++j, ++kb) {
+            if (kb < kb_begin) continue;
+            if (kb >= kb_end) break;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+            tma_load_4d(smemA + stage * kABytes, &p.tmA[sg.tmap], &full_bar[stage],
+                        sg.c0 + j * kBlockK, w0 + sg.dw, h0 + sg.dh, b0);
+            tma_load_2d(smemB + stage * kBBytes, &p.tmB, &full_bar[stage], kb * kBlockK, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (kb >= kb_end) break;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN);
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int ks = (t / tilesM) / p.tilesN;
+        const int kb_begin = ks * p.kb_per_split;
+        const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * 256;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_desc_sw128(smem_u32(smemA + stage * kABytes));
+          const uint64_t bdesc = make_desc_sw128(smem_u32(smemB + stage * kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
+            umma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else {
+    // ------------------------------ epilogue ------------------------------
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int m_idx = t % tilesM;
+      const int rest = t / tilesM;
+      const int n_idx = rest % p.tilesN;
+      const int ks = rest / p.tilesN;
+      const int wt = m_idx % p.tilesW;
+      const int ht = (m_idx / p.tilesW) % p.tilesH;
+      const int bt = m_idx / (p.tilesW * p.tilesH);
+      const int tw = r % p.TW;
+      const int th = (r / p.TW) % p.TH;
+      const int tb = r / (p.TW * p.TH);
+      const int w = wt * p.TW + tw, h = ht * p.TH + th, b = bt * p.TB + tb;
+      const bool row_ok = (w < p.Wo) && (h < p.Ho) && (b < p.Bo);
+      const long long gp = (static_cast<long long>(b) * p.Ho + h) * p.Wo + w;
+      const int n0 = n_idx * BN;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + as * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+
+      if (p.ksplit > 1) {
+        // fp32 partials, reduced (+bias/act/residual) by splitk_reduce_kernel
+        const long long Mtot = static_cast<long long>(p.Bo) * p.Ho * p.Wo;
+        float* dst = p.partial + (static_cast<long long>(ks) * Mtot + gp) * p.N + n0;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(trow + c * 32, v);
+          tmem_wait_ld();
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const int n = n0 + c * 32 + j;
+              if (n + 3 < p.N) {
+                *reinterpret_cast<float4*>(dst + c * 32 + j) =
+                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              } else {
+                for (int q = 0; q < 4; ++q)
+                  if (n + q < p.N) dst[c * 32 + j + q] = __uint_as_float(v[j + q]);
+              }
+            }
+          }
+        }
+      } else if (p.act == ACT_GEGLU) {
+        // packed tile: columns [0,BN/2) = value rows, [BN/2,BN) = gate rows of the same outputs
+        constexpr int HALF = BN / 2;
+        const int nout0 = n_idx * HALF;
+        const int Nout = p.N / 2;
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + gp * p.ldo + nout0;
+#pragma unroll 1
+        for (int c = 0; c < HALF / 32; ++c) {
+          uint32_t v[32], g[32];
+          tmem_ld32(trow + c * 32, v);
+          tmem_ld32(trow + HALF + c * 32, g);
+          tmem_wait_ld();
+          if (row_ok) {
+            uint32_t o[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float a0 = __uint_as_float(v[j]) * p.alpha, a1 = __uint_as_float(v[j + 1]) * p.alpha;
+              float g0 = __uint_as_float(g[j]) * p.alpha, g1 = __uint_as_float(g[j + 1]) * p.alpha;
+              if (p.bias) {
+                a0 += __ldg(p.bias + n0 + c * 32 + j);
+                a1 += __ldg(p.bias + n0 + c * 32 + j + 1);
+                g0 += __ldg(p.bias + n0 + HALF + c * 32 + j);
+                g1 += __ldg(p.bias + n0 + HALF + c * 32 + j + 1);
+              }
+              o[j / 2] = pack_bf16x2(a0 * gelu_erf_f(g0), a1 * gelu_erf_f(g1));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (nout0 + c * 32 + j * 8 + 7 < Nout)
+                *reinterpret_cast<uint4*>(dst + c * 32 + j * 8) =
+                    make_uint4(o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]);
+            }
+          }
+        }
+      } else {
+        const float* bias = p.bias ? p.bias + (p.bias_bstride ? (gp / p.rows_per_batch) * p.bias_bstride : 0) : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          if (n0 + c * 32 >= p.N) break;
+          uint32_t v[32];
+          tmem_ld32(trow + c * 32, v);
+          tmem_wait_ld();
+          if (row_ok) {
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+            const int nb = n0 + c * 32;
+            const bool full = nb + 32 <= p.N;
+            if (bias) {
+              if (full) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + nb + j));
+                  f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (nb + j < p.N) f[j] += __ldg(bias + nb + j);
+              }
+            }
+            if (p.act != ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+            }
+            if (p.resid) {
+              const __nv_bfloat16* rs = p.resid + gp * p.ldr + nb;
+              if (full) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rs + j * 8));
+                  const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const float2 x = unpack_bf16x2(rr[q]);
+                    f[j * 8 + q * 2] += x.x;
+                    f[j * 8 + q * 2 + 1] += x.y;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (nb + j < p.N) f[j] += __bfloat162float(rs[j]);
+              }
+            }
+            if (p.out_f32) {
+              float* dst = reinterpret_cast<float*>(p.out) + gp * p.ldo + nb;
+              if (full) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = f[j];
+              }
+            } else {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + gp * p.ldo + nb;
+              if (full) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  *reinterpret_cast<uint4*>(dst + j * 8) =
+                      make_uint4(pack_bf16x2(f[j * 8], f[j * 8 + 1]), pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]),
+                                 pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]), pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = __float2bfloat16(f[j]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+// split-K reduction + epilogue: out[m, n] = act(alpha * sum_s partial[s, m, n] + bias) + resid
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int ksplit, long long M, int N,
+                                     const float* __restrict__ bias, long long bias_bstride, int rows_per_batch,
+                                     const __nv_bfloat16* __restrict__ resid, long long ldr, void* out,
+                                     long long ldo, int out_f32, int act, float alpha) {
+  const long long total = M * (N / 4);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = i / (N / 4);
+    const int n = static_cast<int>(i % (N / 4)) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < ksplit; ++s) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (static_cast<long long>(s) * M + m) * N + n));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float f[4] = {acc.x * alpha, acc.y * alpha, acc.z * alpha, acc.w * alpha};
+    if (bias) {
+      const float* bp = bias + (bias_bstride ? (m / rows_per_batch) * bias_bstride : 0) + n;
+      for (int q = 0; q < 4; ++q) f[q] += __ldg(bp + q);
+    }
+    for (int q = 0; q < 4; ++q) f[q] = apply_act(f[q], act);
+    if (resid) {
+      for (int q = 0; q < 4; ++q) f[q] += __bfloat162float(resid[m * ldr + n + q]);
+    }
+    if (out_f32) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + m * ldo + n) = make_float4(f[0], f[1], f[2], f[3]);
+    } else {
+      uint2 o = make_uint2(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]));
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + m * ldo + n) = o;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+static int launch_igemm(const IgemmParams& p, int num_tiles, cudaStream_t stream) {
+  constexpr size_t smem = STAGES * (kABytes + BN * kBlockK * 2) + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    VDB_CUDA_CHECK(cudaFuncSetAttribute(igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    configured = true;
+  }
+  const int grid = std::min(num_tiles, num_sms());
+  igemm_kernel<BN, STAGES><<<grid, kNumThreads, smem, stream>>>(p);
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+static int pick_bn(int N, int act, int forced) {
+  if (forced) return forced;
+  if (act == ACT_GEGLU) return 256;
+  if (N <= 64) return 64;
+  if (N % 256 == 0) return 256;
+  if (N % 160 == 0) return 160;
+  if (N % 128 == 0) return 128;
+  if (N <= 128) return 128;
+  if (N <= 160) return 160;
+  return 256;
+}
+
+struct IgemmEpilogue {
+  const float* bias = nullptr;
+  long long bias_bstride = 0;
+  int rows_per_batch = 1;
+  const void* resid = nullptr;
+  long long ldr = 0;
+  void* out = nullptr;
+  long long ldo = 0;
+  int out_f32 = 0;
+  int act = 0;
+  float alpha = 1.f;
+};
+
+// Finish IgemmParams (tiling, split-K, B map) and launch.
+static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot, long long ldw,
+                     const IgemmEpilogue& e, int bn_forced, int ksplit_forced, void* workspace,
+                     size_t ws_bytes, cudaStream_t stream) {
+  const int BN = pick_bn(static_cast<int>(N), e.act, bn_forced);
+  if (BN != 64 && BN != 128 && BN != 160 && BN != 256) return set_error(VDB_ERR_INVALID, "igemm: bad BN");
+  if (e.act == ACT_GEGLU && (N % BN) != 0) return set_error(VDB_ERR_INVALID, "igemm: GEGLU needs N % 256 == 0");
+  p.N = static_cast<int>(N);
+  p.tilesN = static_cast<int>((N + BN - 1) / BN);
+  p.bias = e.bias; p.bias_bstride = e.bias_bstride; p.rows_per_batch = e.rows_per_batch > 0 ? e.rows_per_batch : 1;
+  p.resid = reinterpret_cast<const __nv_bfloat16*>(e.resid); p.ldr = e.ldr;
+  p.out = e.out; p.ldo = e.ldo; p.out_f32 = e.out_f32; p.act = e.act; p.alpha = e.alpha;
+  if (!e.out_f32 && (e.ldo % 8)) return set_error(VDB_ERR_INVALID, "igemm: ldo must be a multiple of 8 for bf16 out");
+  if (e.resid && (e.ldr % 8)) return set_error(VDB_ERR_INVALID, "igemm: ldr must be a multiple of 8");
+  int rc = make_tmap_2d(&p.tmB, Wt, static_cast<uint64_t>(Ktot), static_cast<uint64_t>(N),
+                        static_cast<uint64_t>(ldw) * 2, kBlockK, BN);
+  if (rc) return rc;
+  const long long M = static_cast<long long>(p.Bo) * p.Ho * p.Wo;
+  const int tilesM = p.tilesW * p.tilesH * p.tilesB;
+  const int mn_tiles = tilesM * p.tilesN;
+  // split-K heuristic: fill the machine when the MN grid is small and K is deep
+  int ksplit = 1;
+  if (ksplit_forced > 0) {
+    ksplit = ksplit_forced;
+  } else if (e.act != ACT_GEGLU && mn_tiles * 2 <= num_sms() && p.kb_total >= 16 && (N % 4) == 0) {
+    ksplit = std::min(std::min(num_sms() / mn_tiles, p.kb_total / 8), 16);
+    if (ksplit < 1) ksplit = 1;
+  }
+  if (ksplit > 1) {
+    const size_t need = static_cast<size_t>(ksplit) * M * N * sizeof(float);
+    if (workspace == nullptr || ws_bytes < need || e.act == ACT_GEGLU || (N % 4)) ksplit = 1;
+  }
+  p.ksplit = ksplit;
+  p.kb_per_split = (p.kb_total + ksplit - 1) / ksplit;
+  // drop empty trailing splits
+  p.ksplit = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.partial = reinterpret_cast<float*>(workspace);
+  const int num_tiles = mn_tiles * p.ksplit;
+  switch (BN) {
+    case 64: rc = launch_igemm<64, 8>(p, num_tiles, stream); break;
+    case 128: rc = launch_igemm<128, 6>(p, num_tiles, stream); break;
+    case 160: rc = launch_igemm<160, 5>(p, num_tiles, stream); break;
+    default: rc = launch_igemm<256, 4>(p, num_tiles, stream); break;
+  }
+  if (rc) return rc;
+  if (p.ksplit > 1) {
+    const long long total = M * (N / 4);
+    const int threads = 256;
+    const int blocks = static_cast<int>(std::min<long long>((total + threads - 1) / threads, num_sms() * 8LL));
+    splitk_reduce_kernel<<<blocks, threads, 0, stream>>>(p.partial, p.ksplit, M, static_cast<int>(N), p.bias,
+                                                         p.bias_bstride, p.rows_per_batch, p.resid, p.ldr, p.out,
+                                                         p.ldo, p.out_f32, p.act, p.alpha);
+    VDB_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  return VDB_OK;
+}
+
+static int pow2_ceil(int v) { int t = 1; while (t < v) t <<= 1; return t; }
+
+// M tile = 128 output pixels as a (TW, TH, TB) box of the (W, H, B) pixel grid; box extents are
+// powers of two so that TW*TH*TB == 128 (rows past the grid are zero-filled by TMA and masked on store).
+static void set_tile_shape(IgemmParams& p, int Wo, int Ho, int Bo) {
+  p.Wo = Wo; p.Ho = Ho; p.Bo = Bo;
+  const int TW = std::min(pow2_ceil(Wo), 128);
+  const int TH = std::min(pow2_ceil(Ho), 128 / TW);
+  const int TB = 128 / (TW * TH);
+  p.TW = TW; p.TH = TH; p.TB = TB;
+  p.tilesW = (Wo + TW - 1) / TW;
+  p.tilesH = (Ho + TH - 1) / TH;
+  p.tilesB = (Bo + TB - 1) / TB;
+}
+
+}  // namespace vdb
+
+using namespace vdb;
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+// out[M,N] = act(alpha * [A | A2] @ W^T + bias) + resid     (see include/vdb200.h)
+int vdb_gemm_bf16(const void* A, long long M, long long K, long long lda, const void* A2, long long K2,
+                  long long lda2, const void* W, long long N, long long ldw, const float* bias,
+                  long long bias_bstride, long long rows_per_batch, const void* resid, long long ldr, void* out,
+                  long long ldo, int out_f32, int act, float alpha, int bn, int ksplit, void* workspace,
+                  size_t ws_bytes, void* stream) {
+  if (!A || !W || !out || M <= 0 || N <= 0 || K <= 0) return set_error(VDB_ERR_INVALID, "gemm: null/empty argument");
+  if ((K % 8) || (lda % 8) || (ldw % 8)) return set_error(VDB_ERR_INVALID, "gemm: K, lda, ldw must be multiples of 8");
+  if (A2 && ((K % kBlockK) || (K2 % 8) || (lda2 % 8)))
+    return set_error(VDB_ERR_INVALID, "gemm: two-source A needs K % 64 == 0 and K2, lda2 % 8 == 0");
+  if (M > 0x7fffffffLL || N > 0x7fffffffLL) return set_error(VDB_ERR_INVALID, "gemm: dimension too large");
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  set_tile_shape(p, static_cast<int>(M), 1, 1);
+  int rc = make_tmap_4d(&p.tmA[0], A, K, M, 1, 1, lda * 2, lda * 2 * M, lda * 2 * M, kBlockK, p.TW, 1, 1);
+  if (rc) return rc;
+  p.seg[0] = ASeg{0, 0, 0, static_cast<int16_t>((K + kBlockK - 1) / kBlockK), 0};
+  p.nseg = 1;
+  p.kb_total = p.seg[0].nkb;
+  if (A2) {
+    rc = make_tmap_4d(&p.tmA[1], A2, K2, M, 1, 1, lda2 * 2, lda2 * 2 * M, lda2 * 2 * M, kBlockK, p.TW, 1, 1);
+    if (rc) return rc;
+    p.seg[1] = ASeg{1, 0, 0, static_cast<int16_t>((K2 + kBlockK - 1) / kBlockK), 0};
+    p.nseg = 2;
+    p.kb_total += p.seg[1].nkb;
+  }
+  for (int i = p.nseg; i < kMaxA; ++i) p.tmA[i] = p.tmA[0];
+  IgemmEpilogue e;
+  e.bias = bias; e.bias_bstride = bias_bstride; e.rows_per_batch = static_cast<int>(rows_per_batch);
+  e.resid = resid; e.ldr = ldr; e.out = out; e.ldo = ldo; e.out_f32 = out_f32; e.act = act; e.alpha = alpha;
+  return run_igemm(p, W, N, K + (A2 ? K2 : 0), ldw, e, bn, ksplit, workspace, ws_bytes,
+                   reinterpret_cast<cudaStream_t>(stream));
+}
+
+// 3x3 convolution on NHWC bf16 as implicit GEMM.
+//   mode 0: stride 1, pad 1                       (out H x W)
+//   mode 1: stride 2, pad 1                       (out H/2 x W/2)      openaimodel.py:150-152
+//   mode 2: stride 2, pad (0,1,0,1) then pad 0    (out H/2 x W/2)      autokl_modules.py:72-76
+// Wt is [N, 9*C + Cs1 + Cs2] bf16 with K ordered (ky, kx, c) then the 1x1-skip columns.
+// skip1/skip2: optional raw NHWC tensors at OUTPUT resolution whose 1x1 conv is accumulated too.
+int vdb_conv3x3_bf16(const void* X, int B, int H, int Wd, int C, int mode, const void* Wt, int N, long long ldw,
+                     const void* skip1, int Cs1, const void* skip2, int Cs2, const float* bias,
+                     long long bias_bstride, const void* resid, long long ldr, void* out, long long ldo,
+                     int out_f32, int act, int bn, int ksplit, void* workspace, size_t ws_bytes, void* stream) {
+  if (!X || !Wt || !out || B <= 0 || H <= 0 || Wd <= 0 || C <= 0 || N <= 0)
+    return set_error(VDB_ERR_INVALID, "conv3x3: null/empty argument");
+  if ((C % kBlockK) || (ldw % 8)) return set_error(VDB_ERR_INVALID, "conv3x3: C must be a multiple of 64, ldw of 8");
+  if ((skip1 && (Cs1 % kBlockK)) || (skip2 && (Cs2 % kBlockK)))
+    return set_error(VDB_ERR_INVALID, "conv3x3: skip channels must be multiples of 64");
+  if (mode < 0 || mode > 2) return set_error(VDB_ERR_INVALID, "conv3x3: bad mode");
+  if (mode != 0 && ((H & 1) || (Wd & 1))) return set_error(VDB_ERR_UNSUPPORTED, "conv3x3: stride 2 needs even H, W");
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int Ho = mode ? H / 2 : H, Wo = mode ? Wd / 2 : Wd;
+  set_tile_shape(p, Wo, Ho, B);
+  const uint64_t eb = 2;
+  const int nkb = C / kBlockK;
+  int rc;
+  int nmaps = 0;
+  if (mode == 0) {
+    rc = make_tmap_4d(&p.tmA[0], X, C, Wd, H, B, C * eb, (uint64_t)Wd * C * eb, (uint64_t)H * Wd * C * eb, kBlockK,
+                      p.TW, p.TH, p.TB);
+    if (rc) return rc;
+    nmaps = 1;
+    for (int t = 0; t < 9; ++t)
+      p.seg[t] = ASeg{0, static_cast<int16_t>(t % 3 - 1), static_cast<int16_t>(t / 3 - 1), static_cast<int16_t>(nkb), 0};
+  } else {
+    // four parity sub-lattices of the input: X[b, 2*yo+py, 2*xo+px, c]
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(X) + (static_cast<uint64_t>(py) * Wd + px) * C * eb;
+        rc = make_tmap_4d(&p.tmA[py * 2 + px], base, C, Wo, Ho, B, 2ull * C * eb, 2ull * Wd * C * eb,
+                          (uint64_t)H * Wd * C * eb, kBlockK, p.TW, p.TH, p.TB);
+        if (rc) return rc;
+      }
+    nmaps = 4;
+    for (int t = 0; t < 9; ++t) {
+      const int ky = t / 3, kx = t % 3;
+      int py, dy, px, dx;
+      if (mode == 1) {  // input row = 2*yo + ky - 1
+        py = (ky == 1) ? 0 : 1; dy = (ky == 0) ? -1 : 0;
+        px = (kx == 1) ? 0 : 1; dx = (kx == 0) ? -1 : 0;
+      } else {          // input row = 2*yo + ky (zero pad on bottom/right only)
+        py = (ky == 1) ? 1 : 0; dy = (ky == 2) ? 1 : 0;
+        px = (kx == 1) ? 1 : 0; dx = (kx == 2) ? 1 : 0;
+      }
+      p.seg[t] = ASeg{static_cast<int16_t>(py * 2 + px), static_cast<int16_t>(dx), static_cast<int16_t>(dy),
+                      static_cast<int16_t>(nkb), 0};
+    }
+  }
+  p.nseg = 9;
+  p.kb_total = 9 * nkb;
+  const void* sk[2] = {skip1, skip2};
+  const int sc[2] = {Cs1, Cs2};
+  for (int i = 0; i < 2; ++i) {
+    if (!sk[i]) continue;
+    rc = make_tmap_4d(&p.tmA[nmaps], sk[i], sc[i], Wo, Ho, B, sc[i] * eb, (uint64_t)Wo * sc[i] * eb,
+                      (uint64_t)Ho * Wo * sc[i] * eb, kBlockK, p.TW, p.TH, p.TB);
+    if (rc) return rc;
+    p.seg[p.nseg] = ASeg{static_cast<int16_t>(nmaps), 0, 0, static_cast<int16_t>(sc[i] / kBlockK), 0};
+    p.kb_total += sc[i] / kBlockK;
+    ++p.nseg;
+    ++nmaps;
+  }
+  for (int i = nmaps; i < kMaxA; ++i) p.tmA[i] = p.tmA[0];
+  IgemmEpilogue e;
+  e.bias = bias; e.bias_bstride = bias_bstride; e.rows_per_batch = Ho * Wo;
+  e.resid = resid; e.ldr = ldr; e.out = out; e.ldo = ldo; e.out_f32 = out_f32; e.act = act; e.alpha = 1.f;
+  return run_igemm(p, Wt, N, static_cast<long long>(p.kb_total) * kBlockK, ldw, e, bn, ksplit, workspace, ws_bytes,
+                   reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,56 @@
+"""ctypes loader for libvdb200.so; declares every symbol of include/vdb200.h."""
+import ctypes as C
+import os
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libvdb200.so")
+
+
+class VdbError(RuntimeError):
+    pass
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(nvcc, sm_100a). vdb200 has no CPU / library fallback by design.")
+
+lib = C.CDLL(LIB_PATH)
+
+p, i, ll, f, sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
+
+SIGNATURES = {
+    "vdb_version": (C.c_char_p, []),
+    "vdb_last_error": (C.c_char_p, []),
+    "vdb_launch_count": (ll, []),
+    "vdb_reset_launch_count": (None, []),
+    "vdb_num_sms": (i, []),
+    "vdb_ddim_cfg_step": (i, [p, p, p, p, p, p, f, f, p, p, ll, p]),
+    "vdb_add_int": (i, [p, i, p]),
+    "vdb_gemm_bf16": (i, [p, ll, ll, ll, p, ll, ll, p, ll, ll, p, ll, ll, p, ll, p, ll, i, i, f, i, i, p, sz, p]),
+    "vdb_conv3x3_bf16": (i, [p, i, i, i, i, i, p, i, ll, p, i, p, i, p, ll, p, ll, p, ll, i, i, i, i, p, sz, p]),
+    "vdb_attention_dk_pad": (i, [i]),
+    "vdb_attention_dv_pad": (i, [i]),
+    "vdb_attention_bf16": (i, [p, ll, i, p, ll, i, p, ll, p, ll, i, i, i, i, i, f, i, p]),
+    "vdb_groupnorm_nsplit": (i, [i, i]),
+    "vdb_groupnorm_nhwc": (i, [p, i, p, i, i, i, i, p, p, f, i, p, p, p]),
+    "vdb_layernorm": (i, [p, ll, i, p, p, f, p, p]),
+    "vdb_upsample2x_nhwc": (i, [p, i, i, i, i, p, p]),
+    "vdb_im2col3x3_small": (i, [p, i, i, i, i, i, f, f, p, p]),
+    "vdb_permute_f32": (i, [p, i, i, ll, i, f, f, i, p, p]),
+    "vdb_cast_f32_bf16": (i, [p, p, ll, p]),
+    "vdb_cast_bf16_f32": (i, [p, p, ll, p]),
+    "vdb_timestep_embedding": (i, [p, p, i, i, f, p, p]),
+    "vdb_linear_small": (i, [p, i, i, p, i, p, i, i, p, p]),
+    "vdb_softmax_rows": (i, [p, ll, i, ll, f, p, p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here == header/library mismatch: fail loudly
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = lib.vdb_last_error().decode("utf-8", "replace")
+        raise VdbError(f"vdb200 {what} failed with status {status}: {msg}")

@@ -1,0 +1,266 @@
+"""Torch-tensor front end of the vdb200 C ABI (include/vdb200.h).
+
+torch is used here for device memory, streams and allocation only; every arithmetic op on the hot
+path is a kernel of libvdb200.so.  All functions enqueue on torch's current CUDA stream and are
+CUDA-graph capturable (no host syncs, scratch comes from the caller or torch's caching allocator).
+"""
+import math
+
+import torch
+
+from ._lib import lib, check
+
+ACT_NONE, ACT_SILU, ACT_GELU, ACT_QUICK_GELU, ACT_GEGLU = 0, 1, 2, 3, 4
+BF16 = torch.bfloat16
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _need(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise ValueError(f"{name}: vdb200 kernels need CUDA tensors (no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: must be contiguous")
+
+
+_workspace = {}
+
+
+def workspace(nbytes, device):
+    """Grow-only fp32 scratch for split-K partials (per device)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    w = _workspace.get(key)
+    if w is None or w.numel() * 4 < nbytes:
+        w = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
+        _workspace[key] = w
+    return w
+
+
+def launch_count():
+    return int(lib.vdb_launch_count())
+
+
+def reset_launch_count():
+    lib.vdb_reset_launch_count()
+
+
+# ------------------------------------------------------------------------------------------------
+def ddim_cfg_step(e_uncond, e_cond, x, coef, scale, x_prev=None, pred_x0=None, noise=None,
+                  temperature=1.0, step_idx=None):
+    """K4 (ddim.py:144-171). e_*/x/noise fp32 same shape; coef fp32 [.,4] device tensor."""
+    for n, t in (("e_uncond", e_uncond), ("e_cond", e_cond), ("x", x), ("noise", noise), ("coef", coef)):
+        _need(t, torch.float32, n)
+    if x_prev is None:
+        x_prev = torch.empty_like(x)
+    if step_idx is not None:
+        _need(step_idx, torch.int32, "step_idx")
+    check(lib.vdb_ddim_cfg_step(_ptr(e_uncond), _ptr(e_cond), _ptr(x), _ptr(noise), _ptr(coef), _ptr(step_idx),
+                                float(scale), float(temperature), _ptr(x_prev), _ptr(pred_x0), x.numel(), _stream()),
+          "ddim_cfg_step")
+    return x_prev, pred_x0
+
+
+def add_int(t, delta):
+    _need(t, torch.int32, "counter")
+    check(lib.vdb_add_int(_ptr(t), int(delta), _stream()), "add_int")
+
+
+def gemm(a, w, bias=None, resid=None, out=None, act=ACT_NONE, a2=None, out_dtype=BF16, alpha=1.0,
+         bias_bstride=0, rows_per_batch=1, bn=0, ksplit=0):
+    """out[M,N'] = act(alpha*[a|a2] @ w^T + bias) + resid ; a [M,K] bf16, w [N,K(+K2)] bf16."""
+    _need(a, BF16, "a"); _need(w, BF16, "w"); _need(a2, BF16, "a2"); _need(bias, torch.float32, "bias")
+    _need(resid, BF16, "resid")
+    M, K = a.shape
+    N = w.shape[0]
+    K2 = a2.shape[1] if a2 is not None else 0
+    assert w.shape[1] == K + K2, (w.shape, K, K2)
+    n_out = N // 2 if act == ACT_GEGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=out_dtype, device=a.device)
+    _need(out, out_dtype, "out")
+    ws = None
+    ws_bytes = 0
+    if ksplit != 1:
+        ws_bytes = 16 * M * N * 4 if M * N * 64 <= (1 << 28) else 0
+        ws_bytes = min(ws_bytes, 256 << 20)
+        if M > 4096:  # split-K only ever triggers for small MN grids
+            ws_bytes = 0
+        if ws_bytes:
+            ws = workspace(ws_bytes, a.device)
+    check(lib.vdb_gemm_bf16(_ptr(a), M, K, a.stride(0), _ptr(a2), K2, a2.stride(0) if a2 is not None else 0,
+                            _ptr(w), N, w.stride(0), _ptr(bias), int(bias_bstride), int(rows_per_batch),
+                            _ptr(resid), resid.stride(0) if resid is not None else 0, _ptr(out), out.stride(0),
+                            1 if out_dtype == torch.float32 else 0, int(act), float(alpha), int(bn), int(ksplit),
+                            _ptr(ws), ws_bytes, _stream()), "gemm_bf16")
+    return out
+
+
+def conv3x3(x, w, bias=None, resid=None, out=None, mode=0, skip1=None, skip2=None, act=ACT_NONE,
+            out_dtype=BF16, bias_bstride=0, bn=0, ksplit=0):
+    """3x3 conv on NHWC bf16 x [B,H,W,C]; w [N, 9*C + Cs1 + Cs2] packed (ky,kx,c | skip)."""
+    _need(x, BF16, "x"); _need(w, BF16, "w"); _need(bias, torch.float32, "bias")
+    _need(resid, BF16, "resid"); _need(skip1, BF16, "skip1"); _need(skip2, BF16, "skip2")
+    B, H, W, Cc = x.shape
+    N = w.shape[0]
+    Ho, Wo = (H // 2, W // 2) if mode else (H, W)
+    cs1 = skip1.shape[-1] if skip1 is not None else 0
+    cs2 = skip2.shape[-1] if skip2 is not None else 0
+    assert w.shape[1] == 9 * Cc + cs1 + cs2, (w.shape, Cc, cs1, cs2)
+    if out is None:
+        out = torch.empty((B, Ho, Wo, N), dtype=out_dtype, device=x.device)
+    M = B * Ho * Wo
+    ws, ws_bytes = None, 0
+    if ksplit != 1 and M <= 4096:
+        ws_bytes = 16 * M * N * 4
+        ws = workspace(ws_bytes, x.device)
+    check(lib.vdb_conv3x3_bf16(_ptr(x), B, H, W, Cc, int(mode), _ptr(w), N, w.stride(0), _ptr(skip1), cs1,
+                               _ptr(skip2), cs2, _ptr(bias), int(bias_bstride), _ptr(resid),
+                               resid.shape[-1] if resid is not None else 0, _ptr(out), out.shape[-1],
+                               1 if out_dtype == torch.float32 else 0, int(act), int(bn), int(ksplit), _ptr(ws),
+                               ws_bytes, _stream()), "conv3x3_bf16")
+    return out
+
+
+def attention_pads(d_head):
+    dk, dv = lib.vdb_attention_dk_pad(d_head), lib.vdb_attention_dv_pad(d_head)
+    if dk < 0 or dv < 0:
+        raise ValueError(f"d_head {d_head} unsupported by the attention kernel")
+    return dk, dv
+
+
+def attention(q, k, vt, out, B, H, Nq, Nk, d_head, scale=None, q_col0=0, k_col0=0, causal=False):
+    """Flash attention. q [B*Nq, ldq], k [B*Nk, ldk], vt [H*DVP, >=B*Nk], out [B*Nq, H*d_head]."""
+    _need(q, BF16, "q"); _need(k, BF16, "k"); _need(vt, BF16, "vt"); _need(out, BF16, "out")
+    if scale is None:
+        scale = d_head ** -0.5
+    check(lib.vdb_attention_bf16(_ptr(q), q.stride(0), int(q_col0), _ptr(k), k.stride(0), int(k_col0), _ptr(vt),
+                                 vt.stride(0), _ptr(out), out.stride(0), B, H, Nq, Nk, d_head, float(scale),
+                                 1 if causal else 0, _stream()), "attention_bf16")
+    return out
+
+
+def groupnorm(x1, gamma, beta, eps, act=ACT_NONE, x2=None, out=None, groups=32):
+    """GN32(+SiLU) over NHWC bf16 [B,H,W,C1] (+ concat x2 [B,H,W,C2]) -> [B,H,W,C1+C2]."""
+    _need(x1, BF16, "x1"); _need(x2, BF16, "x2"); _need(gamma, torch.float32, "gamma"); _need(beta, torch.float32, "beta")
+    B = x1.shape[0]
+    C1 = x1.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    HW = x1.numel() // (B * C1)
+    if out is None:
+        out = torch.empty(x1.shape[:-1] + (C1 + C2,), dtype=BF16, device=x1.device)
+    nsplit = lib.vdb_groupnorm_nsplit(B, HW)
+    partial = torch.empty(B * nsplit * 2 * groups, dtype=torch.float32, device=x1.device)
+    check(lib.vdb_groupnorm_nhwc(_ptr(x1), C1, _ptr(x2), C2, B, HW, groups, _ptr(gamma), _ptr(beta), float(eps),
+                                 int(act), _ptr(partial), _ptr(out), _stream()), "groupnorm_nhwc")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    _need(x, BF16, "x"); _need(gamma, torch.float32, "gamma"); _need(beta, torch.float32, "beta")
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.vdb_layernorm(_ptr(x), rows, C, _ptr(gamma), _ptr(beta), float(eps), _ptr(out), _stream()), "layernorm")
+    return out
+
+
+def upsample2x(x, out=None):
+    _need(x, BF16, "x")
+    B, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((B, 2 * H, 2 * W, C), dtype=BF16, device=x.device)
+    check(lib.vdb_upsample2x_nhwc(_ptr(x), B, H, W, C, _ptr(out), _stream()), "upsample2x")
+    return out
+
+
+def im2col3x3_small(x, kpad=64, in_scale=1.0, in_shift=0.0, out=None):
+    """x fp32 NHWC [B,H,W,Cin<=7] -> bf16 [B*H*W, kpad]."""
+    _need(x, torch.float32, "x")
+    B, H, W, Cin = x.shape
+    if out is None:
+        out = torch.empty((B * H * W, kpad), dtype=BF16, device=x.device)
+    check(lib.vdb_im2col3x3_small(_ptr(x), B, H, W, Cin, kpad, float(in_scale), float(in_shift), _ptr(out), _stream()),
+          "im2col3x3_small")
+    return out
+
+
+def nchw_to_nhwc(x, mul=1.0, add=0.0, out=None):
+    _need(x, torch.float32, "x")
+    B, C = x.shape[:2]
+    HW = x.numel() // (B * C)
+    if out is None:
+        out = torch.empty((B,) + tuple(x.shape[2:]) + (C,), dtype=torch.float32, device=x.device)
+    check(lib.vdb_permute_f32(_ptr(x), B, C, HW, 1, float(mul), float(add), 0, _ptr(out), _stream()), "permute")
+    return out
+
+
+def nhwc_to_nchw(x, mul=1.0, add=0.0, clamp01=False, out=None):
+    _need(x, torch.float32, "x")
+    B, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * C)
+    if out is None:
+        out = torch.empty((B, C) + tuple(x.shape[1:-1]), dtype=torch.float32, device=x.device)
+    check(lib.vdb_permute_f32(_ptr(x), B, C, HW, 0, float(mul), float(add), 1 if clamp01 else 0, _ptr(out), _stream()),
+          "permute")
+    return out
+
+
+def to_bf16(x, out=None):
+    _need(x, torch.float32, "x")
+    if out is None:
+        out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    check(lib.vdb_cast_f32_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "cast")
+    return out
+
+
+def to_f32(x, out=None):
+    _need(x, BF16, "x")
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    check(lib.vdb_cast_bf16_f32(_ptr(x), _ptr(out), x.numel(), _stream()), "cast")
+    return out
+
+
+def timestep_embedding(ts, dim, max_period=10000, step_idx=None, batch=None, out=None):
+    """ts int64 device tensor [B] (or a table + step_idx int32 device scalar, broadcast to `batch` rows)."""
+    _need(ts, torch.int64, "timesteps")
+    B = batch if step_idx is not None else ts.shape[0]
+    if out is None:
+        out = torch.empty((B, dim), dtype=torch.float32, device=ts.device)
+    nlp = torch.tensor(-math.log(max_period), dtype=torch.float32).item()
+    check(lib.vdb_timestep_embedding(_ptr(ts), _ptr(step_idx), B, dim, nlp, _ptr(out), _stream()), "timestep_embedding")
+    return out
+
+
+def linear_small(x, w, bias=None, act_in=ACT_NONE, act_out=ACT_NONE, out=None):
+    """x fp32 [M<=16,K], w bf16 [N,K] -> fp32 [M,N]."""
+    _need(x, torch.float32, "x"); _need(w, BF16, "w"); _need(bias, torch.float32, "bias")
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    check(lib.vdb_linear_small(_ptr(x), M, K, _ptr(w), N, _ptr(bias), int(act_in), int(act_out), _ptr(out), _stream()),
+          "linear_small")
+    return out
+
+
+def softmax_rows(x, scale=1.0, out=None):
+    _need(x, BF16, "x")
+    n = x.shape[-1]
+    rows = x.numel() // n
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.vdb_softmax_rows(_ptr(x), rows, n, x.stride(-2) if x.dim() > 1 else n, float(scale), _ptr(out), _stream()),
+          "softmax_rows")
+    return out
