@@ -38,15 +38,19 @@ int vdb_num_sms(void);
  * x_prev = sqrt(a_prev) pred_x0 + sqrt(1 - a_prev - sigma^2) e + sigma*noise*temperature.
  * coef: device fp32 {a_t, a_prev, sigma_t, sqrt_one_minus_a_t}[, more rows]; step_idx (device int,
  * may be NULL) selects the row, so one captured CUDA graph serves every step. e_uncond/noise/pred_x0
- * may be NULL (scale==1 path, eta==0, no pred_x0 wanted). fp32, bit-identical to the reference ops. */
+ * may be NULL (scale==1 path, eta==0, no pred_x0 wanted). x_prev may alias x (in place); x_prev_dup (may be
+ * NULL) receives a second copy — the cond half of the next step's torch.cat([x]*2) (ddim.py:144).
+ * fp32, bit-identical to the reference ops. */
 int vdb_ddim_cfg_step(const float* e_uncond, const float* e_cond, const float* x, const float* noise,
                       const float* coef, const int* step_idx, float scale, float temperature, float* x_prev,
-                      float* pred_x0, long long n, void* stream);
+                      float* x_prev_dup, float* pred_x0, long long n, void* stream);
+/* y = a*x + b*z, fp32 — VD_v2_0.q_sample (vd.py:221-224) for the img2img start (ddim.py:97-103) */
+int vdb_axpby_f32(const float* x, const float* z, float a, float b, float* y, long long n, void* stream);
 int vdb_add_int(int* p, int delta, void* stream); /* device-side step counter update */
 
 /* ---- tcgen05 GEMM — nn.Linear / 1x1 conv call sites: attention.py:37-64,161-193,237,249;
  *      autokl_modules.py:150-202; HF CLIP q/k/v/out/fc1/fc2 (clip.py:58-61,92-100) ----------------
- * out[M,N] = act(alpha * [A | A2] @ W^T + bias) + resid.   A [M,K] (lda), optional A2 [M,K2] (lda2)
+ * out[M,N] = act(alpha * ([A | A2] @ W^T + bias)) + resid.   A [M,K] (lda), optional A2 [M,K2] (lda2)
  * concatenated along K, W [N, K+K2] (ldw).  bias fp32 [N] (bias_bstride==0) or per-batch rows
  * [.., N] selected by row / rows_per_batch.  act = VDB_ACT_*; VDB_ACT_GEGLU expects W/bias rows packed
  * per 256-column tile as 128 value rows then their 128 gate rows and writes N/2 columns
@@ -75,12 +79,15 @@ int vdb_conv3x3_bf16(const void* X, int B, int H, int W, int C, int mode, const 
  * Q [B*Nq, ldq] head h at columns q_col0 + h*DK; K [B*Nk, ldk] at k_col0 + h*DK;
  * Vt [H*DVP, ldv] row h*DVP + c, column b*Nk + j; out [B*Nq, ldo] head h at columns h*d_head.
  * DK = vdb_attention_dk_pad(d_head), DVP = vdb_attention_dv_pad(d_head); pad columns/rows must be
- * zero (the projection weights are zero-padded at pack time). causal != 0: CLIP text mask. */
+ * zero (the projection weights are zero-padded at pack time). causal != 0: CLIP text mask.
+ * Batch b starts at row b*q_bstride of Q/out and at row (K) / column (Vt) b*kv_bstride; kv_bstride must be a
+ * multiple of 8 (TMA: 16-byte aligned innermost coordinate), so ragged contexts (77, 257 tokens) are stored
+ * padded to 80 / 264 per batch item; the pad keys are masked by Nk. 0 = dense (stride = count). */
 int vdb_attention_dk_pad(int d_head);
 int vdb_attention_dv_pad(int d_head);
 int vdb_attention_bf16(const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0,
                        const void* Vt, long long ldv, void* out, long long ldo, int B, int H, int Nq, int Nk,
-                       int d_head, float scale, int causal, void* stream);
+                       int q_bstride, int kv_bstride, int d_head, float scale, int causal, void* stream);
 
 /* ---- GroupNorm(32) [+SiLU] [+channel concat] on NHWC — normalization()/Normalize():
  *      diffusion_utils.py:168-191 (eps 1e-5), attention.py:76-77 & autokl_modules.py:38-39 (1e-6) ----
@@ -104,7 +111,15 @@ int vdb_im2col3x3_small(const float* x, int B, int H, int W, int Cin, int Kpad, 
 /* ---- fp32 NCHW <-> NHWC permute with y = x*mul + add [clamped to [0,1]] (autokl.py:47) ------------ */
 int vdb_permute_f32(const float* x, int B, int C, long long HW, int to_nhwc, float mul, float add, int clamp01,
                     float* y, void* stream);
+/* DiagonalGaussianDistribution.sample (distributions.py:24-37) fused with the latent scale of vae_encode
+ * (vd.py:282-289): z = (mean + exp(0.5*clamp(logvar,-30,20)) * noise) * post_mul on NHWC fp32 moments [npix,2C] */
+int vdb_gaussian_sample(const float* moments, const float* noise, int C, long long npix, float post_mul, float* z,
+                        void* stream);
 int vdb_cast_f32_bf16(const float* x, void* y, long long n, void* stream);
+/* tiny 1x1 conv on fp32 NHWC: y = W (x*pre_mul) + b — quant_conv / post_quant_conv, autokl.py:26-27,36,45 and
+ * the 1/latent_scale_factor of VD_v2_0.vae_decode, vd.py:291-296 */
+int vdb_pointwise_small(const float* x, long long npix, int Cin, int Cout, const float* Wm, const float* bias,
+                        float pre_mul, float* y, void* stream);
 int vdb_cast_bf16_f32(const void* x, float* y, long long n, void* stream);
 
 /* ---- timestep_embedding [cos|sin] — diffusion_utils.py:131-151 ---------------------------------

@@ -195,18 +195,21 @@ def test_conv3x3_resblock_tail():
 
 
 def build_attention_inputs(ops, q, k, v):
-    """q [B,H,Nq,d], k/v [B,H,Nk,d] fp32 -> padded kernel layouts"""
+    """q [B,H,Nq,d], k/v [B,H,Nk,d] fp32 -> padded kernel layouts (kv stride padded to 8 per batch item)"""
     B, H, Nq, d = q.shape
     Nk = k.shape[2]
+    Nkp = (Nk + 7) // 8 * 8
     dk, dv = ops.attention_pads(d)
     Q = torch.zeros(B * Nq, H * dk, dtype=torch.bfloat16, device=DEV)
-    K = torch.zeros(B * Nk, H * dk, dtype=torch.bfloat16, device=DEV)
-    ldv = (B * Nk + 7) // 8 * 8
-    Vt = torch.zeros(H * dv, ldv, dtype=torch.bfloat16, device=DEV)
+    K = torch.zeros(B * Nkp, H * dk, dtype=torch.bfloat16, device=DEV)
+    Vt = torch.zeros(H * dv, B * Nkp, dtype=torch.bfloat16, device=DEV)
     Q.view(B, Nq, H, dk)[..., :d] = q.permute(0, 2, 1, 3).to(torch.bfloat16)
-    K.view(B, Nk, H, dk)[..., :d] = k.permute(0, 2, 1, 3).to(torch.bfloat16)
-    Vt.view(H, dv, ldv)[:, :d, :B * Nk] = v.permute(1, 3, 0, 2).reshape(H, d, B * Nk).to(torch.bfloat16)
-    return Q, K, Vt
+    K.view(B, Nkp, H, dk)[:, :Nk, :, :d] = k.permute(0, 2, 1, 3).to(torch.bfloat16)
+    Vt.view(H, dv, B, Nkp)[:, :d, :, :Nk] = v.permute(1, 3, 0, 2).to(torch.bfloat16)
+    if Nkp != Nk:  # poison the pad keys: the kernel must mask them, not rely on zeros
+        K.view(B, Nkp, H, dk)[:, Nk:] = 7.0
+        Vt.view(H, dv, B, Nkp)[:, :, :, Nk:] = 1000.0
+    return Q, K, Vt, Nkp
 
 
 ATT_CASES = [
@@ -220,7 +223,7 @@ ATT_CASES = [
     (2, 8, 1024, 1028, 80, False),
     (2, 12, 77, 77, 64, True),
     (2, 16, 257, 257, 64, False),
-    (1, 8, 4096, 77, 40, False),
+    (3, 8, 4096, 77, 40, False),
 ]
 
 
@@ -229,9 +232,9 @@ def test_attention(B, H, Nq, Nk, d, causal):
     ops = _ops()
     q, k, v = (rnd(B, H, n, d, seed=s, dtype=torch.float32) for s, n in ((1, Nq), (2, Nk), (3, Nk)))
     q = q * 2.0  # make the softmax peaky enough to exercise the rescale path
-    Q, K, Vt = build_attention_inputs(ops, q, k, v)
+    Q, K, Vt, Nkp = build_attention_inputs(ops, q, k, v)
     out = torch.empty(B * Nq, H * d, dtype=torch.bfloat16, device=DEV)
-    ops.attention(Q, K, Vt, out, B, H, Nq, Nk, d, causal=causal)
+    ops.attention(Q, K, Vt, out, B, H, Nq, Nk, d, causal=causal, kv_bstride=Nkp)
     qb, kb, vb = (t.to(torch.bfloat16).float() for t in (q, k, v))
     sim = torch.einsum("bhid,bhjd->bhij", qb, kb) * d ** -0.5
     if causal:
@@ -296,7 +299,7 @@ def test_timestep_embedding_and_linear_small():
     freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half).to(DEV)
     args = ts[:, None].float() * freqs[None]
     ref = torch.cat([torch.cos(args), torch.sin(args)], -1)
-    assert (emb - ref).abs().max().item() <= 2e-5   # fp32 sin/cos of arguments up to 1e3
+    assert (emb - ref).abs().max().item() <= 2e-4   # fp32 sin/cos of arguments up to 1e3 (1 ulp of freq moves the argument by 1e-4)
     table = torch.tensor([981, 961, 941], dtype=torch.int64, device=DEV)
     idx = torch.tensor([1], dtype=torch.int32, device=DEV)
     emb2 = ops.timestep_embedding(table, 320, step_idx=idx, batch=4)

@@ -1,0 +1,215 @@
+"""Parity of the CUDA path (through the lib.model_zoo drop-in surface -> C ABI) against
+  (1) the committed golden fixtures produced by the UNMODIFIED reference (tests/golden/*.npz), and
+  (2) the CPU oracle restatement (oracle/vd_oracle.py) on fresh seeded inputs.
+
+Tolerances (stated per SURVEY.md §8c): the product computes in bf16 with fp32 accumulation, the
+reference/oracle in fp32.  Single UNet forward / VAE pass: cosine >= 0.999 and max|err| <= 3e-2 * max|ref|;
+multi-step DDIM trajectories amplify rounding, so the 5/10-step latents are held to cosine >= 0.995.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+DEV = "cuda"
+
+
+def _cmp(out, ref, cos_min=0.999, tol=3e-2, what=""):
+    out = torch.as_tensor(out).float().cpu().flatten()
+    ref = torch.as_tensor(ref).float().cpu().flatten()
+    assert torch.isfinite(out).all(), f"{what}: non-finite"
+    cos = F.cosine_similarity(out, ref, dim=0).item()
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-12
+    print(f"[parity] {what}: cos {cos:.6f} max|err| {err:.4g} / {scale:.4g}")
+    assert cos >= cos_min and err <= tol * scale, f"{what}: cos {cos:.6f}, max err {err:.4g} vs scale {scale:.4g}"
+
+
+def build_net(mini=True, with_vae=True):
+    from lib.cfg_helper import model_cfg_bank
+    from lib.model_zoo import get_model
+    from oracle import weights
+    from oracle.make_golden import MINI_UNET, MINI_VAE, WEIGHT_SEED
+    cfg = model_cfg_bank()('vd_four_flow_v1-0')
+    cfg.args.ctx_cfg_list = []
+    if not with_vae:
+        cfg.args.vae_cfg_list = []
+    if mini:
+        for _, d in cfg.args.diffuser_cfg_list:
+            d.args.update(MINI_UNET)
+        if with_vae:
+            cfg.args.vae_cfg_list[0][1].args.ddconfig.update(MINI_VAE)
+    net = get_model()(cfg, verbose=False)
+    shapes = weights.param_shapes(net)
+    sd = weights.synth_state_dict(shapes, seed=WEIGHT_SEED)
+    res = net.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys
+    assert all(k.split(".")[0] not in ("vae", "diffuser") for k in res.missing_keys), res.missing_keys
+    net.eval()
+    net.to(DEV)
+    return net, sd
+
+
+@pytest.fixture(scope="module")
+def mini():
+    net, sd = build_net(mini=True)
+    from oracle.make_golden import golden_inputs
+    gold = dict(np.load(os.path.join(GOLD, "mini.npz")))
+    return net, sd, golden_inputs("mini"), gold
+
+
+def test_state_dict_keys_match_reference():
+    """checkpoint ABI: our parameter names/shapes == the reference's (fixture dumped from the reference)."""
+    from oracle import weights
+    for name, mini_flag in (("keys_mini.json", True), ("keys_full.json", False)):
+        path = os.path.join(GOLD, name)
+        if not os.path.exists(path):
+            pytest.skip(f"{name} not generated")
+        ref = {k: tuple(v) for k, v in json.load(open(path)).items()}
+        if not mini_flag:
+            continue  # full-size construction is covered by test_c1_full
+        net, _ = build_net(mini=True)
+        ours = weights.param_shapes(net)
+        assert set(ours) == set(ref), (sorted(set(ours) ^ set(ref))[:10])
+        assert all(ours[k] == ref[k] for k in ref)
+
+
+def test_apply_model_text_vs_reference_golden(mini):
+    net, sd, gi, gold = mini
+    with torch.no_grad():
+        out = net.apply_model({"type": "image", "x": gi["x"].to(DEV)}, gi["t"].to(DEV),
+                              {"type": "text", "c": gi["c_text"].to(DEV)})
+    _cmp(out, gold["eps_text"], what="apply_model text ctx (reference golden)")
+
+
+def test_apply_model_image_ctx_vs_reference_golden(mini):
+    net, sd, gi, gold = mini
+    with torch.no_grad():
+        out = net.apply_model({"type": "image", "x": gi["x"].to(DEV)}, gi["t"].to(DEV),
+                              {"type": "image", "c": gi["c_img"].to(DEV)})
+    _cmp(out, gold["eps_image"], what="apply_model image ctx (reference golden)")
+
+
+def test_apply_model_multicontext_vs_reference_golden(mini):
+    net, sd, gi, gold = mini
+    with torch.no_grad():
+        out = net.apply_model_multicontext(
+            {"type": "image", "x": gi["x"].to(DEV)}, gi["t"].to(DEV),
+            [{"type": "text", "c": gi["c_text"].to(DEV), "ratio": 0.7},
+             {"type": "image", "c": gi["c_img"].to(DEV), "ratio": 0.3}])
+    _cmp(out, gold["eps_dual"], what="apply_model_multicontext (reference golden)")
+
+
+def test_unet_forward_matches_oracle_fresh_inputs(mini):
+    from oracle import vd_oracle as O
+    net, sd, gi, gold = mini
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(3, 4, 24, 24, generator=g)           # odd batch, non-power-of-two spatial size
+    t = torch.tensor([5, 500, 999])
+    c = torch.randn(3, 50, 768, generator=g) * 0.5        # ragged context length
+    with torch.no_grad():
+        ref = O.apply_model(sd, x, t, [c], model_channels=64)
+        out = net.apply_model({"type": "image", "x": x.to(DEV)}, t.to(DEV), {"type": "text", "c": c.to(DEV)})
+    _cmp(out, ref, what="apply_model vs oracle (24x24, B=3, L=50)")
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_ddim_5_steps_vs_reference_golden(mini, graph):
+    from lib.model_zoo.ddim import DDIMSampler
+    net, sd, gi, gold = mini
+    S = DDIMSampler(net, use_cuda_graph=graph)
+    with torch.no_grad():
+        x, inter = S.sample(steps=5, shape=[1, 4, 16, 16], x_info={"type": "image", "xt": gi["xT"]},
+                            c_info={"type": "text", "conditioning": gi["c"].to(DEV),
+                                    "unconditional_conditioning": gi["u"].to(DEV),
+                                    "unconditional_guidance_scale": 7.5}, verbose=False, eta=0., log_every_t=1)
+    _cmp(x, gold["ddim5_final"], cos_min=0.995, tol=0.1, what=f"5-step DDIM final latent (graph={graph})")
+    _cmp(inter["pred_x0"][0], gold["ddim5_pred_x0"][0], what="first-step pred_x0")
+    assert len(inter["pred_x0"]) == 5
+
+
+def test_ddim_graph_equals_eager_and_is_reusable(mini):
+    from lib.model_zoo.ddim import DDIMSampler
+    net, sd, gi, gold = mini
+    args = dict(steps=6, shape=[2, 4, 16, 16], verbose=False, eta=0.)
+    g = torch.Generator().manual_seed(3)
+    xT = torch.randn(2, 4, 16, 16, generator=g)
+    c, u = torch.randn(2, 77, 768, generator=g).to(DEV), torch.randn(2, 77, 768, generator=g).to(DEV)
+
+    def run(S):
+        with torch.no_grad():
+            return S.sample(x_info={"type": "image", "xt": xT.clone()},
+                            c_info={"type": "text", "conditioning": c, "unconditional_conditioning": u,
+                                    "unconditional_guidance_scale": 5.0}, **args)[0]
+    eager = run(DDIMSampler(net, use_cuda_graph=False))
+    Sg = DDIMSampler(net, use_cuda_graph=True)
+    g1, g2 = run(Sg), run(Sg)
+    assert torch.equal(g1, g2), "graph replay must be deterministic"
+    assert torch.equal(eager, g1), "graph path must be bit-identical to the eager path"
+
+
+def test_vae_decode_encode_vs_reference_golden(mini):
+    net, sd, gi, gold = mini
+    with torch.no_grad():
+        img = net.vae_decode(gi["z"].to(DEV), "image")
+        raw = net.vae["image"].decoder(net.vae["image"]._post_quant_nhwc(gi["z"].to(DEV), 1 / 0.18215))
+        post = net.vae["image"].encode(gi["img"].to(DEV), out_posterior=True)
+    _cmp(img, gold["vae_decode"], what="vae_decode (clamped image)")
+    _cmp(raw.permute(0, 3, 1, 2), gold["vae_decode_raw"], what="decoder output before clamp")
+    _cmp(post.parameters, gold["vae_moments"], what="vae_encode moments")
+
+
+def test_vae_encode_sample_matches_oracle(mini):
+    from oracle import vd_oracle as O
+    net, sd, gi, gold = mini
+    g = torch.Generator().manual_seed(4)
+    noise = torch.randn(1, 4, 8, 8, generator=g)
+    with torch.no_grad():
+        z = net.vae_encode(gi["img"].to(DEV), "image", noise=noise)
+        ref = O.vae_encode(sd, gi["img"], noise=noise)
+    _cmp(z, ref, what="vae_encode sample (scaled latent)")
+
+
+def test_timestep_embedding_vs_reference_golden(mini):
+    from lib.model_zoo.diffusion_utils import timestep_embedding
+    net, sd, gi, gold = mini
+    out = timestep_embedding(torch.tensor([1, 21, 501, 981], device=DEV), 320)
+    assert (out.cpu() - torch.as_tensor(gold["t_emb"])).abs().max().item() <= 2e-4
+
+
+def test_c1_full_config_vs_reference_golden():
+    """BASELINE config 1 at full size: t2i 256x256, 10-step DDIM, bs 1, CFG 7.5 — reference golden."""
+    path = os.path.join(GOLD, "c1_full.npz")
+    if not os.path.exists(path):
+        pytest.skip("c1_full.npz not generated")
+    from lib.model_zoo.ddim import DDIMSampler
+    from oracle.make_golden import golden_inputs
+    gold = dict(np.load(path))
+    net, sd = build_net(mini=False)
+    del sd
+    gi = golden_inputs("c1")
+    with torch.no_grad():
+        x_in = torch.cat([gi["xT"]] * 2).to(DEV)
+        eps0 = net.apply_model({"type": "image", "x": x_in}, torch.tensor([901, 901], device=DEV),
+                               {"type": "text", "c": torch.cat([gi["u"], gi["c"]]).to(DEV)})
+        _cmp(eps0, gold["eps0"], what="C1 first-step eps (full-size UNet)")
+        S = DDIMSampler(net)
+        x, inter = S.sample(steps=10, shape=[1, 4, 32, 32], x_info={"type": "image", "xt": gi["xT"]},
+                            c_info={"type": "text", "conditioning": gi["c"].to(DEV),
+                                    "unconditional_conditioning": gi["u"].to(DEV),
+                                    "unconditional_guidance_scale": 7.5}, verbose=False, eta=0.)
+        _cmp(x, gold["final"], cos_min=0.995, tol=0.1, what="C1 10-step final latent")
+        # decode the REFERENCE latent so the image comparison isolates the VAE
+        img = net.vae_decode(torch.as_tensor(gold["final"]).to(DEV), "image")
+    ref_img = torch.as_tensor(gold["image"].astype(np.float32))
+    mse = ((img.float().cpu() - ref_img) ** 2).mean().item()
+    psnr = 10 * np.log10(1.0 / max(mse, 1e-12))
+    print(f"[parity] C1 decoded image PSNR {psnr:.1f} dB")
+    assert psnr >= 30.0

@@ -12,6 +12,7 @@
 //               128B-swizzled shared memory (double buffered), lazy O rescale in TMEM, final
 //               normalise + store.
 // Operand layouts (all K-major, 128B swizzle, written by the projection GEMMs):
+// Batch b occupies rows [b*q_bs, b*q_bs+Nq) of Q/O, rows [b*kv_bs, +Nk) of K, columns [b*kv_bs, +Nk) of Vt.
 //   Q  [B*Nq, ldq]  head h at columns q_col0 + h*DK .. (+DK, zero padded beyond d_head)
 //   K  [B*Nk, ldk]  head h at columns k_col0 + h*DK ..
 //   Vt [H*DVP, >=B*Nk]  row h*DVP + c = channel c of head h (zero rows beyond d_head), column b*Nk + j
@@ -31,6 +32,7 @@ struct alignas(64) AttnParams {
   CUtensorMap tmK;   // 2D (cols, rows) box (64, 128)
   CUtensorMap tmV;   // 2D (kv, H*DVP) box (64, DVP)
   int Nq, Nk;        // per-batch query / key counts
+  int q_bs, kv_bs;   // per-batch row stride of Q/out, row (K) / column (Vt) stride of the keys (kv_bs % 8 == 0)
   int q_col0, k_col0;
   int dv;            // valid head channels (<= DVP)
   int causal;
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
       // Q tile
       mbar_arrive_expect_tx(q_full, kQBytes);
       for (int a = 0; a < KA; ++a)
-        tma_load_2d(sQ + a * kBQ * 128, &p.tmQ, q_full, p.q_col0 + head * DK + a * 64, b * p.Nq + q0);
+        tma_load_2d(sQ + a * kBQ * 128, &p.tmQ, q_full, p.q_col0 + head * DK + a * 64, b * p.q_bs + q0);
       // K / V rings
       for (int j = 0; j < ntiles; ++j) {
         const int st = j % KV_STAGES;
@@ -114,11 +116,11 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
         mbar_arrive_expect_tx(&k_full[st], kKBytes);
         for (int a = 0; a < KA; ++a)
           tma_load_2d(sK + st * kKBytes + a * kBKV * 128, &p.tmK, &k_full[st], p.k_col0 + head * DK + a * 64,
-                      b * p.Nk + j * kBKV);
+                      b * p.kv_bs + j * kBKV);
         mbar_wait(&v_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&v_full[st], kVBytes);
         for (int a = 0; a < 2; ++a)
-          tma_load_2d(sV + st * kVBytes + a * kVAtom, &p.tmV, &v_full[st], b * p.Nk + j * kBKV + a * 64, head * DVP);
+          tma_load_2d(sV + st * kVBytes + a * kVAtom, &p.tmV, &v_full[st], b * p.kv_bs + j * kBKV + a * 64, head * DVP);
       }
     }
   } else if (warp == 1) {
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
     tc_fence_after();
     const float inv_l = 1.f / l_sum;
     const bool row_ok = q_idx < p.Nq;
-    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.Nq + q_idx) * p.ldo + head * p.dv;
+    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.q_bs + q_idx) * p.ldo + head * p.dv;
 #pragma unroll 1
     for (int c = 0; c < DVP / 16; ++c) {
       uint32_t o[16];
@@ -326,22 +328,28 @@ int vdb_attention_dv_pad(int d_head) {
 
 int vdb_attention_bf16(const void* Q, long long ldq, int q_col0, const void* K, long long ldk, int k_col0,
                        const void* Vt, long long ldv, void* out, long long ldo, int B, int H, int Nq, int Nk,
-                       int d_head, float scale, int causal, void* stream) {
+                       int q_bstride, int kv_bstride, int d_head, float scale, int causal, void* stream) {
   if (!Q || !K || !Vt || !out || B <= 0 || H <= 0 || Nq <= 0 || Nk <= 0)
     return set_error(VDB_ERR_INVALID, "attention: null/empty argument");
   const int DK = vdb_attention_dk_pad(d_head), DVP = vdb_attention_dv_pad(d_head);
   if (DK < 0 || DVP < 0) return set_error(VDB_ERR_UNSUPPORTED, "attention: d_head %d not supported (<= 160)", d_head);
   if ((d_head % 8) || (ldo % 8) || (ldq % 8) || (ldk % 8) || (ldv % 8))
     return set_error(VDB_ERR_INVALID, "attention: d_head and leading dims must be multiples of 8");
+  if (q_bstride <= 0) q_bstride = Nq;
+  if (kv_bstride <= 0) kv_bstride = Nk;
+  // TMA needs the innermost box coordinate (the kv column of V^T) on a 16-byte boundary
+  if (q_bstride < Nq || kv_bstride < Nk || (kv_bstride % 8))
+    return set_error(VDB_ERR_INVALID, "attention: need q_bstride >= Nq, kv_bstride >= Nk and kv_bstride %% 8 == 0 (got %d, %d)",
+                     q_bstride, kv_bstride);
   AttnParams p;
   memset(&p, 0, sizeof(p));
-  int rc = make_tmap_2d(&p.tmQ, Q, static_cast<uint64_t>(ldq), static_cast<uint64_t>(B) * Nq, ldq * 2, 64, kBQ);
+  int rc = make_tmap_2d(&p.tmQ, Q, static_cast<uint64_t>(ldq), static_cast<uint64_t>(B) * q_bstride, ldq * 2, 64, kBQ);
   if (rc) return rc;
-  rc = make_tmap_2d(&p.tmK, K, static_cast<uint64_t>(ldk), static_cast<uint64_t>(B) * Nk, ldk * 2, 64, kBKV);
+  rc = make_tmap_2d(&p.tmK, K, static_cast<uint64_t>(ldk), static_cast<uint64_t>(B) * kv_bstride, ldk * 2, 64, kBKV);
   if (rc) return rc;
-  rc = make_tmap_2d(&p.tmV, Vt, static_cast<uint64_t>(B) * Nk, static_cast<uint64_t>(H) * DVP, ldv * 2, 64, DVP);
+  rc = make_tmap_2d(&p.tmV, Vt, static_cast<uint64_t>(B) * kv_bstride, static_cast<uint64_t>(H) * DVP, ldv * 2, 64, DVP);
   if (rc) return rc;
-  p.Nq = Nq; p.Nk = Nk; p.q_col0 = q_col0; p.k_col0 = k_col0; p.dv = d_head; p.causal = causal;
+  p.Nq = Nq; p.Nk = Nk; p.q_bs = q_bstride; p.kv_bs = kv_bstride; p.q_col0 = q_col0; p.k_col0 = k_col0; p.dv = d_head; p.causal = causal;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;

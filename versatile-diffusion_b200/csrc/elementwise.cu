@@ -21,7 +21,7 @@ __global__ void ddim_cfg_step_kernel(const float* __restrict__ e_uncond, const f
                                      const float* __restrict__ x, const float* __restrict__ noise,
                                      const float* __restrict__ coef, const int* __restrict__ step_idx,
                                      float scale, float temperature, float* __restrict__ x_prev,
-                                     float* __restrict__ pred_x0, long long n) {
+                                     float* __restrict__ x_prev_dup, float* __restrict__ pred_x0, long long n) {
   const float* c = coef + (step_idx ? 4 * (*step_idx) : 0);
   const float a_t = c[0], a_prev = c[1], sigma = c[2], s1m = c[3];
   const float sqrt_at = __fsqrt_rn(a_t);
@@ -56,11 +56,13 @@ __global__ void ddim_cfg_step_kernel(const float* __restrict__ e_uncond, const f
     }
     if (i + 3 < n) {
       *reinterpret_cast<float4*>(x_prev + i) = *reinterpret_cast<float4*>(xp);
+      if (x_prev_dup) *reinterpret_cast<float4*>(x_prev_dup + i) = *reinterpret_cast<float4*>(xp);
       if (pred_x0) *reinterpret_cast<float4*>(pred_x0 + i) = *reinterpret_cast<float4*>(p0);
     } else {
       for (int q = 0; q < 4; ++q)
         if (i + q < n) {
           x_prev[i + q] = xp[q];
+          if (x_prev_dup) x_prev_dup[i + q] = xp[q];
           if (pred_x0) pred_x0[i + q] = p0[q];
         }
     }
@@ -68,6 +70,14 @@ __global__ void ddim_cfg_step_kernel(const float* __restrict__ e_uncond, const f
 }
 
 __global__ void add_int_kernel(int* p, int delta) { *p += delta; }
+
+// y = a*x + b*z  (VD_v2_0.q_sample, vd.py:221-224: sqrt(ac_t)*x0 + sqrt(1-ac_t)*noise)
+__global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ z, float a, float b,
+                             float* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    y[i] = __fadd_rn(__fmul_rn(a, x[i]), __fmul_rn(b, z[i]));
+}
 
 // ---------------------------------------------------------------------------------------------
 // GroupNorm(32) statistics over NHWC bf16, optional two-source channel concat.
@@ -322,6 +332,41 @@ __global__ void permute_f32_kernel(const float* __restrict__ x, int B, int C, in
   }
 }
 
+// y[p, o] = (sum_c W[o, c] * x[p, c] + b[o]) * mul for tiny channel counts (post_quant_conv 4->4,
+// quant_conv 8->8: autokl.py:26-27,36,45), fp32 NHWC in/out.
+__global__ void pointwise_small_kernel(const float* __restrict__ x, long long npix, int Cin, int Cout,
+                                       const float* __restrict__ Wm, const float* __restrict__ bias, float pre_mul,
+                                       float* __restrict__ y) {
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < npix;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float xin[8];
+    for (int c = 0; c < Cin; ++c) xin[c] = x[p * Cin + c] * pre_mul;
+    for (int o = 0; o < Cout; ++o) {
+      float acc = bias ? bias[o] : 0.f;
+      for (int c = 0; c < Cin; ++c) acc += Wm[o * Cin + c] * xin[c];
+      y[p * Cout + o] = acc;
+    }
+  }
+}
+
+// DiagonalGaussianDistribution.sample (distributions.py:24-37) on NHWC fp32 moments [npix, 2*C]:
+// z = (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise) * post_mul ; noise NHWC [npix, C] or null (mode)
+__global__ void gaussian_sample_kernel(const float* __restrict__ moments, const float* __restrict__ noise, int C,
+                                       long long npix, float post_mul, float* __restrict__ z) {
+  const long long total = npix * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i / C;
+    const int c = static_cast<int>(i % C);
+    const float mean = moments[p * 2 * C + c];
+    float lv = moments[p * 2 * C + C + c];
+    lv = fminf(fmaxf(lv, -30.f), 20.f);
+    float v = mean;
+    if (noise) v = __fadd_rn(mean, __fmul_rn(expf(0.5f * lv), noise[i]));
+    z[i] = v * post_mul;
+  }
+}
+
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
@@ -453,14 +498,23 @@ extern "C" {
 
 int vdb_ddim_cfg_step(const float* e_uncond, const float* e_cond, const float* x, const float* noise,
                       const float* coef, const int* step_idx, float scale, float temperature, float* x_prev,
-                      float* pred_x0, long long n, void* stream) {
+                      float* x_prev_dup, float* pred_x0, long long n, void* stream) {
   if (!e_cond || !x || !coef || !x_prev || n <= 0) return set_error(VDB_ERR_INVALID, "ddim_cfg_step: null/empty argument");
   if ((reinterpret_cast<uintptr_t>(e_cond) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_prev) |
-       reinterpret_cast<uintptr_t>(e_uncond) | reinterpret_cast<uintptr_t>(noise) | reinterpret_cast<uintptr_t>(pred_x0)) & 15)
+       reinterpret_cast<uintptr_t>(e_uncond) | reinterpret_cast<uintptr_t>(noise) | reinterpret_cast<uintptr_t>(pred_x0) |
+       reinterpret_cast<uintptr_t>(x_prev_dup)) & 15)
     return set_error(VDB_ERR_INVALID, "ddim_cfg_step: pointers must be 16-byte aligned");
   const int threads = 256;
   ddim_cfg_step_kernel<<<ew_blocks((n + 3) / 4, threads), threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      e_uncond, e_cond, x, noise, coef, step_idx, scale, temperature, x_prev, pred_x0, n);
+      e_uncond, e_cond, x, noise, coef, step_idx, scale, temperature, x_prev, x_prev_dup, pred_x0, n);
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_axpby_f32(const float* x, const float* z, float a, float b, float* y, long long n, void* stream) {
+  if (!x || !z || !y || n <= 0) return set_error(VDB_ERR_INVALID, "axpby: null/empty argument");
+  axpby_kernel<<<ew_blocks(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, z, a, b, y, n);
   VDB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return VDB_OK;
@@ -555,6 +609,27 @@ int vdb_permute_f32(const float* x, int B, int C, long long HW, int to_nhwc, flo
   const long long total = static_cast<long long>(B) * C * HW;
   permute_f32_kernel<<<ew_blocks(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, B, C, static_cast<int>(HW), to_nhwc, mul, add, clamp01, y);
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_pointwise_small(const float* x, long long npix, int Cin, int Cout, const float* Wm, const float* bias,
+                        float pre_mul, float* y, void* stream) {
+  if (!x || !Wm || !y || Cin <= 0 || Cin > 8 || Cout <= 0 || Cout > 8)
+    return set_error(VDB_ERR_INVALID, "pointwise_small: need 1 <= Cin, Cout <= 8");
+  pointwise_small_kernel<<<ew_blocks(npix, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, npix, Cin, Cout, Wm,
+                                                                                                  bias, pre_mul, y);
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_gaussian_sample(const float* moments, const float* noise, int C, long long npix, float post_mul, float* z,
+                        void* stream) {
+  if (!moments || !z || C <= 0 || npix <= 0) return set_error(VDB_ERR_INVALID, "gaussian_sample: bad argument");
+  gaussian_sample_kernel<<<ew_blocks(npix * C, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      moments, noise, C, npix, post_mul, z);
   VDB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return VDB_OK;

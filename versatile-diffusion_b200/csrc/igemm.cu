@@ -57,7 +57,7 @@ struct alignas(64) IgemmParams {
   long long ldo;
   int out_f32;                // 1: fp32 output
   int act;                    // 0 none, 1 silu, 2 gelu(erf), 3 quick_gelu, 4 geglu (packed halves)
-  float alpha;                // accumulator scale applied before bias
+  float alpha;                // out = act(alpha * (acc + bias)) + resid
   float* partial;             // split-K: [ksplit, M, N] fp32
 };
 
@@ -247,8 +247,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
             uint32_t o[16];
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-              float a0 = __uint_as_float(v[j]) * p.alpha, a1 = __uint_as_float(v[j + 1]) * p.alpha;
-              float g0 = __uint_as_float(g[j]) * p.alpha, g1 = __uint_as_float(g[j + 1]) * p.alpha;
+              float a0 = __uint_as_float(v[j]), a1 = __uint_as_float(v[j + 1]);
+              float g0 = __uint_as_float(g[j]), g1 = __uint_as_float(g[j + 1]);
               if (p.bias) {
                 a0 += __ldg(p.bias + n0 + c * 32 + j);
                 a1 += __ldg(p.bias + n0 + c * 32 + j + 1);
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
           if (row_ok) {
             float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
             const int nb = n0 + c * 32;
             const bool full = nb + 32 <= p.N;
             if (bias) {
@@ -290,6 +290,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
 #pragma unroll
                 for (int j = 0; j < 32; ++j) if (nb + j < p.N) f[j] += __ldg(bias + nb + j);
               }
+            }
+            if (p.alpha != 1.f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
             }
             if (p.act != ACT_NONE) {
 #pragma unroll
@@ -351,7 +355,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
-// split-K reduction + epilogue: out[m, n] = act(alpha * sum_s partial[s, m, n] + bias) + resid
+// split-K reduction + epilogue: out[m, n] = act(alpha * (sum_s partial[s, m, n] + bias)) + resid
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int ksplit, long long M, int N,
                                      const float* __restrict__ bias, long long bias_bstride, int rows_per_batch,
                                      const __nv_bfloat16* __restrict__ resid, long long ldr, void* out,
@@ -366,11 +370,12 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int kspl
       const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (static_cast<long long>(s) * M + m) * N + n));
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    float f[4] = {acc.x * alpha, acc.y * alpha, acc.z * alpha, acc.w * alpha};
+    float f[4] = {acc.x, acc.y, acc.z, acc.w};
     if (bias) {
       const float* bp = bias + (bias_bstride ? (m / rows_per_batch) * bias_bstride : 0) + n;
       for (int q = 0; q < 4; ++q) f[q] += __ldg(bp + q);
     }
+    for (int q = 0; q < 4; ++q) f[q] *= alpha;
     for (int q = 0; q < 4; ++q) f[q] = apply_act(f[q], act);
     if (resid) {
       for (int q = 0; q < 4; ++q) f[q] += __bfloat162float(resid[m * ldr + n + q]);
@@ -510,7 +515,7 @@ using namespace vdb;
 // ---------------------------------------------------------------------------------------------
 extern "C" {
 
-// out[M,N] = act(alpha * [A | A2] @ W^T + bias) + resid     (see include/vdb200.h)
+// out[M,N] = act(alpha * ([A | A2] @ W^T + bias)) + resid     (see include/vdb200.h)
 int vdb_gemm_bf16(const void* A, long long M, long long K, long long lda, const void* A2, long long K2,
                   long long lda2, const void* W, long long N, long long ldw, const float* bias,
                   long long bias_bstride, long long rows_per_batch, const void* resid, long long ldr, void* out,

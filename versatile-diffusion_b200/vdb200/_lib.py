@@ -24,21 +24,24 @@ SIGNATURES = {
     "vdb_launch_count": (ll, []),
     "vdb_reset_launch_count": (None, []),
     "vdb_num_sms": (i, []),
-    "vdb_ddim_cfg_step": (i, [p, p, p, p, p, p, f, f, p, p, ll, p]),
+    "vdb_ddim_cfg_step": (i, [p, p, p, p, p, p, f, f, p, p, p, ll, p]),
+    "vdb_axpby_f32": (i, [p, p, f, f, p, ll, p]),
     "vdb_add_int": (i, [p, i, p]),
     "vdb_gemm_bf16": (i, [p, ll, ll, ll, p, ll, ll, p, ll, ll, p, ll, ll, p, ll, p, ll, i, i, f, i, i, p, sz, p]),
     "vdb_conv3x3_bf16": (i, [p, i, i, i, i, i, p, i, ll, p, i, p, i, p, ll, p, ll, p, ll, i, i, i, i, p, sz, p]),
     "vdb_attention_dk_pad": (i, [i]),
     "vdb_attention_dv_pad": (i, [i]),
-    "vdb_attention_bf16": (i, [p, ll, i, p, ll, i, p, ll, p, ll, i, i, i, i, i, f, i, p]),
+    "vdb_attention_bf16": (i, [p, ll, i, p, ll, i, p, ll, p, ll, i, i, i, i, i, i, i, f, i, p]),
     "vdb_groupnorm_nsplit": (i, [i, i]),
     "vdb_groupnorm_nhwc": (i, [p, i, p, i, i, i, i, p, p, f, i, p, p, p]),
     "vdb_layernorm": (i, [p, ll, i, p, p, f, p, p]),
     "vdb_upsample2x_nhwc": (i, [p, i, i, i, i, p, p]),
     "vdb_im2col3x3_small": (i, [p, i, i, i, i, i, f, f, p, p]),
     "vdb_permute_f32": (i, [p, i, i, ll, i, f, f, i, p, p]),
+    "vdb_gaussian_sample": (i, [p, p, i, ll, f, p, p]),
     "vdb_cast_f32_bf16": (i, [p, p, ll, p]),
     "vdb_cast_bf16_f32": (i, [p, p, ll, p]),
+    "vdb_pointwise_small": (i, [p, ll, i, i, p, p, f, p, p]),
     "vdb_timestep_embedding": (i, [p, p, i, i, f, p, p]),
     "vdb_linear_small": (i, [p, i, i, p, i, p, i, i, p, p]),
     "vdb_softmax_rows": (i, [p, ll, i, ll, f, p, p]),

@@ -22,13 +22,15 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
-def _need(t, dtype, name):
+def _need(t, dtype, name, rows_ok=False):
     if t is None:
         return
     if not t.is_cuda:
         raise ValueError(f"{name}: vdb200 kernels need CUDA tensors (no CPU fallback)")
     if t.dtype != dtype:
         raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if rows_ok and t.dim() == 2 and t.stride(1) == 1:
+        return  # row-strided 2-D view: the kernels take a leading dimension
     if not t.is_contiguous():
         raise ValueError(f"{name}: must be contiguous")
 
@@ -56,7 +58,7 @@ def reset_launch_count():
 
 # ------------------------------------------------------------------------------------------------
 def ddim_cfg_step(e_uncond, e_cond, x, coef, scale, x_prev=None, pred_x0=None, noise=None,
-                  temperature=1.0, step_idx=None):
+                  temperature=1.0, step_idx=None, x_prev_dup=None):
     """K4 (ddim.py:144-171). e_*/x/noise fp32 same shape; coef fp32 [.,4] device tensor."""
     for n, t in (("e_uncond", e_uncond), ("e_cond", e_cond), ("x", x), ("noise", noise), ("coef", coef)):
         _need(t, torch.float32, n)
@@ -65,9 +67,18 @@ def ddim_cfg_step(e_uncond, e_cond, x, coef, scale, x_prev=None, pred_x0=None, n
     if step_idx is not None:
         _need(step_idx, torch.int32, "step_idx")
     check(lib.vdb_ddim_cfg_step(_ptr(e_uncond), _ptr(e_cond), _ptr(x), _ptr(noise), _ptr(coef), _ptr(step_idx),
-                                float(scale), float(temperature), _ptr(x_prev), _ptr(pred_x0), x.numel(), _stream()),
+                                float(scale), float(temperature), _ptr(x_prev), _ptr(x_prev_dup), _ptr(pred_x0), x.numel(),
+                                _stream()),
           "ddim_cfg_step")
     return x_prev, pred_x0
+
+
+def axpby(x, z, a, b, out=None):
+    _need(x, torch.float32, "x"); _need(z, torch.float32, "z")
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.vdb_axpby_f32(_ptr(x), _ptr(z), float(a), float(b), _ptr(out), x.numel(), _stream()), "axpby")
+    return out
 
 
 def add_int(t, delta):
@@ -78,8 +89,8 @@ def add_int(t, delta):
 def gemm(a, w, bias=None, resid=None, out=None, act=ACT_NONE, a2=None, out_dtype=BF16, alpha=1.0,
          bias_bstride=0, rows_per_batch=1, bn=0, ksplit=0):
     """out[M,N'] = act(alpha*[a|a2] @ w^T + bias) + resid ; a [M,K] bf16, w [N,K(+K2)] bf16."""
-    _need(a, BF16, "a"); _need(w, BF16, "w"); _need(a2, BF16, "a2"); _need(bias, torch.float32, "bias")
-    _need(resid, BF16, "resid")
+    _need(a, BF16, "a", True); _need(w, BF16, "w", True); _need(a2, BF16, "a2", True); _need(bias, torch.float32, "bias")
+    _need(resid, BF16, "resid", True)
     M, K = a.shape
     N = w.shape[0]
     K2 = a2.shape[1] if a2 is not None else 0
@@ -87,7 +98,7 @@ def gemm(a, w, bias=None, resid=None, out=None, act=ACT_NONE, a2=None, out_dtype
     n_out = N // 2 if act == ACT_GEGLU else N
     if out is None:
         out = torch.empty((M, n_out), dtype=out_dtype, device=a.device)
-    _need(out, out_dtype, "out")
+    _need(out, out_dtype, "out", True)
     ws = None
     ws_bytes = 0
     if ksplit != 1:
@@ -138,13 +149,16 @@ def attention_pads(d_head):
     return dk, dv
 
 
-def attention(q, k, vt, out, B, H, Nq, Nk, d_head, scale=None, q_col0=0, k_col0=0, causal=False):
-    """Flash attention. q [B*Nq, ldq], k [B*Nk, ldk], vt [H*DVP, >=B*Nk], out [B*Nq, H*d_head]."""
-    _need(q, BF16, "q"); _need(k, BF16, "k"); _need(vt, BF16, "vt"); _need(out, BF16, "out")
+def attention(q, k, vt, out, B, H, Nq, Nk, d_head, scale=None, q_col0=0, k_col0=0, causal=False,
+              q_bstride=0, kv_bstride=0):
+    """Flash attention. q [B*q_bstride, ldq], k [B*kv_bstride, ldk], vt [H*DVP, B*kv_bstride], out [B*q_bstride, H*d_head].
+    kv_bstride (default Nk) must be a multiple of 8: pad ragged contexts per batch item."""
+    _need(q, BF16, "q", True); _need(k, BF16, "k", True); _need(vt, BF16, "vt", True); _need(out, BF16, "out", True)
     if scale is None:
         scale = d_head ** -0.5
     check(lib.vdb_attention_bf16(_ptr(q), q.stride(0), int(q_col0), _ptr(k), k.stride(0), int(k_col0), _ptr(vt),
-                                 vt.stride(0), _ptr(out), out.stride(0), B, H, Nq, Nk, d_head, float(scale),
+                                 vt.stride(0), _ptr(out), out.stride(0), B, H, Nq, Nk, int(q_bstride), int(kv_bstride), d_head,
+                                 float(scale),
                                  1 if causal else 0, _stream()), "attention_bf16")
     return out
 
@@ -229,6 +243,30 @@ def to_f32(x, out=None):
     if out is None:
         out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
     check(lib.vdb_cast_bf16_f32(_ptr(x), _ptr(out), x.numel(), _stream()), "cast")
+    return out
+
+
+def pointwise_small(x, w, bias=None, pre_mul=1.0, out=None):
+    """x fp32 [..., Cin<=8] NHWC, w fp32 [Cout, Cin] -> fp32 [..., Cout]."""
+    _need(x, torch.float32, "x"); _need(w, torch.float32, "w"); _need(bias, torch.float32, "bias")
+    cout, cin = w.shape
+    npix = x.numel() // cin
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (cout,), dtype=torch.float32, device=x.device)
+    check(lib.vdb_pointwise_small(_ptr(x), npix, cin, cout, _ptr(w), _ptr(bias), float(pre_mul), _ptr(out), _stream()),
+          "pointwise_small")
+    return out
+
+
+def gaussian_sample(moments, noise=None, post_mul=1.0, out=None):
+    """moments fp32 NHWC [..., 2C]; noise fp32 NHWC [..., C] or None (posterior mean)."""
+    _need(moments, torch.float32, "moments"); _need(noise, torch.float32, "noise")
+    C = moments.shape[-1] // 2
+    npix = moments.numel() // (2 * C)
+    if out is None:
+        out = torch.empty(moments.shape[:-1] + (C,), dtype=torch.float32, device=moments.device)
+    check(lib.vdb_gaussian_sample(_ptr(moments), _ptr(noise), C, npix, float(post_mul), _ptr(out), _stream()),
+          "gaussian_sample")
     return out
 
 
