@@ -1,0 +1,343 @@
+"""bench.py — headline benchmark of the B200-native Versatile-Diffusion sampling hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one batch: DDIMSampler.sample (50 DDIM steps, CFG 7.5, eta 0)
++ VD_v2_0.vae_decode for bs=4 512x512 images per GPU (BASELINE.json configs[1]: text-to-image single flow,
+bf16).  Weights are random-init at the full architecture size (no checkpoints offline), contexts are
+synthetic [bs,77,768] tensors (CLIP encoding is per-prompt and amortised), x_T is seeded noise.
+
+Prints ONE JSON line (rank 0): value = whole-job images/s with inputs resident in HBM; e2e = the same
+through the public API with pinned-host inputs (H2D of contexts + x_T, D2H of the uint8-able images) inside
+the timed region; roofline = dominant kernel family timed with CUDA events inside this run; cpu_baseline =
+the oracle port timed on the host cores on a bounded sample.  `--impl reference` times the reference's CPU
+path (oracle port of lib/model_zoo, all host threads) on the same config with bounded samples.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "versatile-diffusion_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "512x512 images/sec @ 50-step DDIM (bs=4/GPU)"
+UNIT = "images/s"
+BS, LAT, DDIM_STEPS, SCALE = 4, 64, 50, 7.5
+FLOP_PER_IMAGE = 80.33e12 + 2.5145e12      # 100 UNet rows + VAE decode per 512^2 image
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"tflops_burst": d.get("bf16_tflops"), "tflops_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "measured"}
+    return {"tflops_burst": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def build_net(device):
+    """Full-size VD (image VAE + 2D diffuser + text-context blocks), random init on the GPU, bf16 compute."""
+    import torch
+    from lib.cfg_helper import model_cfg_bank
+    from lib.model_zoo import get_model
+    cfg = model_cfg_bank()('vd_four_flow_v1-0')
+    cfg.args.ctx_cfg_list = []            # contexts are synthetic here (CLIP is timed separately)
+    torch.manual_seed(0)
+    with torch.device(device):
+        net = get_model()(cfg, verbose=False)
+    g = torch.Generator(device=device).manual_seed(1)
+    with torch.no_grad():                  # zero_module() tensors and biases -> N(0, 0.02) (SURVEY §8c pitfall)
+        for _, p in net.named_parameters():
+            if p.ndim == 1 or not bool(p.any()):
+                if p.ndim == 1 and p.shape[0] > 0 and bool((p == 1).all()):
+                    continue               # norm scales stay at 1
+                p.normal_(0.0, 0.02, generator=g)
+    net.eval()
+    net.to(device)
+    return net
+
+
+def make_inputs(rank, device, pinned):
+    import torch
+    g = torch.Generator().manual_seed(100 + rank)
+    kw = {"pin_memory": True} if pinned else {}
+    xT = torch.randn(BS, 4, LAT, LAT, generator=g).contiguous()
+    return (torch.empty_like(xT, **kw).copy_(xT),)
+
+
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+    from lib.model_zoo.ddim import DDIMSampler
+    from vdb200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    net = build_net(device)
+    sampler = DDIMSampler(net)
+
+    # contexts: rank 0 "encodes" (synthetic) and broadcasts over NCCL — the only collective of the path
+    g = torch.Generator().manual_seed(2)
+    cond_h = (torch.randn(1, 77, 768, generator=g) * 0.5).pin_memory()
+    uncond_h = (torch.randn(1, 77, 768, generator=g) * 0.5).pin_memory()
+    cond, uncond = cond_h.to(device), uncond_h.to(device)
+    if world > 1:
+        dist.broadcast(cond, 0)
+        dist.broadcast(uncond, 0)
+    (xT_h,) = make_inputs(rank, device, pinned=True)
+    xT_d = xT_h.to(device)
+    c_d, u_d = cond.repeat(BS, 1, 1).contiguous(), uncond.repeat(BS, 1, 1).contiguous()
+    img_h = torch.empty(BS, 3, 8 * LAT, 8 * LAT, dtype=torch.float32).pin_memory()
+
+    def one_pass(host_io):
+        if host_io:
+            x0 = xT_h.to(device, non_blocking=True)
+            c = cond_h.to(device, non_blocking=True).repeat(BS, 1, 1)
+            u = uncond_h.to(device, non_blocking=True).repeat(BS, 1, 1)
+        else:
+            x0, c, u = xT_d, c_d, u_d
+        x, _ = sampler.sample(steps=DDIM_STEPS, shape=[BS, 4, LAT, LAT], x_info={"type": "image", "xt": x0},
+                              c_info={"type": "text", "conditioning": c, "unconditional_conditioning": u,
+                                      "unconditional_guidance_scale": SCALE}, verbose=False, eta=0.)
+        im = net.vae_decode(x, "image")
+        if host_io:
+            img_h.copy_(im, non_blocking=True)
+        return im
+
+    def timed(n, host_io):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            one_pass(host_io)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            one_pass(False)
+        one_pass(True)
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        ops.reset_launch_count()
+        ms = timed(args.steps, False)
+        # launches: graph replays do not pass through the C ABI, so count one DDIM step and scale
+        per_step = getattr(sampler, "last_step_launches", 0)
+        decode_launches = 0
+        c0 = ops.launch_count()
+        net.vae_decode(xT_d, "image")
+        decode_launches = ops.launch_count() - c0
+        launches = args.steps * (per_step * DDIM_STEPS + decode_launches + 4)
+        ms_e2e = timed(args.steps, True)
+        clk = clocks.stop() if rank == 0 else None
+
+        # ---- roofline leg: per-family CUDA-event timing of one eager DDIM step + decode
+        roof, fam = None, None
+        if rank == 0:
+            eager = DDIMSampler(net, use_cuda_graph=False)
+            ops.profile_start()
+            eager.sample(steps=2, shape=[BS, 4, LAT, LAT], x_info={"type": "image", "xt": xT_d},
+                         c_info={"type": "text", "conditioning": c_d, "unconditional_conditioning": u_d,
+                                 "unconditional_guidance_scale": SCALE}, verbose=False, eta=0.)
+            fam = ops.profile_stop()
+            peaks = measured_peaks()
+            top = max(fam, key=lambda k: fam[k]["ms"])
+            d = fam[top]
+            tflops = d["flops"] / d["ms"] / 1e9 if d["ms"] > 0 else 0.0
+            if d["flops"] > 0:
+                roof = {"bound": "tensor", "kernel": top, "achieved": round(tflops, 1), "peak": peaks["tflops_sustained"],
+                        "unit": "TFLOP/s", "frac": round(tflops / peaks["tflops_sustained"], 4), "traffic": None,
+                        "peak_source": peaks["source"] + " (sustained: timed inside a long step)",
+                        "launches": d["launches"], "avg_launch_ms": round(d["ms"] / d["launches"], 4)}
+            else:
+                gbs = d["bytes"] / d["ms"] / 1e6
+                roof = {"bound": "hbm", "kernel": top, "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": round(gbs / peaks["hbm_gbs"], 4), "traffic": None, "peak_source": peaks["source"]}
+            roof["families"] = {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                                    "tflops": round(v["flops"] / v["ms"] / 1e9, 1) if v["ms"] > 0 else 0.0}
+                                for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+
+    images = BS * world * args.steps
+    value = images / (ms / 1e3)
+    e2e_value = images / (ms_e2e / 1e3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = cpu_baseline_sample(net) if world == 1 and not args.no_cpu_baseline else None
+    peaks = measured_peaks()
+    line = {
+        "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random-init weights, synthetic context)",
+        "config": {"workload": "t2i single-flow 512x512, 50-step DDIM, CFG 7.5, eta 0, bs 4/GPU + VAE decode (configs[1])",
+                   "global_batch": BS * world, "latent": [4, LAT, LAT], "parallelism": f"dp{world} (batch shards, one NCCL context broadcast)",
+                   "l2": "working set (3.3 GB weights + activations) exceeds the 126 MB L2 every step; no explicit flush",
+                   "tensor_frac_of_step": round(value / world * FLOP_PER_IMAGE / (peaks["tflops_sustained"] * 1e12), 4)},
+        "e2e": {"value": round(e2e_value, 4), "unit": UNIT,
+                "h2d_bytes_per_step": int(xT_h.numel() * 4 + 2 * cond_h.numel() * 4),
+                "d2h_bytes_per_step": int(img_h.numel() * 4)},
+        "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the only places bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------
+def _cpu_state_dict(net=None):
+    """fp32 CPU weights for the oracle port: copied from the product net when given, else synthesised."""
+    import torch
+    if net is not None:
+        return {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
+    from lib.cfg_helper import model_cfg_bank
+    from lib.model_zoo import get_model
+    cfg = model_cfg_bank()('vd_four_flow_v1-0')
+    cfg.args.ctx_cfg_list = []
+    torch.manual_seed(0)
+    m = get_model()(cfg, verbose=False)
+    with torch.no_grad():
+        for p in m.parameters():
+            if not bool(p.any()):
+                p.normal_(0.0, 0.02)
+    return {k: v.detach().float() for k, v in m.state_dict().items()}
+
+
+def _cpu_time_step(sd, reps):
+    """One CFG UNet evaluation for ONE image (B=2 rows, latent 64x64, text ctx) + one K4-equivalent update."""
+    import torch
+    from oracle import vd_oracle as O
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(1, 4, LAT, LAT, generator=g)
+    c, u = torch.randn(1, 77, 768, generator=g) * 0.5, torch.randn(1, 77, 768, generator=g) * 0.5
+    sched = O.ddim_schedule(O.ddpm_schedule()["alphas_cumprod"], DDIM_STEPS)
+    ts = []
+    with torch.no_grad():
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            O.p_sample_ddim(sd, x, [c], [u], torch.tensor([981]), DDIM_STEPS - 1, sched, SCALE)
+            ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def cpu_baseline_sample(net=None):
+    import torch
+    from oracle import vd_oracle as O
+    threads = torch.get_num_threads()
+    sd = _cpu_state_dict(net)
+    ts = _cpu_time_step(sd, 2)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        O.vae_decode(sd, torch.randn(1, 4, LAT, LAT))
+        t_dec = time.perf_counter() - t0
+    per_image = DDIM_STEPS * min(ts) + t_dec
+    return {"value": round(1.0 / per_image, 6), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"oracle/vd_oracle.py (fp32 torch CPU port of lib/model_zoo): 2 CFG UNet steps of one image "
+                      f"(B=2, latent 64x64) at {min(ts):.2f} s/step + 1 VAE decode at {t_dec:.2f} s, "
+                      f"extrapolated to 50 steps", "s_per_ddim_step": round(min(ts), 3), "s_vae_decode": round(t_dec, 3)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path for this config, timed on the host cores.
+    /root/reference does not exist on the GPU box, so this is the oracle PORT (kind 'port')."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    from oracle import vd_oracle as O
+    sd = _cpu_state_dict(None)
+    threads = torch.get_num_threads()
+    _cpu_time_step(sd, args.warmup if args.warmup > 0 else 1)
+    ts = _cpu_time_step(sd, args.steps)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        O.vae_decode(sd, torch.randn(1, 4, LAT, LAT))
+        t_dec = time.perf_counter() - t0
+    step_s = sum(ts) / len(ts)
+    per_image = DDIM_STEPS * step_s + t_dec
+    value = 1.0 / per_image
+    sample = (f"each step = one CFG DDIM step of one 512x512 image (UNet B=2, latent 64x64, 77-token text ctx) on CPU fp32, "
+              f"{step_s:.2f} s; images/s extrapolated as 1/(50*step + vae_decode {t_dec:.2f} s)")
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 6), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_s * 1e3, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init weights, synthetic context)",
+            "config": {"workload": "t2i single-flow 512x512, 50-step DDIM, CFG 7.5, eta 0 (configs[1]) — bounded CPU sample",
+                       "global_batch": 1},
+            "cpu_baseline": {"value": round(value, 6), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": round(value, 6), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -528,7 +528,10 @@ int vdb_gemm_bf16(const void* A, long long M, long long K, long long lda, const 
   if (M > 0x7fffffffLL || N > 0x7fffffffLL) return set_error(VDB_ERR_INVALID, "gemm: dimension too large");
   IgemmParams p;
   memset(&p, 0, sizeof(p));
-  set_tile_shape(p, static_cast<int>(M), 1, 1);
+  // GEMM view of the pixel grid: one row of M "pixels"; the box is always 128 rows (TMA zero-fills past M)
+  p.Wo = static_cast<int>(M); p.Ho = 1; p.Bo = 1;
+  p.TW = kBlockM; p.TH = 1; p.TB = 1;
+  p.tilesW = static_cast<int>((M + kBlockM - 1) / kBlockM); p.tilesH = 1; p.tilesB = 1;
   int rc = make_tmap_4d(&p.tmA[0], A, K, M, 1, 1, lda * 2, lda * 2 * M, lda * 2 * M, kBlockK, p.TW, 1, 1);
   if (rc) return rc;
   p.seg[0] = ASeg{0, 0, 0, static_cast<int16_t>((K + kBlockK - 1) / kBlockK), 0};

@@ -18,6 +18,15 @@ def _ops():
     return ops
 
 
+class PaddedContext(object):
+    """A context batch already in kernel layout: bf16 [B, Lp, C] with Lp = L rounded up to 8 and zero pad rows.
+    DDIMSampler keeps one per context in a persistent buffer so the captured CUDA graph (and the cached K / V^T
+    of every cross-attention layer) stay valid when a new prompt is copied in."""
+
+    def __init__(self, data, length):
+        self.data, self.length = data, length
+
+
 def Normalize(in_channels):
     return torch.nn.GroupNorm(num_groups=32, num_channels=in_channels, eps=1e-6, affine=True)
 
@@ -81,26 +90,41 @@ class CrossAttention(PackedModule):
         dk, dv = _ops().attention_pads(self.dim_head)
         wq, wk = self._pad_heads(self.to_q.weight, dk), self._pad_heads(self.to_k.weight, dk)
         self._kv_cache = None
-        return {"dk": dk, "dv": dv, "wq": wq, "wk": wk, "wqk": torch.cat([wq, wk], 0).contiguous(),
+        return {"dk": dk, "dv": dv, "wq": wq, "wk": wk, "wqk": torch.cat([wq, wk], 0).contiguous() if self.is_self else None,
                 "wv": self._pad_heads(self.to_v.weight, dv), "wo": bf16(self.to_out[0].weight),
                 "bo": f32(self.to_out[0].bias)}
 
     def context_kv(self, context):
-        """K [B*Lp, H*dk] and V^T [H*dvp, B*Lp] of a context [B, L, Cc]; cached while the same tensor is
-        passed again (the context is constant over the DDIM loop, so this runs once per sample() call)."""
+        """K [B*Lp, H*dk] and V^T [H*dvp, B*Lp] of a context; cached while the same tensor (and version) is passed
+        again — the context is constant over the DDIM loop, so this runs once per sample() call, not per step."""
         p = self.packed()
+        ops = _ops()
+        if isinstance(context, PaddedContext):
+            data, L = context.data, context.length
+            B, Lp, Cc = data.shape
+            key = ("padded", data.data_ptr(), (B, Lp, Cc), L)
+            cflat = data.view(B * Lp, Cc)
+            ent = self._kv_cache
+            if ent is not None and ent[0] == key:
+                k, vt, ver = ent[1]
+                if ver != data._version:          # new prompt copied into the same buffer: refresh IN PLACE
+                    ops.gemm(cflat, p["wk"], out=k)
+                    ops.gemm(p["wv"], cflat, out=vt)
+                    self._kv_cache = (key, (k, vt, data._version))
+                return k, vt, L, Lp
+            k = ops.gemm(cflat, p["wk"])
+            vt = ops.gemm(p["wv"], cflat)
+            self._kv_cache = (key, (k, vt, data._version))
+            return k, vt, L, Lp
         key = (context.data_ptr(), context._version, tuple(context.shape), context.dtype)
         if self._kv_cache is not None and self._kv_cache[0] == key:
             return self._kv_cache[1]
-        ops = _ops()
         B, L, Cc = context.shape
         Lp = (L + 7) // 8 * 8   # kv stride per batch item must be a multiple of 8 (TMA alignment)
         cpad = torch.zeros(B, Lp, Cc, dtype=torch.bfloat16, device=context.device)
         cpad[:, :L] = context.to(torch.bfloat16)
         cflat = cpad.view(B * Lp, Cc)
-        k = ops.gemm(cflat, p["wk"])
-        vt = ops.gemm(p["wv"], cflat)
-        val = (k, vt, L, Lp)
+        val = (ops.gemm(cflat, p["wk"]), ops.gemm(p["wv"], cflat), L, Lp)
         self._kv_cache = (key, val)
         return val
 
@@ -111,10 +135,21 @@ class CrossAttention(PackedModule):
         H, d, dk = self.heads, self.dim_head, p["dk"]
         N = x.shape[0] // B
         o = torch.empty(x.shape[0], H * d, dtype=torch.bfloat16, device=x.device)
-        if context is None:
+        if context is None and N % 8 == 0:
             qk = ops.gemm(x, p["wqk"])                    # [B*N, 2*H*dk]: q | k
             vt = ops.gemm(p["wv"], x)                     # [H*dvp, B*N]
             ops.attention(qk, qk, vt, o, B, H, N, N, d, scale=self.scale, q_col0=0, k_col0=H * dk)
+        elif context is None:
+            # ragged token count (latent sides not a multiple of 8 at this level): keys/values from a copy of
+            # the tokens padded to a multiple of 8 per batch item (TMA alignment of the V^T columns)
+            Np = (N + 7) // 8 * 8
+            xp = torch.zeros(B, Np, x.shape[1], dtype=torch.bfloat16, device=x.device)
+            xp[:, :N] = x.view(B, N, -1)
+            xp = xp.view(B * Np, -1)
+            q = ops.gemm(x, p["wq"])
+            k = ops.gemm(xp, p["wk"])
+            vt = ops.gemm(p["wv"], xp)
+            ops.attention(q, k, vt, o, B, H, N, N, d, scale=self.scale, kv_bstride=Np)
         else:
             q = ops.gemm(x, p["wq"])
             k, vt, L, Lp = self.context_kv(context)

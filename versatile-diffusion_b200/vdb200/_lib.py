@@ -53,7 +53,16 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.argtypes = _args
 
 
+_TRACE = bool(os.environ.get("VDB_TRACE"))
+
+
 def check(status: int, what: str = "") -> None:
+    if _TRACE:  # debugging aid: name every launch and wait for it, so a hung kernel is identified
+        import sys
+        import torch
+        print(f"[vdb] {what} ...", file=sys.stderr, flush=True)
+        torch.cuda.synchronize()
+        print(f"[vdb] {what} done", file=sys.stderr, flush=True)
     if status != 0:
         msg = lib.vdb_last_error().decode("utf-8", "replace")
         raise VdbError(f"vdb200 {what} failed with status {status}: {msg}")

@@ -36,16 +36,63 @@ def _need(t, dtype, name, rows_ok=False):
 
 
 _workspace = {}
+WORKSPACE_BYTES = 160 << 20   # covers 16-way split-K of any MN grid that fits in half the SMs (74 tiles x 128 x 256 fp32)
 
 
-def workspace(nbytes, device):
-    """Grow-only fp32 scratch for split-K partials (per device)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+def workspace(device):
+    """Fixed-size fp32 split-K scratch per device. Never reallocated: its address is baked into captured CUDA graphs."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
     w = _workspace.get(key)
-    if w is None or w.numel() * 4 < nbytes:
-        w = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
+    if w is None:
+        w = torch.empty(WORKSPACE_BYTES // 4, dtype=torch.float32, device=device)
         _workspace[key] = w
     return w
+
+
+# ------------------------------------------------------------------------------------------------
+# optional per-family device timing (bench.py roofline leg): CUDA events on the launching stream
+# ------------------------------------------------------------------------------------------------
+_PROFILE = None
+
+
+class _Span(object):
+    __slots__ = ("name", "flops", "nbytes", "e0", "e1")
+
+    def __init__(self, name, flops, nbytes):
+        self.name, self.flops, self.nbytes = name, flops, nbytes
+
+    def __enter__(self):
+        if _PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _PROFILE is not None:
+            self.e1.record()
+            _PROFILE.append(self)
+        return False
+
+
+def profile_start():
+    global _PROFILE
+    _PROFILE = []
+
+
+def profile_stop():
+    """-> {family: {"ms": total, "launches": n, "flops": total, "bytes": total}}"""
+    global _PROFILE
+    spans, _PROFILE = _PROFILE, None
+    torch.cuda.synchronize()
+    out = {}
+    for sp in spans or []:
+        d = out.setdefault(sp.name, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
+        d["ms"] += sp.e0.elapsed_time(sp.e1)
+        d["launches"] += 1
+        d["flops"] += sp.flops
+        d["bytes"] += sp.nbytes
+    return out
 
 
 def launch_count():
@@ -99,20 +146,15 @@ def gemm(a, w, bias=None, resid=None, out=None, act=ACT_NONE, a2=None, out_dtype
     if out is None:
         out = torch.empty((M, n_out), dtype=out_dtype, device=a.device)
     _need(out, out_dtype, "out", True)
-    ws = None
-    ws_bytes = 0
-    if ksplit != 1:
-        ws_bytes = 16 * M * N * 4 if M * N * 64 <= (1 << 28) else 0
-        ws_bytes = min(ws_bytes, 256 << 20)
-        if M > 4096:  # split-K only ever triggers for small MN grids
-            ws_bytes = 0
-        if ws_bytes:
-            ws = workspace(ws_bytes, a.device)
-    check(lib.vdb_gemm_bf16(_ptr(a), M, K, a.stride(0), _ptr(a2), K2, a2.stride(0) if a2 is not None else 0,
-                            _ptr(w), N, w.stride(0), _ptr(bias), int(bias_bstride), int(rows_per_batch),
-                            _ptr(resid), resid.stride(0) if resid is not None else 0, _ptr(out), out.stride(0),
-                            1 if out_dtype == torch.float32 else 0, int(act), float(alpha), int(bn), int(ksplit),
-                            _ptr(ws), ws_bytes, _stream()), "gemm_bf16")
+    ws, ws_bytes = None, 0
+    if ksplit != 1 and M <= 8192:   # split-K only ever triggers for small MN grids
+        ws, ws_bytes = workspace(a.device), WORKSPACE_BYTES
+    with _Span("gemm", 2.0 * M * N * (K + K2), 2.0 * (M * (K + K2) + N * (K + K2) + M * n_out)):
+        check(lib.vdb_gemm_bf16(_ptr(a), M, K, a.stride(0), _ptr(a2), K2, a2.stride(0) if a2 is not None else 0,
+                                _ptr(w), N, w.stride(0), _ptr(bias), int(bias_bstride), int(rows_per_batch),
+                                _ptr(resid), resid.stride(0) if resid is not None else 0, _ptr(out), out.stride(0),
+                                1 if out_dtype == torch.float32 else 0, int(act), float(alpha), int(bn), int(ksplit),
+                                _ptr(ws), ws_bytes, _stream()), "gemm_bf16")
     return out
 
 
@@ -131,14 +173,15 @@ def conv3x3(x, w, bias=None, resid=None, out=None, mode=0, skip1=None, skip2=Non
         out = torch.empty((B, Ho, Wo, N), dtype=out_dtype, device=x.device)
     M = B * Ho * Wo
     ws, ws_bytes = None, 0
-    if ksplit != 1 and M <= 4096:
-        ws_bytes = 16 * M * N * 4
-        ws = workspace(ws_bytes, x.device)
-    check(lib.vdb_conv3x3_bf16(_ptr(x), B, H, W, Cc, int(mode), _ptr(w), N, w.stride(0), _ptr(skip1), cs1,
-                               _ptr(skip2), cs2, _ptr(bias), int(bias_bstride), _ptr(resid),
-                               resid.shape[-1] if resid is not None else 0, _ptr(out), out.shape[-1],
-                               1 if out_dtype == torch.float32 else 0, int(act), int(bn), int(ksplit), _ptr(ws),
-                               ws_bytes, _stream()), "conv3x3_bf16")
+    if ksplit != 1 and M <= 8192:
+        ws, ws_bytes = workspace(x.device), WORKSPACE_BYTES
+    ktot = 9 * Cc + cs1 + cs2
+    with _Span("conv3x3", 2.0 * M * N * ktot, 2.0 * (B * H * W * Cc + M * (cs1 + cs2) + N * ktot + M * N)):
+        check(lib.vdb_conv3x3_bf16(_ptr(x), B, H, W, Cc, int(mode), _ptr(w), N, w.stride(0), _ptr(skip1), cs1,
+                                   _ptr(skip2), cs2, _ptr(bias), int(bias_bstride), _ptr(resid),
+                                   resid.shape[-1] if resid is not None else 0, _ptr(out), out.shape[-1],
+                                   1 if out_dtype == torch.float32 else 0, int(act), int(bn), int(ksplit), _ptr(ws),
+                                   ws_bytes, _stream()), "conv3x3_bf16")
     return out
 
 
@@ -156,10 +199,11 @@ def attention(q, k, vt, out, B, H, Nq, Nk, d_head, scale=None, q_col0=0, k_col0=
     _need(q, BF16, "q", True); _need(k, BF16, "k", True); _need(vt, BF16, "vt", True); _need(out, BF16, "out", True)
     if scale is None:
         scale = d_head ** -0.5
-    check(lib.vdb_attention_bf16(_ptr(q), q.stride(0), int(q_col0), _ptr(k), k.stride(0), int(k_col0), _ptr(vt),
-                                 vt.stride(0), _ptr(out), out.stride(0), B, H, Nq, Nk, int(q_bstride), int(kv_bstride), d_head,
-                                 float(scale),
-                                 1 if causal else 0, _stream()), "attention_bf16")
+    with _Span("attention", 4.0 * B * H * Nq * Nk * d_head, 2.0 * B * H * d_head * (2 * Nq + 2 * Nk)):
+        check(lib.vdb_attention_bf16(_ptr(q), q.stride(0), int(q_col0), _ptr(k), k.stride(0), int(k_col0), _ptr(vt),
+                                     vt.stride(0), _ptr(out), out.stride(0), B, H, Nq, Nk, int(q_bstride),
+                                     int(kv_bstride), d_head, float(scale), 1 if causal else 0, _stream()),
+              "attention_bf16")
     return out
 
 
@@ -174,8 +218,9 @@ def groupnorm(x1, gamma, beta, eps, act=ACT_NONE, x2=None, out=None, groups=32):
         out = torch.empty(x1.shape[:-1] + (C1 + C2,), dtype=BF16, device=x1.device)
     nsplit = lib.vdb_groupnorm_nsplit(B, HW)
     partial = torch.empty(B * nsplit * 2 * groups, dtype=torch.float32, device=x1.device)
-    check(lib.vdb_groupnorm_nhwc(_ptr(x1), C1, _ptr(x2), C2, B, HW, groups, _ptr(gamma), _ptr(beta), float(eps),
-                                 int(act), _ptr(partial), _ptr(out), _stream()), "groupnorm_nhwc")
+    with _Span("groupnorm", 0.0, 2.0 * 3 * B * HW * (C1 + C2)):
+        check(lib.vdb_groupnorm_nhwc(_ptr(x1), C1, _ptr(x2), C2, B, HW, groups, _ptr(gamma), _ptr(beta), float(eps),
+                                     int(act), _ptr(partial), _ptr(out), _stream()), "groupnorm_nhwc")
     return out
 
 
@@ -185,7 +230,8 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
     rows = x.numel() // C
     if out is None:
         out = torch.empty_like(x)
-    check(lib.vdb_layernorm(_ptr(x), rows, C, _ptr(gamma), _ptr(beta), float(eps), _ptr(out), _stream()), "layernorm")
+    with _Span("layernorm", 0.0, 2.0 * 2 * rows * C):
+        check(lib.vdb_layernorm(_ptr(x), rows, C, _ptr(gamma), _ptr(beta), float(eps), _ptr(out), _stream()), "layernorm")
     return out
 
 
