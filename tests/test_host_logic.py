@@ -1,0 +1,110 @@
+"""Host-side logic of the drop-in surface (CPU only): config bank, registry, checkpoint key ABI against the
+reference-dumped fixtures, layer orders, DDIMSampler.make_schedule against reference tables, error behaviour."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def build(mini, device="cpu"):
+    from lib.cfg_helper import model_cfg_bank
+    from lib.model_zoo import get_model
+    cfg = model_cfg_bank()('vd_four_flow_v1-0')
+    cfg.args.ctx_cfg_list = []
+    if mini:
+        for _, d in cfg.args.diffuser_cfg_list:
+            d.args.update(dict(model_channels=64))
+        cfg.args.vae_cfg_list[0][1].args.ddconfig.update(dict(ch=64))
+    with torch.device(device):
+        return get_model()(cfg, verbose=False)
+
+
+@pytest.mark.parametrize("mini,fixture", [(True, "keys_mini.json"), (False, "keys_full.json")])
+def test_checkpoint_keys_and_shapes_match_reference(mini, fixture):
+    ref = {k: tuple(v) for k, v in json.load(open(os.path.join(GOLD, fixture))).items()}
+    net = build(mini, device="cpu" if mini else "meta")     # full size: shapes only
+    ours = {k: tuple(v.shape) for k, v in net.named_parameters()}
+    assert set(ours) == set(ref), sorted(set(ours) ^ set(ref))[:10]
+    assert all(ours[k] == ref[k] for k in ref)
+    # the 12 schedule buffers live at the top level like the reference's
+    for b in ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+              "posterior_variance", "posterior_mean_coef1", "posterior_mean_coef2"):
+        assert b in dict(net.named_buffers())
+
+
+def test_layer_orders_match_the_reference_walk():
+    from oracle.vd_oracle import unet_layout
+    net = build(True)
+    d2, d0 = net.diffuser["image"], net.diffuser["text"]
+    assert d2.layer_order == d0.layer_order and net.check_diffuser()
+    assert d2.layer_order.count('d') == 30 and d2.layer_order.count('c') == 16
+    assert d2.layer_order.count('save_hidden_feature') == 12 == d2.layer_order.count('load_hidden_feature')
+    kinds = {"conv_in": "d", "res": "d", "down": "d", "up": "d", "out": "d", "ctx": "c", "save": "save_hidden_feature",
+             "load": "load_hidden_feature"}
+    assert [kinds[k] for k, _, _ in unet_layout(model_channels=64)] == d2.layer_order
+    assert len(d2.data_blocks) == 30 and len(d2.context_blocks) == 16 and len(d0.context_blocks) == 16
+    assert not hasattr(d0, "data_blocks") and set(d2.parameter_group) == {"global", "data", "context"}
+
+
+def test_ddim_make_schedule_matches_reference_tables():
+    from lib.model_zoo.ddim import DDIMSampler
+    net = build(True)
+    sched = json.load(open(os.path.join(GOLD, "schedule.json")))
+    for steps in (50, 10):
+        S = DDIMSampler(net)
+        S.make_schedule(ddim_num_steps=steps, ddim_eta=0., verbose=False)
+        g = sched[str(steps)]
+        assert [int(v) for v in S.ddim_timesteps] == g["timesteps"]
+        np.testing.assert_array_equal(np.asarray(S.ddim_alphas, dtype=np.float32), np.asarray(g["alphas"], dtype=np.float32))
+        np.testing.assert_array_equal(np.asarray(S.ddim_alphas_prev, dtype=np.float32), np.asarray(g["alphas_prev"], dtype=np.float32))
+        np.testing.assert_array_equal(np.asarray(S.ddim_sqrt_one_minus_alphas, dtype=np.float32),
+                                      np.asarray(g["sqrt_one_minus_alphas"], dtype=np.float32))
+        assert not np.any(np.asarray(S.ddim_sigmas))
+    assert S.ddpm_num_timesteps == 1000
+
+
+def test_config_bank_and_registry_surface():
+    from lib.cfg_helper import model_cfg_bank
+    from lib.model_zoo import get_model
+    bank = model_cfg_bank()
+    u = bank("openai_unet_2d_v1")
+    assert u.type == "openai_unet_2d_next" and u.args.model_channels == 320 and u.args.channel_mult == [1, 2, 4, 4]
+    assert bank("openai_unet_0d_v1_c").args.parts == ["context"]
+    assert bank("autokl_v1").args.ddconfig.ch_mult == [1, 2, 4, 4]
+    vd = bank("vd_four_flow_v1-0")
+    assert vd.args.latent_scale_factor["image"] == 0.18215 and vd.args.global_layer_ptr == "image"
+    with pytest.raises(KeyError):
+        bank("optimus_v1")                               # text-latent flows are out of the hot-path build
+    assert get_model() is get_model()                    # singleton like the reference
+    with pytest.raises(NotImplementedError):
+        get_model()(bank("openai_unet_0d_v1"))           # 0-D data blocks: out of scope, fails loudly
+
+
+def test_to_returns_none_and_no_cpu_path():
+    from lib.model_zoo.ddim import DDIMSampler
+    net = build(True)
+    assert net.to("cpu") is None and net.device == "cpu"             # reference semantics (vd.py:114-116)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        net.apply_model({"type": "image", "x": torch.zeros(1, 4, 8, 8)}, torch.zeros(1, dtype=torch.long),
+                        {"type": "text", "c": torch.zeros(1, 77, 768)})
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        DDIMSampler(net).sample(steps=2, shape=[1, 4, 8, 8], x_info={"type": "image"},
+                                c_info={"type": "text", "conditioning": torch.zeros(1, 77, 768),
+                                        "unconditional_conditioning": torch.zeros(1, 77, 768),
+                                        "unconditional_guidance_scale": 7.5}, verbose=False)
+
+
+def test_packed_weights_invalidate_on_load_and_cast():
+    net = build(True)
+    rb = net.diffuser["image"].data_blocks[1][0]
+    rb._packed = {"stale": True}
+    net.load_state_dict(net.state_dict())
+    assert rb._packed is None
+    rb._packed = {"stale": True}
+    net.half()
+    assert rb._packed is None and rb.in_layers[2].weight.dtype == torch.float16

@@ -131,7 +131,8 @@ def test_ddim_5_steps_vs_reference_golden(mini, graph):
                                     "unconditional_conditioning": gi["u"].to(DEV),
                                     "unconditional_guidance_scale": 7.5}, verbose=False, eta=0., log_every_t=1)
     _cmp(x, gold["ddim5_final"], cos_min=0.995, tol=0.1, what=f"5-step DDIM final latent (graph={graph})")
-    _cmp(inter["pred_x0"][0], gold["ddim5_pred_x0"][0], what="first-step pred_x0")
+    # pred_x0 at the first step divides the eps error by sqrt(a_t) = 0.07: looser bound than eps itself
+    _cmp(inter["pred_x0"][0], gold["ddim5_pred_x0"][0], cos_min=0.997, tol=0.1, what="first-step pred_x0")
     assert len(inter["pred_x0"]) == 5
 
 

@@ -8,18 +8,19 @@ import torch.nn as nn
 
 
 def make_beta_schedule(schedule, n_timestep, linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3):
-    """fp64 beta tables (reference :8-30)."""
+    """fp64 beta tables (reference :8-30); always built on the host, even under a torch.device(cuda) context."""
+    cpu = torch.device("cpu")
     if schedule == "linear":
-        betas = torch.linspace(linear_start ** 0.5, linear_end ** 0.5, n_timestep, dtype=torch.float64) ** 2
+        betas = torch.linspace(linear_start ** 0.5, linear_end ** 0.5, n_timestep, dtype=torch.float64, device=cpu) ** 2
     elif schedule == "cosine":
-        ts = torch.arange(n_timestep + 1, dtype=torch.float64) / n_timestep + cosine_s
+        ts = torch.arange(n_timestep + 1, dtype=torch.float64, device=cpu) / n_timestep + cosine_s
         alphas = torch.cos(ts / (1 + cosine_s) * np.pi / 2).pow(2)
         alphas = alphas / alphas[0]
         betas = np.clip(1 - alphas[1:] / alphas[:-1], a_min=0, a_max=0.999)
     elif schedule == "sqrt_linear":
-        betas = torch.linspace(linear_start, linear_end, n_timestep, dtype=torch.float64)
+        betas = torch.linspace(linear_start, linear_end, n_timestep, dtype=torch.float64, device=cpu)
     elif schedule == "sqrt":
-        betas = torch.linspace(linear_start, linear_end, n_timestep, dtype=torch.float64) ** 0.5
+        betas = torch.linspace(linear_start, linear_end, n_timestep, dtype=torch.float64, device=cpu) ** 0.5
     else:
         raise ValueError(f"schedule '{schedule}' unknown.")
     return betas.numpy() if isinstance(betas, torch.Tensor) else np.asarray(betas)
