@@ -91,10 +91,13 @@ int vdb_attention_bf16(const void* Q, long long ldq, int q_col0, const void* K, 
 
 /* ---- GroupNorm(32) [+SiLU] [+channel concat] on NHWC — normalization()/Normalize():
  *      diffusion_utils.py:168-191 (eps 1e-5), attention.py:76-77 & autokl_modules.py:38-39 (1e-6) ----
- * y[B,HW,C1+C2] = act(GN32(cat(x1,x2))) ; partial: scratch of B*vdb_groupnorm_nsplit(B,HW)*64 floats. */
+ * y[B,HW,C1+C2] = act(GN32(cat(x1,x2))).  scratch: ZERO-INITIALISED device buffer of
+ * vdb_groupnorm_scratch_floats(B,HW) floats (partial sums, finalised mean/rstd, per-batch arrival counters); it may
+ * be reused by later calls on the same stream (the kernels leave the counters at zero). Deterministic: no float atomics. */
 int vdb_groupnorm_nsplit(int B, int HW);
+long long vdb_groupnorm_scratch_floats(int B, int HW);
 int vdb_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int B, int HW, int groups, const float* gamma,
-                       const float* beta, float eps, int act, float* partial, void* y, void* stream);
+                       const float* beta, float eps, int act, float* scratch, void* y, void* stream);
 
 /* ---- LayerNorm over the last dim — BasicTransformerBlock.norm1/2/3 attention.py:206-208 ---------- */
 int vdb_layernorm(const void* x, long long rows, int C, const float* gamma, const float* beta, float eps, void* y,

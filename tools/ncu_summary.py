@@ -1,0 +1,18 @@
+"""ncu -i <rep> --page raw --csv  ->  compact per-launch table of the metrics DESIGN.md/bench.py quote."""
+import csv, subprocess, sys
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__grid_size",
+        "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "sm__cycles_elapsed.avg"]
+for rep in sys.argv[1:]:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    print(f"# {rep}")
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        print(d.get("Kernel Name", "?")[:70])
+        for w in WANT:
+            if w in d:
+                print(f"    {w:75s} {d[w]:>16s} {units[hdr.index(w)]}")

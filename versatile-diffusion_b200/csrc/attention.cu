@@ -41,14 +41,26 @@ struct alignas(64) AttnParams {
   long long ldo;
 };
 
-template <int DK, int DVP, int KV_STAGES>
-__global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
+VDB_DEVINL float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// SB = S accumulator buffers in TMEM (1 or 2), PB = P buffers in smem (1 or 2). SB = PB = 1 keeps the CTA at
+// <= 110 KB smem / 256 TMEM columns so TWO CTAs share an SM: one CTA's softmax (MUFU-bound) overlaps the other's MMAs.
+template <int DK, int DVP, int KV_STAGES, int SB, int PB>
+__global__ void __launch_bounds__(kAttThreads, (SB == 1 && PB == 1) ? 2 : 1)
+attention_kernel(const __grid_constant__ AttnParams p) {
   constexpr int KA = DK / 64;                      // 64-wide K atoms of the QK^T reduction
   constexpr uint32_t kQBytes = KA * kBQ * 128;     // Q tile
   constexpr uint32_t kKBytes = KA * kBKV * 128;    // one K stage
   constexpr uint32_t kVAtom = DVP * 128;           // one 64-kv atom of V^T
   constexpr uint32_t kVBytes = 2 * kVAtom;         // one V stage (128 kv)
   constexpr uint32_t kPBytes = 2 * kBQ * 128;      // one P buffer (128 x 128 bf16)
+  constexpr uint32_t kOCols = DVP <= 64 ? 64 : (DVP <= 128 ? 128 : 256);
+  constexpr uint32_t kTmemCols = (SB * 128 + kOCols <= 256) ? 256 : 512;
+  static_assert(SB * 128 + DVP <= 512, "TMEM budget");
   static_assert(kVAtom % 1024 == 0, "V atom must keep 1024B alignment");
   static_assert(DVP % 16 == 0 && DVP <= 256, "invalid UMMA N for PV");
 
@@ -58,7 +70,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
   uint8_t* sK = sQ + kQBytes;
   uint8_t* sV = sK + KV_STAGES * kKBytes;
   uint8_t* sP = sV + KV_STAGES * kVBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + PB * kPBytes);
   uint64_t* q_full = bars;            // 1
   uint64_t* k_full = bars + 1;        // [2]
   uint64_t* k_empty = bars + 3;       // [2]
@@ -94,13 +106,13 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_holder);
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_holder);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  const uint32_t tmem_S = tmem_base;        // 2 x 128 columns
-  const uint32_t tmem_O = tmem_base + 256;  // DVP columns
+  const uint32_t tmem_S = tmem_base;             // SB x 128 columns
+  const uint32_t tmem_O = tmem_base + SB * 128;  // DVP columns
 
   if (warp == 0) {
     if (lane == 0) {
@@ -131,7 +143,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
         const int st = j % KV_STAGES;
         mbar_wait(&k_full[st], (j / KV_STAGES) & 1);
         tc_fence_after();
-        const uint32_t d = tmem_S + (j & 1) * 128;
+        const uint32_t d = tmem_S + (j % SB) * 128;
 #pragma unroll
         for (int a = 0; a < KA; ++a) {
           const uint64_t qd = make_desc_sw128(smem_u32(sQ + a * kBQ * 128));
@@ -140,18 +152,18 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
           for (int k = 0; k < 4; ++k) umma_bf16_ss(d, qd + 2 * k, kd + 2 * k, idesc_s, (a > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&k_empty[st]);
-        umma_commit(&s_full[j & 1]);
+        umma_commit(&s_full[j % SB]);
       };
       mbar_wait(q_full, 0);
       issue_S(0);
-      // with a single KV stage, S_{j+1} can only be issued once K_{j+1} has landed, which needs S_j retired
-      if (ntiles > 1) issue_S(1);
+      if (SB == 2 && ntiles > 1) issue_S(1);
       for (int j = 0; j < ntiles; ++j) {
         const int st = j % KV_STAGES;
-        mbar_wait(p_full, j & 1);
+        mbar_wait(p_full, j & 1);                 // P_j written, O rescaled, S_j consumed
+        if (SB == 1 && j + 1 < ntiles) issue_S(j + 1);   // single S buffer: free now; queue it ahead of PV_j
         mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
         tc_fence_after();
-        const uint8_t* pb = sP + (j & 1) * kPBytes;
+        const uint8_t* pb = sP + (j % PB) * kPBytes;
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
           const uint64_t pd = make_desc_sw128(smem_u32(pb + a * kBQ * 128));
@@ -162,7 +174,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
         }
         umma_commit(&v_empty[st]);
         umma_commit(pv_done);
-        if (j + 2 < ntiles) issue_S(j + 2);
+        if (SB == 2 && j + 2 < ntiles) issue_S(j + 2);
       }
     }
   } else {
@@ -174,9 +186,9 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
     float m_ref = -INFINITY;  // reference max (raw score units)
     float l_sum = 0.f;
     for (int j = 0; j < ntiles; ++j) {
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      mbar_wait(&s_full[j % SB], (j / SB) & 1);
       tc_fence_after();
-      const uint32_t ts = tmem_S + (j & 1) * 128 + lane_off;
+      const uint32_t ts = tmem_S + (j % SB) * 128 + lane_off;
       const int kv0 = j * kBKV;
       const bool need_mask = (kv0 + kBKV > p.Nk) || p.causal;
       const int kv_lim = p.causal ? min(p.Nk, q_idx + 1) : p.Nk;  // valid kv indices are < kv_lim
@@ -206,14 +218,19 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
         const bool want = (m_new - m_ref) * p.scale_log2 > kRescaleThreshold;
         rescale = __any_sync(0xffffffffu, want);
         if (rescale) {
-          factor = exp2f((m_ref - m_new) * p.scale_log2);  // m_ref finite for j > 0
+          factor = ex2_approx((m_ref - m_new) * p.scale_log2);  // m_ref finite for j > 0
           m_ref = m_new;
           l_sum *= factor;
         }
       }
       const float m_scaled = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;
       // pass 2: P = exp2(s*scale - m), row sum, bf16 -> swizzled smem
-      uint8_t* prow = sP + (j & 1) * kPBytes + r * 128;
+      // single P buffer: PV_{j-1} must have finished reading it (and O must be settled) before pass 2
+      if (PB == 1 && j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+      }
+      uint8_t* prow = sP + (j % PB) * kPBytes + r * 128;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
@@ -222,7 +239,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
         float pf[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float e = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_scaled));
+          float e = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_scaled));
           if (need_mask && !(kv0 + c * 32 + i < kv_lim)) e = 0.f;
           pf[i] = e;
           l_sum += e;
@@ -238,8 +255,10 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
       }
       // O must be settled (PV_{j-1} retired) before it is rescaled / accumulated into again
       if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);
-        tc_fence_after();
+        if (PB == 2) {
+          mbar_wait(pv_done, (j - 1) & 1);
+          tc_fence_after();
+        }
         if (rescale) {
 #pragma unroll 1
           for (int c = 0; c < DVP / 16; ++c) {
@@ -288,23 +307,23 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
+  if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
-template <int DK, int DVP, int KV_STAGES>
+template <int DK, int DVP, int KV_STAGES, int SB, int PB>
 static int launch_attention(const AttnParams& p, int B, int H, cudaStream_t stream) {
   constexpr int KA = DK / 64;
-  constexpr size_t smem = KA * kBQ * 128 + KV_STAGES * (KA * kBKV * 128 + 2 * DVP * 128) + 2 * (2 * kBQ * 128) +
+  constexpr size_t smem = KA * kBQ * 128 + KV_STAGES * (KA * kBKV * 128 + 2 * DVP * 128) + PB * (2 * kBQ * 128) +
                           13 * 8 + 16 + 1024;
   static_assert(smem <= 227 * 1024, "attention smem budget");
   static bool configured = false;
   if (!configured) {
-    VDB_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<DK, DVP, KV_STAGES>,
+    VDB_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<DK, DVP, KV_STAGES, SB, PB>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = true;
   }
   dim3 grid((p.Nq + kBQ - 1) / kBQ, H, B);
-  attention_kernel<DK, DVP, KV_STAGES><<<grid, kAttThreads, smem, stream>>>(p);
+  attention_kernel<DK, DVP, KV_STAGES, SB, PB><<<grid, kAttThreads, smem, stream>>>(p);
   VDB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return VDB_OK;
@@ -354,10 +373,10 @@ int vdb_attention_bf16(const void* Q, long long ldq, int q_col0, const void* K, 
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (DK == 64 && DVP == 48) return launch_attention<64, 48, 2>(p, B, H, st);
-  if (DK == 64 && DVP == 64) return launch_attention<64, 64, 2>(p, B, H, st);
-  if (DK == 128 && DVP == 80) return launch_attention<128, 80, 2>(p, B, H, st);
-  if (DK == 192 && DVP == 160) return launch_attention<192, 160, 1>(p, B, H, st);
+  if (DK == 64 && DVP == 48) return launch_attention<64, 48, 2, 1, 1>(p, B, H, st);   // 2 CTAs / SM
+  if (DK == 64 && DVP == 64) return launch_attention<64, 64, 2, 1, 1>(p, B, H, st);   // 2 CTAs / SM
+  if (DK == 128 && DVP == 80) return launch_attention<128, 80, 2, 2, 2>(p, B, H, st);
+  if (DK == 192 && DVP == 160) return launch_attention<192, 160, 1, 2, 2>(p, B, H, st);
   return set_error(VDB_ERR_UNSUPPORTED, "attention: no kernel for d_head %d", d_head);
 }
 

@@ -88,18 +88,25 @@ __global__ void axpby_kernel(const float* __restrict__ x, const float* __restric
 // ---------------------------------------------------------------------------------------------
 constexpr int kGnThreads = 512;
 
+// scratch layout (floats): [kGnMaxBatch arrival counters (int), always at the front so that calls with different
+// shapes never alias them][B*2*groups {mean, rstd}][B*nsplit*2*groups partial sums]
+constexpr int kGnMaxBatch = 1024;
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1,
                                                               const __nv_bfloat16* __restrict__ x2, int C2,
-                                                              int HW, int groups, float* __restrict__ partial) {
+                                                              int HW, int groups, float eps, float* __restrict__ scratch) {
   const int C = C1 + C2;
   const int V = C / 8;
   const int cpg = C / groups;
-  const int b = blockIdx.y, split = blockIdx.x, nsplit = gridDim.x;
+  const int b = blockIdx.y, split = blockIdx.x, nsplit = gridDim.x, B = gridDim.y;
+  int* counters = reinterpret_cast<int*>(scratch);
+  float* stats = scratch + kGnMaxBatch;
+  float* partial = stats + static_cast<size_t>(B) * 2 * groups;
   const int pix_per = (HW + nsplit - 1) / nsplit;
   const int p_begin = split * pix_per;
   const int p_end = min(HW, p_begin + pix_per);
-  // deterministic two-level reduction (no atomics): [pixel lane][channel][sum|sumsq] -> channel -> group
+  // deterministic two-level reduction (no float atomics): [pixel lane][channel][sum|sumsq] -> channel -> group
   __shared__ float part[kGnThreads * 16];
+  __shared__ int is_last;
   const int lanes = kGnThreads / V;  // pixel lanes (>= 1 because V <= 512)
   const int v = threadIdx.x % V;
   const int pl = threadIdx.x / V;
@@ -110,9 +117,25 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __nv_bfloat1
     const bool first = v * 8 < C1;
     const __nv_bfloat16* src = first ? x1 + static_cast<long long>(b) * HW * C1 + v * 8
                                      : x2 + static_cast<long long>(b) * HW * C2 + (v * 8 - C1);
-    const int Cs = first ? C1 : C2;
-    for (int p = p_begin + pl; p < p_end; p += lanes) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(p) * Cs));
+    const long long Cs = first ? C1 : C2;
+    int p = p_begin + pl;
+    for (; p + 3 * lanes < p_end; p += 4 * lanes) {   // 4 independent 16-byte loads in flight per thread
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(src + (p + k * lanes) * Cs));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack_bf16x2(w[i]);
+          s[2 * i] += f.x; q[2 * i] += f.x * f.x;
+          s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+        }
+      }
+    }
+    for (; p < p_end; p += lanes) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + p * Cs));
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -145,41 +168,49 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __nv_bfloat1
     float* o = partial + (static_cast<long long>(b) * nsplit + split) * 2 * groups + 2 * threadIdx.x;
     o[0] = s; o[1] = q;
   }
+  // the last CTA of this batch item to finish folds the partials (fixed order => deterministic) into mean / rstd
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(&counters[b], 1) == nsplit - 1);
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (threadIdx.x < groups) {
+      float s = 0.f, q = 0.f;
+      const float* pp = partial + static_cast<long long>(b) * nsplit * 2 * groups + 2 * threadIdx.x;
+#pragma unroll 4
+      for (int i = 0; i < nsplit; ++i) { s += __ldcg(pp + static_cast<long long>(i) * 2 * groups); q += __ldcg(pp + static_cast<long long>(i) * 2 * groups + 1); }
+      const float inv_n = 1.0f / (static_cast<float>(HW) * cpg);
+      const float mean = s * inv_n;
+      const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+      stats[(static_cast<long long>(b) * groups + threadIdx.x) * 2] = mean;
+      stats[(static_cast<long long>(b) * groups + threadIdx.x) * 2 + 1] = rsqrtf(var + eps);
+    }
+    if (threadIdx.x == 0) counters[b] = 0;   // ready for the next launch (stream-ordered reuse of the scratch)
+  }
 }
 
 // y = act((x - mean) * rstd * gamma + beta), written as one concatenated NHWC bf16 tensor.
 // grid (nblk, B), block 256; dynamic smem = 2*C floats (per-channel scale/shift).
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int C1,
                                                        const __nv_bfloat16* __restrict__ x2, int C2, int HW,
-                                                       int groups, const float* __restrict__ partial, int nsplit,
+                                                       int groups, const float* __restrict__ stats,
                                                        const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, float eps, int act,
+                                                       const float* __restrict__ beta, int act,
                                                        __nv_bfloat16* __restrict__ y) {
   extern __shared__ float sm[];
   const int C = C1 + C2;
   const int cpg = C / groups;
   float* scale = sm;
   float* shift = sm + C;
-  __shared__ float gmean[32], grstd[32];
   const int b = blockIdx.y;
-  if (threadIdx.x < groups) {
-    float s = 0.f, q = 0.f;
-    for (int i = 0; i < nsplit; ++i) {
-      const float* pp = partial + (static_cast<long long>(b) * nsplit + i) * 2 * groups + 2 * threadIdx.x;
-      s += pp[0]; q += pp[1];
-    }
-    const float inv_n = 1.0f / (static_cast<float>(HW) * cpg);
-    const float mean = s * inv_n;
-    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
-    gmean[threadIdx.x] = mean;
-    grstd[threadIdx.x] = rsqrtf(var + eps);
-  }
-  __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
-    const float sc = grstd[g] * __ldg(gamma + c);
+    const float mean = stats[(static_cast<long long>(b) * groups + g) * 2];
+    const float rstd = stats[(static_cast<long long>(b) * groups + g) * 2 + 1];
+    const float sc = rstd * __ldg(gamma + c);
     scale[c] = sc;
-    shift[c] = __ldg(beta + c) - gmean[g] * sc;
+    shift[c] = __ldg(beta + c) - mean * sc;
   }
   __syncthreads();
   const int V = C / 8;
@@ -528,33 +559,41 @@ int vdb_add_int(int* p, int delta, void* stream) {
   return VDB_OK;
 }
 
-// partial must hold B * nsplit * 2 * groups floats; returns nsplit through *nsplit_out when partial == null
+// scratch: ZERO-INITIALISED device buffer of vdb_groupnorm_scratch_floats(B, HW) floats (reusable across calls on
+// one stream: the kernels leave its counters at zero)
 int vdb_groupnorm_nsplit(int B, int HW) {
-  int ns = (HW + 255) / 256;
-  const int want = std::max(1, (2 * num_sms()) / std::max(B, 1));
+  int ns = (HW + 127) / 128;
+  const int want = std::max(1, (4 * num_sms()) / std::max(B, 1));
   ns = std::min(ns, want);
   ns = std::min(ns, 256);
   return std::max(ns, 1);
 }
+long long vdb_groupnorm_scratch_floats(int B, int HW) {
+  const long long ns = vdb_groupnorm_nsplit(B, HW);
+  return kGnMaxBatch + static_cast<long long>(B) * 64 + static_cast<long long>(B) * ns * 64;
+}
 
 int vdb_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int B, int HW, int groups, const float* gamma,
-                       const float* beta, float eps, int act, float* partial, void* y, void* stream) {
+                       const float* beta, float eps, int act, float* scratch, void* y, void* stream) {
   const int C = C1 + (x2 ? C2 : 0);
-  if (!x1 || !gamma || !beta || !partial || !y) return set_error(VDB_ERR_INVALID, "groupnorm: null argument");
+  if (!x1 || !gamma || !beta || !scratch || !y) return set_error(VDB_ERR_INVALID, "groupnorm: null argument");
+  if (B > kGnMaxBatch) return set_error(VDB_ERR_UNSUPPORTED, "groupnorm: batch > %d", kGnMaxBatch);
   if (groups != 32 || (C % groups) || (C1 % 8) || (x2 && (C2 % 8)) || C / 8 > kGnThreads)
     return set_error(VDB_ERR_UNSUPPORTED, "groupnorm: need 32 groups, C %% 32 == 0, C/8 <= 512 (C=%d)", C);
   if (!x2) C2 = 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nsplit = vdb_groupnorm_nsplit(B, HW);
   gn_stats_kernel<<<dim3(nsplit, B), kGnThreads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x1), C1,
-                                                         reinterpret_cast<const __nv_bfloat16*>(x2), C2, HW, groups,
-                                                         partial);
+                                                         reinterpret_cast<const __nv_bfloat16*>(x2), C2, HW, groups, eps,
+                                                         scratch);
   VDB_CUDA_CHECK(cudaGetLastError());
+  const float* stats = scratch + kGnMaxBatch;
   const long long work = static_cast<long long>(HW) * (C / 8);
-  int nblk = static_cast<int>(std::min<long long>((work + 255) / 256, std::max(1, (num_sms() * 8) / std::max(B, 1))));
+  // ~8 vectors per thread: amortises the per-CTA scale/shift prologue
+  int nblk = static_cast<int>(std::min<long long>((work + 2047) / 2048, std::max(1, (num_sms() * 8) / std::max(B, 1))));
   gn_apply_kernel<<<dim3(nblk, B), 256, 2 * C * sizeof(float), st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x1), C1, reinterpret_cast<const __nv_bfloat16*>(x2), C2, HW, groups,
-      partial, nsplit, gamma, beta, eps, act, reinterpret_cast<__nv_bfloat16*>(y));
+      stats, gamma, beta, act, reinterpret_cast<__nv_bfloat16*>(y));
   VDB_CUDA_CHECK(cudaGetLastError());
   count_launch(2);
   return VDB_OK;

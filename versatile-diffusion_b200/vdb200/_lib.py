@@ -33,6 +33,7 @@ SIGNATURES = {
     "vdb_attention_dv_pad": (i, [i]),
     "vdb_attention_bf16": (i, [p, ll, i, p, ll, i, p, ll, p, ll, i, i, i, i, i, i, i, f, i, p]),
     "vdb_groupnorm_nsplit": (i, [i, i]),
+    "vdb_groupnorm_scratch_floats": (ll, [i, i]),
     "vdb_groupnorm_nhwc": (i, [p, i, p, i, i, i, i, p, p, f, i, p, p, p]),
     "vdb_layernorm": (i, [p, ll, i, p, p, f, p, p]),
     "vdb_upsample2x_nhwc": (i, [p, i, i, i, i, p, p]),

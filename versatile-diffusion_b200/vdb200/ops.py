@@ -95,6 +95,21 @@ def profile_stop():
     return out
 
 
+_gn_scratch_buf = {}
+
+
+def _gn_scratch(device, nfloats):
+    """Persistent zero-initialised GroupNorm scratch per device (the kernels restore its counters to zero)."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    buf = _gn_scratch_buf.get(key)
+    if buf is None or buf.numel() < nfloats:
+        if buf is not None and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("GroupNorm scratch must be sized before CUDA-graph capture (run one eager step first)")
+        buf = torch.zeros(max(int(nfloats), 1 << 20), dtype=torch.float32, device=device)
+        _gn_scratch_buf[key] = buf
+    return buf
+
+
 def launch_count():
     return int(lib.vdb_launch_count())
 
@@ -216,8 +231,7 @@ def groupnorm(x1, gamma, beta, eps, act=ACT_NONE, x2=None, out=None, groups=32):
     HW = x1.numel() // (B * C1)
     if out is None:
         out = torch.empty(x1.shape[:-1] + (C1 + C2,), dtype=BF16, device=x1.device)
-    nsplit = lib.vdb_groupnorm_nsplit(B, HW)
-    partial = torch.empty(B * nsplit * 2 * groups, dtype=torch.float32, device=x1.device)
+    partial = _gn_scratch(x1.device, lib.vdb_groupnorm_scratch_floats(B, HW))
     with _Span("groupnorm", 0.0, 2.0 * 3 * B * HW * (C1 + C2)):
         check(lib.vdb_groupnorm_nhwc(_ptr(x1), C1, _ptr(x2), C2, B, HW, groups, _ptr(gamma), _ptr(beta), float(eps),
                                      int(act), _ptr(partial), _ptr(out), _stream()), "groupnorm_nhwc")
