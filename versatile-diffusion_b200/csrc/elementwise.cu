@@ -94,6 +94,8 @@ constexpr int kGnMaxBatch = 1024;
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1,
                                                               const __nv_bfloat16* __restrict__ x2, int C2,
                                                               int HW, int groups, float eps, float* __restrict__ scratch) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = C1 + C2;
   const int V = C / 8;
   const int cpg = C / groups;
@@ -199,6 +201,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
                                                        const float* __restrict__ beta, int act,
                                                        __nv_bfloat16* __restrict__ y) {
   extern __shared__ float sm[];
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = C1 + C2;
   const int cpg = C / groups;
   float* scale = sm;
@@ -215,84 +219,113 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
   __syncthreads();
   const int V = C / 8;
   const long long total = static_cast<long long>(HW) * V;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = static_cast<int>(i % V);
-    const long long p = i / V;
-    const int c0 = v * 8;
-    const uint4 u = (c0 < C1)
-                        ? __ldg(reinterpret_cast<const uint4*>(x1 + (static_cast<long long>(b) * HW + p) * C1 + c0))
-                        : __ldg(reinterpret_cast<const uint4*>(x2 + (static_cast<long long>(b) * HW + p) * C2 + (c0 - C1)));
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-    uint32_t o[4];
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const __nv_bfloat16* xb1 = x1 + static_cast<long long>(b) * HW * C1;
+  const __nv_bfloat16* xb2 = x2 ? x2 + static_cast<long long>(b) * HW * C2 : nullptr;
+  __nv_bfloat16* yb = y + static_cast<long long>(b) * HW * C;
+  for (long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    uint4 u[4];
+    int c0[4];
+    long long pp[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {   // issue up to 4 independent 16-byte loads before touching any of them
+      const long long i = i0 + k * stride;
+      if (i < total) {
+        const int v = static_cast<int>(i % V);
+        pp[k] = i / V;
+        c0[k] = v * 8;
+        u[k] = (c0[k] < C1) ? __ldg(reinterpret_cast<const uint4*>(xb1 + pp[k] * C1 + c0[k]))
+                            : __ldg(reinterpret_cast<const uint4*>(xb2 + pp[k] * C2 + (c0[k] - C1)));
+      }
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float2 f = unpack_bf16x2(w[k]);
-      float a = f.x * scale[c0 + 2 * k] + shift[c0 + 2 * k];
-      float bb = f.y * scale[c0 + 2 * k + 1] + shift[c0 + 2 * k + 1];
-      if (act == 1) { a = silu_f(a); bb = silu_f(bb); }
-      o[k] = pack_bf16x2(a, bb);
+      if (i0 + k * stride < total) {
+        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = unpack_bf16x2(w[q]);
+          float a = f.x * scale[c0[k] + 2 * q] + shift[c0[k] + 2 * q];
+          float bb = f.y * scale[c0[k] + 2 * q + 1] + shift[c0[k] + 2 * q + 1];
+          if (act == 1) { a = silu_f(a); bb = silu_f(bb); }
+          o[q] = pack_bf16x2(a, bb);
+        }
+        *reinterpret_cast<uint4*>(yb + pp[k] * C + c0[k]) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
     }
-    *reinterpret_cast<uint4*>(y + (static_cast<long long>(b) * HW + p) * C + c0) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // LayerNorm over the last dim of [rows, C] bf16 (one warp per row, two-pass in registers).
 // ---------------------------------------------------------------------------------------------
-template <int MAXV>  // max 16-byte vectors per lane
+template <int MAXV, int R>  // MAXV: max 16-byte vectors per lane; R: rows processed concurrently per warp (memory-level parallelism)
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps,
                                                         __nv_bfloat16* __restrict__ y) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int V = C / 8;
-  for (long long r = warp; r < rows; r += nwarps) {
-    float f[MAXV][8];
-    float s = 0.f;
+  for (long long r0 = static_cast<long long>(warp) * R; r0 < rows; r0 += static_cast<long long>(nwarps) * R) {
+    uint4 raw[R][MAXV];
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int v = lane + i * 32;
-      if (v < V) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + r * C + v * 8));
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int j = 0; j < R; ++j)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 t = unpack_bf16x2(w[k]);
-          f[i][2 * k] = t.x; f[i][2 * k + 1] = t.y;
-          s += t.x + t.y;
+      for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + i * 32;
+        if (v < V && r0 + j < rows) raw[j][i] = __ldg(reinterpret_cast<const uint4*>(x + (r0 + j) * C + v * 8));
+      }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      if (r0 + j >= rows) break;   // warp-uniform
+      float f[MAXV][8];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        if (lane + i * 32 < V) {
+          const uint32_t w[4] = {raw[j][i].x, raw[j][i].y, raw[j][i].z, raw[j][i].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 t = unpack_bf16x2(w[k]);
+            f[i][2 * k] = t.x; f[i][2 * k + 1] = t.y;
+            s += t.x + t.y;
+          }
         }
       }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / C;
-    float q = 0.f;
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s / C;
+      float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      if (lane + i * 32 < V) {
+      for (int i = 0; i < MAXV; ++i) {
+        if (lane + i * 32 < V) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { const float d = f[i][k] - mean; q += d * d; }
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q / C + eps);
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int v = lane + i * 32;
-      if (v < V) {
-        uint32_t o[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = v * 8 + 2 * k;
-          const float a = (f[i][2 * k] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-          const float b2 = (f[i][2 * k + 1] - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
-          o[k] = pack_bf16x2(a, b2);
+          for (int k = 0; k < 8; ++k) { const float d = f[i][k] - mean; q += d * d; }
         }
-        *reinterpret_cast<uint4*>(y + r * C + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q / C + eps);
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + i * 32;
+        if (v < V) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            o[k] = pack_bf16x2((f[i][2 * k] - mean) * rstd * gg[2 * k] + bb[2 * k],
+                               (f[i][2 * k + 1] - mean) * rstd * gg[2 * k + 1] + bb[2 * k + 1]);
+          *reinterpret_cast<uint4*>(y + (r0 + j) * C + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
       }
     }
   }
@@ -447,36 +480,50 @@ __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restri
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
-  for (int n = blockIdx.x * nwarps + warp; n < N; n += gridDim.x * nwarps) {
-    float acc[16];
+  constexpr int NC = 4;  // output columns per warp iteration: NC independent weight streams in flight
+  for (int n0 = (blockIdx.x * nwarps + warp) * NC; n0 < N; n0 += gridDim.x * nwarps * NC) {
+    float acc[NC][16];
 #pragma unroll
-    for (int m = 0; m < 16; ++m) acc[m] = 0.f;
-    const __nv_bfloat16* wr = Wt + static_cast<long long>(n) * K;
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int m = 0; m < 16; ++m) acc[c][m] = 0.f;
     for (int k = lane * 8; k < K; k += 256) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(wr + k));
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-      float wf[8];
+      uint4 u[NC];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { const float2 t = unpack_bf16x2(w[q]); wf[2 * q] = t.x; wf[2 * q + 1] = t.y; }
+      for (int c = 0; c < NC; ++c)
+        if (n0 + c < N) u[c] = __ldg(reinterpret_cast<const uint4*>(Wt + static_cast<long long>(n0 + c) * K + k));
 #pragma unroll
-      for (int m = 0; m < 16; ++m) {
-        if (m < M) {
-          const float* xr = xs + m * K + k;
+      for (int c = 0; c < NC; ++c) {
+        if (n0 + c < N) {
+          const uint32_t w[4] = {u[c].x, u[c].y, u[c].z, u[c].w};
+          float wf[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) acc[m] += xr[q] * wf[q];
+          for (int q = 0; q < 4; ++q) { const float2 t = unpack_bf16x2(w[q]); wf[2 * q] = t.x; wf[2 * q + 1] = t.y; }
+#pragma unroll
+          for (int m = 0; m < 16; ++m) {
+            if (m < M) {
+              const float* xr = xs + m * K + k;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) acc[c][m] += xr[q] * wf[q];
+            }
+          }
         }
       }
     }
 #pragma unroll
-    for (int m = 0; m < 16; ++m) {
-      if (m < M) {
-        float v = acc[m];
+    for (int c = 0; c < NC; ++c) {
+      if (n0 + c >= N) break;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) {
-          v += bias ? bias[n] : 0.f;
-          if (act_out == 1) v = silu_f(v);
-          out[static_cast<long long>(m) * N + n] = v;
+      for (int m = 0; m < 16; ++m) {
+        if (m < M) {
+          float v = acc[c][m];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0) {
+            v += bias ? bias[n0 + c] : 0.f;
+            if (act_out == 1) v = silu_f(v);
+            out[static_cast<long long>(m) * N + n0 + c] = v;
+          }
         }
       }
     }
@@ -583,18 +630,16 @@ int vdb_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int B, in
   if (!x2) C2 = 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nsplit = vdb_groupnorm_nsplit(B, HW);
-  gn_stats_kernel<<<dim3(nsplit, B), kGnThreads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x1), C1,
-                                                         reinterpret_cast<const __nv_bfloat16*>(x2), C2, HW, groups, eps,
-                                                         scratch);
-  VDB_CUDA_CHECK(cudaGetLastError());
+  VDB_CUDA_CHECK(launch_pdl(gn_stats_kernel, dim3(nsplit, B), dim3(kGnThreads), 0, st,
+                            reinterpret_cast<const __nv_bfloat16*>(x1), C1, reinterpret_cast<const __nv_bfloat16*>(x2), C2,
+                            HW, groups, eps, scratch));
   const float* stats = scratch + kGnMaxBatch;
   const long long work = static_cast<long long>(HW) * (C / 8);
   // ~8 vectors per thread: amortises the per-CTA scale/shift prologue
   int nblk = static_cast<int>(std::min<long long>((work + 2047) / 2048, std::max(1, (num_sms() * 8) / std::max(B, 1))));
-  gn_apply_kernel<<<dim3(nblk, B), 256, 2 * C * sizeof(float), st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x1), C1, reinterpret_cast<const __nv_bfloat16*>(x2), C2, HW, groups,
-      stats, gamma, beta, act, reinterpret_cast<__nv_bfloat16*>(y));
-  VDB_CUDA_CHECK(cudaGetLastError());
+  VDB_CUDA_CHECK(launch_pdl(gn_apply_kernel, dim3(nblk, B), dim3(256), 2 * C * sizeof(float), st,
+                            reinterpret_cast<const __nv_bfloat16*>(x1), C1, reinterpret_cast<const __nv_bfloat16*>(x2), C2,
+                            HW, groups, stats, gamma, beta, act, reinterpret_cast<__nv_bfloat16*>(y)));
   count_launch(2);
   return VDB_OK;
 }
@@ -605,18 +650,17 @@ int vdb_layernorm(const void* x, long long rows, int C, const float* gamma, cons
   if ((C % 8) || C > 8 * 32 * 8) return set_error(VDB_ERR_UNSUPPORTED, "layernorm: C must be a multiple of 8, <= 2048");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int threads = 256;
-  const int blocks = static_cast<int>(std::min<long long>((rows + 7) / 8, num_sms() * 8LL));
   const int V = C / 8;
+  const int R = V <= 64 ? 4 : (V <= 160 ? 2 : 1);
+  const int blocks = static_cast<int>(std::min<long long>((rows + 8 * R - 1) / (8 * R), num_sms() * 8LL));
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
   if (V <= 64)
-    layernorm_kernel<2><<<blocks, threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, C, gamma, beta, eps,
-                                                    reinterpret_cast<__nv_bfloat16*>(y));
+    VDB_CUDA_CHECK(launch_pdl(layernorm_kernel<2, 4>, dim3(blocks), dim3(threads), 0, st, xp, rows, C, gamma, beta, eps, yp));
   else if (V <= 160)
-    layernorm_kernel<5><<<blocks, threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, C, gamma, beta, eps,
-                                                    reinterpret_cast<__nv_bfloat16*>(y));
+    VDB_CUDA_CHECK(launch_pdl(layernorm_kernel<5, 2>, dim3(blocks), dim3(threads), 0, st, xp, rows, C, gamma, beta, eps, yp));
   else
-    layernorm_kernel<8><<<blocks, threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, C, gamma, beta, eps,
-                                                    reinterpret_cast<__nv_bfloat16*>(y));
-  VDB_CUDA_CHECK(cudaGetLastError());
+    VDB_CUDA_CHECK(launch_pdl(layernorm_kernel<8, 1>, dim3(blocks), dim3(threads), 0, st, xp, rows, C, gamma, beta, eps, yp));
   count_launch();
   return VDB_OK;
 }
@@ -711,7 +755,7 @@ int vdb_linear_small(const float* x, int M, int K, const void* Wt, int N, const 
     VDB_CUDA_CHECK(cudaFuncSetAttribute(linear_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  const int blocks = std::min((N + 7) / 8, num_sms() * 2);
+  const int blocks = std::min((N + 31) / 32, num_sms() * 2);
   linear_small_kernel<<<blocks, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, M, K, reinterpret_cast<const __nv_bfloat16*>(Wt), N, bias, act_in, act_out, out);
   VDB_CUDA_CHECK(cudaGetLastError());

@@ -1,5 +1,6 @@
 #include "host_util.h"
 #include <cstdarg>
+#include <cstdlib>
 #include <atomic>
 #include <mutex>
 
@@ -16,6 +17,11 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VDB_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
 
 int num_sms() {
   static int sms = 0;

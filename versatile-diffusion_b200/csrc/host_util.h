@@ -11,6 +11,7 @@
 namespace vdb {
 
 int set_error(int code, const char* fmt, ...);   // records message, returns code
+bool pdl_enabled();                               // VDB_PDL=0 disables programmatic dependent launch
 int num_sms();
 void count_launch(int n = 1);
 
@@ -27,5 +28,20 @@ int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint
 int make_tmap_4d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
                  uint64_t stride1, uint64_t stride2, uint64_t stride3, uint32_t box0, uint32_t box1,
                  uint32_t box2, uint32_t box3);
+
+// Launch with the programmatic-stream-serialization attribute: the kernel's prologue may overlap the tail of
+// the previous kernel in the stream; every kernel launched this way calls pdl_wait() before reading its inputs.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 }  // namespace vdb

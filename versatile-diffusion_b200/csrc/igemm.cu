@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_launch_dependents();
+  pdl_wait();   // everything above overlapped the previous kernel's tail; global inputs are valid from here
 
   const int tilesM = p.tilesW * p.tilesH * p.tilesB;
   const int num_tiles = tilesM * p.tilesN * p.ksplit;
@@ -360,6 +362,8 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int kspl
                                      const float* __restrict__ bias, long long bias_bstride, int rows_per_batch,
                                      const __nv_bfloat16* __restrict__ resid, long long ldr, void* out,
                                      long long ldo, int out_f32, int act, float alpha) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = M * (N / 4);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -402,8 +406,7 @@ static int launch_igemm(const IgemmParams& p, int num_tiles, cudaStream_t stream
     configured = true;
   }
   const int grid = std::min(num_tiles, num_sms());
-  igemm_kernel<BN, STAGES><<<grid, kNumThreads, smem, stream>>>(p);
-  VDB_CUDA_CHECK(cudaGetLastError());
+  VDB_CUDA_CHECK(launch_pdl(igemm_kernel<BN, STAGES>, dim3(grid), dim3(kNumThreads), smem, stream, p));
   count_launch();
   return VDB_OK;
 }
@@ -482,10 +485,9 @@ static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot
     const long long total = M * (N / 4);
     const int threads = 256;
     const int blocks = static_cast<int>(std::min<long long>((total + threads - 1) / threads, num_sms() * 8LL));
-    splitk_reduce_kernel<<<blocks, threads, 0, stream>>>(p.partial, p.ksplit, M, static_cast<int>(N), p.bias,
-                                                         p.bias_bstride, p.rows_per_batch, p.resid, p.ldr, p.out,
-                                                         p.ldo, p.out_f32, p.act, p.alpha);
-    VDB_CUDA_CHECK(cudaGetLastError());
+    VDB_CUDA_CHECK(launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(threads), 0, stream, (const float*)p.partial,
+                              p.ksplit, M, static_cast<int>(N), p.bias, p.bias_bstride, p.rows_per_batch, p.resid,
+                              p.ldr, p.out, p.ldo, p.out_f32, p.act, p.alpha));
     count_launch();
   }
   return VDB_OK;
