@@ -235,10 +235,9 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         float pf[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          // alternate the SFU and the FMA-pipe polynomial so both pipes work on the same tile (MUFU alone
-          // caps d=40 self-attention at 16 exp/clk/SM)
-          const float t = fmaf(__uint_as_float(v[i]), p.scale_log2, -m_scaled);
-          float e = (i & 1) ? ex2_poly(t) : ex2_mufu(t);
+          // (measured: routing alternate elements through ex2_poly() on the FMA pipe is SLOWER at the current
+          //  occupancy — the softmax warps are issue/latency bound, not MUFU bound; revisit once they are)
+          float e = ex2_mufu(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_scaled));
           if (need_mask && !(kv0 + c * 32 + i < kv_lim)) e = 0.f;
           pf[i] = e;
           l_sum += e;

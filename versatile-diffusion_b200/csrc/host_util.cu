@@ -19,7 +19,7 @@ int set_error(int code, const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 bool pdl_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("VDB_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  if (v < 0) { const char* e = getenv("VDB_PDL"); v = (e && e[0] == '1') ? 1 : 0; }   // measured neutral inside the step graph: opt-in
   return v != 0;
 }
 

@@ -11,7 +11,7 @@
 namespace vdb {
 
 int set_error(int code, const char* fmt, ...);   // records message, returns code
-bool pdl_enabled();                               // VDB_PDL=0 disables programmatic dependent launch
+bool pdl_enabled();                               // VDB_PDL=1 enables programmatic dependent launch (default off)
 int num_sms();
 void count_launch(int n = 1);
 
