@@ -136,6 +136,22 @@ int vdb_timestep_embedding(const long long* ts, const int* step_idx, int B, int 
 int vdb_linear_small(const float* x, int M, int K, const void* Wt, int N, const float* bias, int act_in, int act_out,
                      float* out, void* stream);
 
+/* ---- CLIP context-encoder front/back ends — CLIPTextContextEncoder.encode clip.py:53-62, CLIPImageContextEncoder
+ *      ._encode / ._encode_wmask clip.py:88-143 (the arithmetic of transformers.CLIPModel around the encoder layers,
+ *      which run on vdb_layernorm / vdb_gemm_bf16 / vdb_attention_bf16).  Token streams are bf16 [B, Lp, C] with
+ *      Lp = L rounded up to a multiple of 8 and zero pad rows. ------------------------------------------------- */
+/* x[b,n] = token_embedding[tokens[b,n]] + position_embedding[n] */
+int vdb_clip_text_embed(const long long* tokens, const float* tok_emb, const float* pos_emb, int B, int L, int Lp, int C,
+                        void* x, void* stream);
+/* PxP patches of NCHW fp32 pixels -> bf16 [B*(HW/P)^2, Kpad] rows in the patch_embedding conv's (c,py,px) order */
+int vdb_patchify(const float* pixels, int B, int Cin, int HW, int P, int Kpad, void* y, void* stream);
+/* [class_embedding ; patch embeddings] + position_embedding, optional per-token scale (masked variant) */
+int vdb_vit_assemble(const void* patches, const float* cls, const float* pos, const float* tok_scale, int B, int L, int Lp,
+                     int C, void* x, void* stream);
+/* out[b,n,:] = z[b,n,:] / ||z[b, idx[b], :]|| [* row_scale[b,n]], fp32 [B,L,C] (idx NULL = token 0) */
+int vdb_scale_by_row_norm(const void* z, const int* idx, const float* row_scale, int B, int L, int Lp, int C, float* out,
+                          void* stream);
+
 /* ---- row softmax (VAE AttnBlock, autokl_modules.py:186-188) ------------------------------------- */
 int vdb_softmax_rows(const void* x, long long rows, int n, long long ld, float scale, void* y, void* stream);
 

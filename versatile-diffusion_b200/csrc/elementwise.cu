@@ -560,6 +560,97 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const __nv_bfloat16* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// CLIP front/back ends (HF CLIPModel arithmetic around the transformer blocks; reference call sites clip.py:57-62,
+// 95-101).  Token streams are stored [B, Lp, C] with Lp = L rounded up to 8 and zero pad rows.
+// ---------------------------------------------------------------------------------------------
+// x[b, n, :] = tok_emb[tokens[b, n], :] + pos_emb[n, :]          (CLIPTextEmbeddings)
+__global__ void clip_text_embed_kernel(const long long* __restrict__ tokens, const float* __restrict__ tok_emb,
+                                       const float* __restrict__ pos_emb, int B, int L, int Lp, int C,
+                                       __nv_bfloat16* __restrict__ x) {
+  const long long total = static_cast<long long>(B) * Lp * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const int n = static_cast<int>((i / C) % Lp);
+    const int b = static_cast<int>(i / (static_cast<long long>(C) * Lp));
+    float v = 0.f;
+    if (n < L) v = tok_emb[tokens[b * L + n] * C + c] + pos_emb[static_cast<long long>(n) * C + c];
+    x[i] = __float2bfloat16(v);
+  }
+}
+
+// non-overlapping PxP patches of NCHW fp32 pixels -> bf16 rows [B*G*G, Kpad], column (c*P + py)*P + px (the
+// flattening of the patch_embedding conv weight [C_out, 3, P, P]); zero padded to Kpad
+__global__ void patchify_kernel(const float* __restrict__ px, int B, int Cin, int HW, int P, int Kpad,
+                                __nv_bfloat16* __restrict__ y) {
+  const int G = HW / P;
+  const long long total = static_cast<long long>(B) * G * G * Kpad;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % Kpad);
+    const long long row = i / Kpad;
+    float v = 0.f;
+    if (k < Cin * P * P) {
+      const int c = k / (P * P), py = (k / P) % P, pxx = k % P;
+      const int gx = static_cast<int>(row % G), gy = static_cast<int>((row / G) % G);
+      const int b = static_cast<int>(row / (G * G));
+      v = px[((static_cast<long long>(b) * Cin + c) * HW + gy * P + py) * HW + gx * P + pxx];
+    }
+    y[i] = __float2bfloat16(v);
+  }
+}
+
+// x[b, 0] = cls + pos[0]; x[b, 1+j] = patch[b, j] + pos[1+j]; optional per-token scale (masked variant,
+// clip.py:117-133); rows >= L zero                                              (CLIPVisionEmbeddings)
+__global__ void vit_assemble_kernel(const __nv_bfloat16* __restrict__ patches, const float* __restrict__ cls,
+                                    const float* __restrict__ pos, const float* __restrict__ tok_scale, int B, int L,
+                                    int Lp, int C, __nv_bfloat16* __restrict__ x) {
+  const long long total = static_cast<long long>(B) * Lp * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const int n = static_cast<int>((i / C) % Lp);
+    const int b = static_cast<int>(i / (static_cast<long long>(C) * Lp));
+    float v = 0.f;
+    if (n < L) {
+      v = (n == 0) ? cls[c] : __bfloat162float(patches[(static_cast<long long>(b) * (L - 1) + n - 1) * C + c]);
+      v += pos[static_cast<long long>(n) * C + c];
+      if (tok_scale) v *= tok_scale[b * L + n];
+    }
+    x[i] = __float2bfloat16(v);
+  }
+}
+
+// out[b, n, :] = z[b, n, :] / || z[b, idx[b], :] ||  [* row_scale[b, n]]   (clip.py:60-61, 99-100, 142)
+__global__ void __launch_bounds__(256) scale_by_row_norm_kernel(const __nv_bfloat16* __restrict__ z,
+                                                                const int* __restrict__ idx,
+                                                                const float* __restrict__ row_scale, int L, int Lp,
+                                                                int C, float* __restrict__ out) {
+  __shared__ float red[8];
+  __shared__ float inv;
+  const int b = blockIdx.x;
+  const int r = idx ? idx[b] : 0;
+  const __nv_bfloat16* zr = z + (static_cast<long long>(b) * Lp + r) * C;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { const float v = __bfloat162float(zr[c]); s += v * v; }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+    inv = 1.0f / sqrtf(t);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < L * C; i += blockDim.x) {
+    const int n = i / C, c = i % C;
+    float v = __bfloat162float(z[(static_cast<long long>(b) * Lp + n) * C + c]) * inv;
+    if (row_scale) v *= row_scale[b * L + n];
+    out[(static_cast<long long>(b) * L + n) * C + c] = v;
+  }
+}
+
 static int ew_blocks(long long work_items, int threads) {
   long long b = (work_items + threads - 1) / threads;
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -758,6 +849,46 @@ int vdb_linear_small(const float* x, int M, int K, const void* Wt, int N, const 
   const int blocks = std::min((N + 31) / 32, num_sms() * 2);
   linear_small_kernel<<<blocks, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, M, K, reinterpret_cast<const __nv_bfloat16*>(Wt), N, bias, act_in, act_out, out);
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_clip_text_embed(const long long* tokens, const float* tok_emb, const float* pos_emb, int B, int L, int Lp, int C,
+                        void* x, void* stream) {
+  if (!tokens || !tok_emb || !pos_emb || !x || Lp < L) return set_error(VDB_ERR_INVALID, "clip_text_embed: bad argument");
+  clip_text_embed_kernel<<<ew_blocks(static_cast<long long>(B) * Lp * C, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      tokens, tok_emb, pos_emb, B, L, Lp, C, reinterpret_cast<__nv_bfloat16*>(x));
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_patchify(const float* pixels, int B, int Cin, int HW, int P, int Kpad, void* y, void* stream) {
+  if (!pixels || !y || HW % P || Cin * P * P > Kpad || (Kpad % 8)) return set_error(VDB_ERR_INVALID, "patchify: bad argument");
+  const int G = HW / P;
+  patchify_kernel<<<ew_blocks(static_cast<long long>(B) * G * G * Kpad, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      pixels, B, Cin, HW, P, Kpad, reinterpret_cast<__nv_bfloat16*>(y));
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_vit_assemble(const void* patches, const float* cls, const float* pos, const float* tok_scale, int B, int L, int Lp,
+                     int C, void* x, void* stream) {
+  if (!patches || !cls || !pos || !x || Lp < L) return set_error(VDB_ERR_INVALID, "vit_assemble: bad argument");
+  vit_assemble_kernel<<<ew_blocks(static_cast<long long>(B) * Lp * C, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(patches), cls, pos, tok_scale, B, L, Lp, C, reinterpret_cast<__nv_bfloat16*>(x));
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_scale_by_row_norm(const void* z, const int* idx, const float* row_scale, int B, int L, int Lp, int C, float* out,
+                          void* stream) {
+  if (!z || !out || B <= 0 || Lp < L) return set_error(VDB_ERR_INVALID, "scale_by_row_norm: bad argument");
+  scale_by_row_norm_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(z), idx, row_scale, L, Lp, C, out);
   VDB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return VDB_OK;

@@ -46,6 +46,10 @@ SIGNATURES = {
     "vdb_timestep_embedding": (i, [p, p, i, i, f, p, p]),
     "vdb_linear_small": (i, [p, i, i, p, i, p, i, i, p, p]),
     "vdb_softmax_rows": (i, [p, ll, i, ll, f, p, p]),
+    "vdb_clip_text_embed": (i, [p, p, p, i, i, i, i, p, p]),
+    "vdb_patchify": (i, [p, i, i, i, i, i, p, p]),
+    "vdb_vit_assemble": (i, [p, p, p, p, i, i, i, i, p, p]),
+    "vdb_scale_by_row_norm": (i, [p, p, p, i, i, i, i, p, p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

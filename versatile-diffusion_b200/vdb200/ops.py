@@ -362,3 +362,41 @@ def softmax_rows(x, scale=1.0, out=None):
     check(lib.vdb_softmax_rows(_ptr(x), rows, n, x.stride(-2) if x.dim() > 1 else n, float(scale), _ptr(out), _stream()),
           "softmax_rows")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ CLIP ends
+def clip_text_embed(tokens, tok_emb, pos_emb, Lp):
+    _need(tokens, torch.int64, "tokens"); _need(tok_emb, torch.float32, "tok_emb"); _need(pos_emb, torch.float32, "pos_emb")
+    B, L = tokens.shape
+    C = tok_emb.shape[1]
+    x = torch.empty((B, Lp, C), dtype=BF16, device=tokens.device)
+    check(lib.vdb_clip_text_embed(_ptr(tokens), _ptr(tok_emb), _ptr(pos_emb), B, L, Lp, C, _ptr(x), _stream()), "clip_text_embed")
+    return x
+
+
+def patchify(pixels, patch, kpad):
+    _need(pixels, torch.float32, "pixels")
+    B, Cin, H, W = pixels.shape
+    assert H == W
+    g = H // patch
+    y = torch.empty((B * g * g, kpad), dtype=BF16, device=pixels.device)
+    check(lib.vdb_patchify(_ptr(pixels), B, Cin, H, patch, kpad, _ptr(y), _stream()), "patchify")
+    return y
+
+
+def vit_assemble(patches, cls, pos, B, L, Lp, tok_scale=None):
+    _need(patches, BF16, "patches"); _need(cls, torch.float32, "cls"); _need(pos, torch.float32, "pos")
+    _need(tok_scale, torch.float32, "tok_scale")
+    C = patches.shape[1]
+    x = torch.empty((B, Lp, C), dtype=BF16, device=patches.device)
+    check(lib.vdb_vit_assemble(_ptr(patches), _ptr(cls), _ptr(pos), _ptr(tok_scale), B, L, Lp, C, _ptr(x), _stream()), "vit_assemble")
+    return x
+
+
+def scale_by_row_norm(z, L, idx=None, row_scale=None):
+    """z bf16 [B, Lp, C] -> fp32 [B, L, C] divided by the norm of row idx[b] (token 0 when idx is None)."""
+    _need(z, BF16, "z"); _need(idx, torch.int32, "idx"); _need(row_scale, torch.float32, "row_scale")
+    B, Lp, C = z.shape
+    out = torch.empty((B, L, C), dtype=torch.float32, device=z.device)
+    check(lib.vdb_scale_by_row_norm(_ptr(z), _ptr(idx), _ptr(row_scale), B, L, Lp, C, _ptr(out), _stream()), "scale_by_row_norm")
+    return out
