@@ -88,6 +88,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* sbias = reinterpret_cast<float*>(tmem_holder + 4);   // [BN] bias of the current output tile
+  auto epi_bar_sync = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };   // the four epilogue warps only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -202,6 +204,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
       const int w = wt * p.TW + tw, h = ht * p.TH + th, b = bt * p.TB + tb;
       const bool row_ok = (w < p.Wo) && (h < p.Ho) && (b < p.Bo);
       const long long gp = (static_cast<long long>(b) * p.Ho + h) * p.Wo + w;
+      const long long gp_first = (static_cast<long long>(bt * p.TB) * p.Ho + ht * p.TH) * p.Wo + wt * p.TW;
       const int n0 = n_idx * BN;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -233,65 +236,77 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
             }
           }
         }
-      } else if (p.act == ACT_GEGLU) {
-        // packed tile: columns [0,BN/2) = value rows, [BN/2,BN) = gate rows of the same outputs
-        constexpr int HALF = BN / 2;
-        const int nout0 = n_idx * HALF;
-        const int Nout = p.N / 2;
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + gp * p.ldo + nout0;
+      } else {
+        // ---- bias tile -> shared memory (one global read per tile instead of one per chunk per thread) ----
+        // one bias row serves the whole tile unless it is per-batch and the tile's first / last rows differ in batch
+        const long long gp_last = (static_cast<long long>(bt * p.TB + p.TB - 1) * p.Ho + ht * p.TH + p.TH - 1) * p.Wo +
+                                  wt * p.TW + p.TW - 1;
+        const bool bias_uniform =
+            p.bias && (p.bias_bstride == 0 || gp_first / p.rows_per_batch == gp_last / p.rows_per_batch);
+        if (bias_uniform) {
+          epi_bar_sync();                       // previous tile's readers are done with sbias
+          const float* brow = p.bias + (p.bias_bstride ? (gp_first / p.rows_per_batch) * p.bias_bstride : 0);
+          for (int i = threadIdx.x - 64; i < BN; i += 128) sbias[i] = (n0 + i < p.N) ? __ldg(brow + n0 + i) : 0.f;
+          epi_bar_sync();
+        }
+        const float* bias_g = (p.bias && !bias_uniform)
+                                  ? p.bias + (p.bias_bstride ? (gp / p.rows_per_batch) * p.bias_bstride : 0) : nullptr;
+        if (p.act == ACT_GEGLU) {
+          // packed tile: columns [0,BN/2) = value rows, [BN/2,BN) = gate rows of the same outputs
+          constexpr int HALF = BN / 2;
+          const int nout0 = n_idx * HALF;
+          const int Nout = p.N / 2;
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + gp * p.ldo + nout0;
 #pragma unroll 1
-        for (int c = 0; c < HALF / 32; ++c) {
-          uint32_t v[32], g[32];
-          tmem_ld32(trow + c * 32, v);
-          tmem_ld32(trow + HALF + c * 32, g);
-          tmem_wait_ld();
-          if (row_ok) {
-            uint32_t o[16];
+          for (int c = 0; c < HALF / 32; ++c) {
+            uint32_t v[32], g[32];
+            tmem_ld32(trow + c * 32, v);
+            tmem_ld32(trow + HALF + c * 32, g);
+            tmem_wait_ld();
+            if (row_ok) {
+              uint32_t o[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float a0 = __uint_as_float(v[j]), a1 = __uint_as_float(v[j + 1]);
-              float g0 = __uint_as_float(g[j]), g1 = __uint_as_float(g[j + 1]);
-              if (p.bias) {
-                a0 += __ldg(p.bias + n0 + c * 32 + j);
-                a1 += __ldg(p.bias + n0 + c * 32 + j + 1);
-                g0 += __ldg(p.bias + n0 + HALF + c * 32 + j);
-                g1 += __ldg(p.bias + n0 + HALF + c * 32 + j + 1);
+              for (int j = 0; j < 32; j += 2) {
+                float a0 = __uint_as_float(v[j]), a1 = __uint_as_float(v[j + 1]);
+                float g0 = __uint_as_float(g[j]), g1 = __uint_as_float(g[j + 1]);
+                if (p.bias) {
+                  a0 += sbias[c * 32 + j]; a1 += sbias[c * 32 + j + 1];
+                  g0 += sbias[HALF + c * 32 + j]; g1 += sbias[HALF + c * 32 + j + 1];
+                }
+                o[j / 2] = pack_bf16x2(a0 * gelu_fast_f(g0), a1 * gelu_fast_f(g1));
               }
-              o[j / 2] = pack_bf16x2(a0 * gelu_erf_f(g0), a1 * gelu_erf_f(g1));
-            }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (nout0 + c * 32 + j * 8 + 7 < Nout)
-                *reinterpret_cast<uint4*>(dst + c * 32 + j * 8) =
-                    make_uint4(o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]);
+              for (int j = 0; j < 4; ++j) {
+                if (nout0 + c * 32 + j * 8 + 7 < Nout)
+                  *reinterpret_cast<uint4*>(dst + c * 32 + j * 8) =
+                      make_uint4(o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]);
+              }
             }
           }
-        }
-      } else {
-        const float* bias = p.bias ? p.bias + (p.bias_bstride ? (gp / p.rows_per_batch) * p.bias_bstride : 0) : nullptr;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          if (n0 + c * 32 >= p.N) break;
-          uint32_t v[32];
-          tmem_ld32(trow + c * 32, v);
-          tmem_wait_ld();
-          if (row_ok) {
+        } else {
+          // ---- software-pipelined chunks: the TMEM load and the residual loads of chunk c+1 are in flight while
+          //      chunk c is converted and stored ----
+          const int nchunks = min(BN / 32, (p.N - n0 + 31) / 32);
+          const __nv_bfloat16* rs_row = p.resid ? p.resid + gp * p.ldr + n0 : nullptr;
+          auto load_resid = [&](int c, uint4 (&rr)[4]) {
+            if (rs_row && row_ok && n0 + c * 32 + 32 <= p.N) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) rr[j] = __ldg(reinterpret_cast<const uint4*>(rs_row + c * 32 + j * 8));
+            }
+          };
+          auto process = [&](int c, const uint32_t (&v)[32], const uint4 (&rr)[4]) {
+            if (!row_ok) return;
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
             const int nb = n0 + c * 32;
             const bool full = nb + 32 <= p.N;
-            if (bias) {
-              if (full) {
+            if (bias_uniform) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + nb + j));
-                  f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
-                }
-              } else {
+              for (int j = 0; j < 32; ++j) f[j] += sbias[c * 32 + j];
+            } else if (bias_g) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) if (nb + j < p.N) f[j] += __ldg(bias + nb + j);
-              }
+              for (int j = 0; j < 32; ++j) if (nb + j < p.N) f[j] += __ldg(bias_g + nb + j);
             }
             if (p.alpha != 1.f) {
 #pragma unroll
@@ -301,23 +316,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
             }
-            if (p.resid) {
-              const __nv_bfloat16* rs = p.resid + gp * p.ldr + nb;
+            if (rs_row) {
               if (full) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rs + j * 8));
-                  const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+                  const uint32_t w4[4] = {rr[j].x, rr[j].y, rr[j].z, rr[j].w};
 #pragma unroll
                   for (int q = 0; q < 4; ++q) {
-                    const float2 x = unpack_bf16x2(rr[q]);
+                    const float2 x = unpack_bf16x2(w4[q]);
                     f[j * 8 + q * 2] += x.x;
                     f[j * 8 + q * 2 + 1] += x.y;
                   }
                 }
               } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) if (nb + j < p.N) f[j] += __bfloat162float(rs[j]);
+                for (int j = 0; j < 32; ++j) if (nb + j < p.N) f[j] += __bfloat162float(rs_row[c * 32 + j]);
               }
             }
             if (p.out_f32) {
@@ -342,6 +355,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
 #pragma unroll
                 for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = __float2bfloat16(f[j]);
               }
+            }
+          };
+          uint32_t va[32], vb[32];
+          uint4 ra[4], rb[4];
+          tmem_ld32(trow, va);
+          load_resid(0, ra);
+#pragma unroll 1
+          for (int c = 0; c < nchunks; c += 2) {
+            tmem_wait_ld();                                  // va (chunk c) has landed
+            if (c + 1 < nchunks) { tmem_ld32(trow + (c + 1) * 32, vb); load_resid(c + 1, rb); }
+            process(c, va, ra);
+            if (c + 1 < nchunks) {
+              tmem_wait_ld();                                // vb (chunk c+1)
+              if (c + 2 < nchunks) { tmem_ld32(trow + (c + 2) * 32, va); load_resid(c + 2, ra); }
+              process(c + 1, vb, rb);
             }
           }
         }
@@ -398,7 +426,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int kspl
 // ----------------------------------------------------------------------------------------------
 template <int BN, int STAGES>
 static int launch_igemm(const IgemmParams& p, int num_tiles, cudaStream_t stream) {
-  constexpr size_t smem = STAGES * (kABytes + BN * kBlockK * 2) + (2 * STAGES + 4) * 8 + 16 + 1024;
+  constexpr size_t smem = STAGES * (kABytes + BN * kBlockK * 2) + (2 * STAGES + 4) * 8 + 16 + BN * 4 + 1024;
   static bool configured = false;
   if (!configured) {
     VDB_CUDA_CHECK(cudaFuncSetAttribute(igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
