@@ -9,10 +9,10 @@
 //     autokl_modules.py:42-141), with the 1x1 skip_connection of a channel-changing ResBlock folded
 //     in as extra K segments of the same accumulator.
 //
-// Structure: grid = #SMs (persistent, static round-robin over output tiles), 192 threads:
+// Structure: grid = #SMs (persistent, static round-robin over output tiles), 320 threads:
 //   warp 0   : TMA producer  (cp.async.bulk.tensor 4D box loads of A, 2D box loads of W)
 //   warp 1   : MMA issuer    (tcgen05.mma cta_group::1 kind::f16, 128 x BN x 16, fp32 accum in TMEM)
-//   warps 2-5: epilogue      (tcgen05.ld -> bias/act/residual -> bf16/fp32 global stores)
+//   warps 2-9: epilogue      (tcgen05.ld -> smem transpose -> bias/act/residual -> coalesced bf16 stores)
 // smem ring of STAGES x (A 128x64 bf16 | W BNx64 bf16), both 128B-swizzled K-major; TMEM holds two
 // accumulator stages (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
@@ -24,7 +24,9 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // bf16 elements = 128 B = one swizzle row
 constexpr int kMaxA = 6;     // A tensor maps per launch
 constexpr int kMaxSeg = 12;  // K segments per launch
-constexpr int kNumThreads = 192;
+constexpr int kNumEpiWarps = 8;
+constexpr int kNumEpiThreads = kNumEpiWarps * 32;
+constexpr int kNumThreads = 64 + kNumEpiThreads;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
 
 struct ASeg {
@@ -59,9 +61,18 @@ struct alignas(64) IgemmParams {
   int act;                    // 0 none, 1 silu, 2 gelu(erf), 3 quick_gelu, 4 geglu (packed halves)
   float alpha;                // out = act(alpha * (acc + bias)) + resid
   float* partial;             // split-K: [ksplit, M, N] fp32
+  unsigned long long* timeline; // debug: per-tile role timestamps of CTA 0 (null = off)
 };
 
 enum { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_QGELU = 3, ACT_GEGLU = 4 };
+
+VDB_DEVINL unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define VDB_TL(slot, it) do { if (p.timeline && blockIdx.x == 0 && (it) < 8) p.timeline[(it) * 16 + (slot)] = gtime(); } while (0)
+#define VDB_TLE(slot, it) do { if (warp == 2 && lane == 0) VDB_TL(slot, it); } while (0)
 
 VDB_DEVINL float apply_act(float v, int act) {
   switch (act) {
@@ -89,7 +100,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* sbias = reinterpret_cast<float*>(tmem_holder + 4);   // [BN] bias of the current output tile
-  auto epi_bar_sync = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };   // the four epilogue warps only
+  float* sstage = sbias + BN;                                  // kNumEpiWarps x [32][32] fp32 swizzled transposition tiles
+  auto epi_bar_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiThreads) : "memory"); };   // the epilogue warps only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -105,7 +117,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], kNumEpiWarps);
     }
     fence_barrier_init();
   }
@@ -137,6 +149,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
         const int kb_begin = ks * p.kb_per_split;
         const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
         int kb = 0;
+        VDB_TL(0, (t - blockIdx.x) / gridDim.x);   // producer: starts issuing this tile
         for (int s = 0; s < p.nseg; ++s) {
           const ASeg sg = p.seg[s];
           if (kb + sg.nkb <= kb_begin) { kb += sg.nkb; continue; }
@@ -166,8 +179,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
         const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
+        VDB_TL(1, it);                             // MMA: wants the accumulator stage
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
+        VDB_TL(2, it);                             // MMA: got it
         const uint32_t tmem_d = tmem_base + as * 256;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
@@ -183,13 +198,37 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[as]);
+        VDB_TL(3, it);                             // MMA: all MMAs of the tile issued
       }
     }
   } else {
     // ------------------------------ epilogue ------------------------------
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // Eight warps: warps w and w+4 own the same TMEM lane quarter (w & 3) and alternate 32-column chunks, so each
+    // SM sub-partition interleaves two epilogue warps (a single warp per sub-partition was measured to be
+    // instruction-latency bound: ~770 ns per chunk).  tcgen05.ld hands each thread one ROW of 32 columns; the
+    // warp writes the raw fp32 block to a private XOR-swizzled 4 KB shared-memory tile and reads it back
+    // transposed, so every global access is 8 rows x 64 contiguous bytes per instruction (4 lanes per row), and
+    // bias / activation / residual / bf16 conversion run on 8 fixed columns per lane (bias lives in registers).
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;      // which of the two warps of the quarter
     const int r = quarter * 32 + lane;
+    const int tr_row = lane >> 2, tr_q = lane & 3;   // transposed role: rows tr_row + 8k, columns tr_q*8 .. +7
+    float* stage = sstage + (warp - 2) * 1024;       // [32 rows][32 fp32], 16-byte chunk j of row i at (j ^ (i & 7))
+    auto stage_write = [&](const uint32_t (&v)[32]) {
+      float* srow = stage + lane * 32;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(srow + ((j ^ (lane & 7)) << 2)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    };
+    auto stage_read = [&](int k, float (&o)[8]) {   // row tr_row + 8k, columns tr_q*8 .. +7
+      const int row = k * 8 + tr_row;
+      const float* srow = stage + row * 32;
+      const float4 x0 = *reinterpret_cast<const float4*>(srow + (((2 * tr_q) ^ (row & 7)) << 2));
+      const float4 x1 = *reinterpret_cast<const float4*>(srow + (((2 * tr_q + 1) ^ (row & 7)) << 2));
+      o[0] = x0.x; o[1] = x0.y; o[2] = x0.z; o[3] = x0.w; o[4] = x1.x; o[5] = x1.y; o[6] = x1.z; o[7] = x1.w;
+    };
     int it = 0;
+    const float* sbias_src = nullptr;   // which bias row/offset currently sits in sbias
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int m_idx = t % tilesM;
       const int rest = t / tilesM;
@@ -208,8 +247,45 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
       const int n0 = n_idx * BN;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+
+      // per-tile row bookkeeping for the transposed role (independent of the accumulator: done before the wait)
+      long long gp_k[4];
+      bool ok_k[4];
+      {
+        const unsigned okmask = __ballot_sync(0xffffffffu, row_ok);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int src = k * 8 + tr_row;
+          const unsigned lo = __shfl_sync(0xffffffffu, static_cast<unsigned>(gp & 0xffffffffu), src);
+          const unsigned hi = __shfl_sync(0xffffffffu, static_cast<unsigned>(static_cast<unsigned long long>(gp) >> 32), src);
+          gp_k[k] = static_cast<long long>((static_cast<unsigned long long>(hi) << 32) | lo);
+          ok_k[k] = (okmask >> src) & 1u;
+        }
+      }
+      // bias tile -> shared memory (one global read per tile); one row serves the tile unless the bias is per-batch
+      // and the tile's first / last rows belong to different batch items
+      const long long gp_last = (static_cast<long long>(bt * p.TB + p.TB - 1) * p.Ho + ht * p.TH + p.TH - 1) * p.Wo +
+                                wt * p.TW + p.TW - 1;
+      const bool bias_uniform = p.bias && p.ksplit == 1 &&
+                                (p.bias_bstride == 0 || gp_first / p.rows_per_batch == gp_last / p.rows_per_batch);
+      if (bias_uniform) {
+        // consecutive tiles of a CTA usually share the N tile (M is the fast tile index): reload only on change,
+        // otherwise the ~0.7 us global-load latency + two barriers sit between every two tiles
+        const float* brow = p.bias + (p.bias_bstride ? (gp_first / p.rows_per_batch) * p.bias_bstride : 0) + n0;
+        if (brow != sbias_src) {              // uniform across the epilogue threads
+          epi_bar_sync();                     // previous tile's readers are done with sbias
+          for (int i = threadIdx.x - 64; i < BN; i += kNumEpiThreads) sbias[i] = (n0 + i < p.N) ? __ldg(brow + i) : 0.f;
+          epi_bar_sync();
+          sbias_src = brow;
+        }
+      }
+      const float* bias_g = (p.bias && !bias_uniform)
+                                ? p.bias + (p.bias_bstride ? (gp / p.rows_per_batch) * p.bias_bstride : 0) : nullptr;
+
+      VDB_TLE(4, it);   // epilogue: waiting for the accumulator
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
+      VDB_TLE(5, it);   // epilogue: accumulator complete
       const uint32_t trow = tmem_base + as * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
 
       if (p.ksplit > 1) {
@@ -217,7 +293,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
         const long long Mtot = static_cast<long long>(p.Bo) * p.Ho * p.Wo;
         float* dst = p.partial + (static_cast<long long>(ks) * Mtot + gp) * p.N + n0;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half; c < BN / 32; c += 2) {
+          if (n0 + c * 32 >= p.N) break;
           uint32_t v[32];
           tmem_ld32(trow + c * 32, v);
           tmem_wait_ld();
@@ -236,146 +313,140 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
             }
           }
         }
-      } else {
-        // ---- bias tile -> shared memory (one global read per tile instead of one per chunk per thread) ----
-        // one bias row serves the whole tile unless it is per-batch and the tile's first / last rows differ in batch
-        const long long gp_last = (static_cast<long long>(bt * p.TB + p.TB - 1) * p.Ho + ht * p.TH + p.TH - 1) * p.Wo +
-                                  wt * p.TW + p.TW - 1;
-        const bool bias_uniform =
-            p.bias && (p.bias_bstride == 0 || gp_first / p.rows_per_batch == gp_last / p.rows_per_batch);
-        if (bias_uniform) {
-          epi_bar_sync();                       // previous tile's readers are done with sbias
-          const float* brow = p.bias + (p.bias_bstride ? (gp_first / p.rows_per_batch) * p.bias_bstride : 0);
-          for (int i = threadIdx.x - 64; i < BN; i += 128) sbias[i] = (n0 + i < p.N) ? __ldg(brow + n0 + i) : 0.f;
-          epi_bar_sync();
-        }
-        const float* bias_g = (p.bias && !bias_uniform)
-                                  ? p.bias + (p.bias_bstride ? (gp / p.rows_per_batch) * p.bias_bstride : 0) : nullptr;
-        if (p.act == ACT_GEGLU) {
-          // packed tile: columns [0,BN/2) = value rows, [BN/2,BN) = gate rows of the same outputs
-          constexpr int HALF = BN / 2;
-          const int nout0 = n_idx * HALF;
-          const int Nout = p.N / 2;
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + gp * p.ldo + nout0;
+      } else if (p.act == ACT_GEGLU) {
+        // packed tile: columns [0,BN/2) = value rows, [BN/2,BN) = gate rows of the same outputs
+        constexpr int HALF = BN / 2;
+        const int nout0 = n_idx * HALF;
+        const int Nout = p.N / 2;
 #pragma unroll 1
-          for (int c = 0; c < HALF / 32; ++c) {
-            uint32_t v[32], g[32];
-            tmem_ld32(trow + c * 32, v);
-            tmem_ld32(trow + HALF + c * 32, g);
-            tmem_wait_ld();
-            if (row_ok) {
-              uint32_t o[16];
+        for (int c = half; c < HALF / 32; c += 2) {
+          uint32_t v[32];
+          float a[4][8];
+          tmem_ld32(trow + c * 32, v);
+          tmem_wait_ld();
+          stage_write(v);
+          __syncwarp();
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                float a0 = __uint_as_float(v[j]), a1 = __uint_as_float(v[j + 1]);
-                float g0 = __uint_as_float(g[j]), g1 = __uint_as_float(g[j + 1]);
-                if (p.bias) {
-                  a0 += sbias[c * 32 + j]; a1 += sbias[c * 32 + j + 1];
-                  g0 += sbias[HALF + c * 32 + j]; g1 += sbias[HALF + c * 32 + j + 1];
-                }
-                o[j / 2] = pack_bf16x2(a0 * gelu_fast_f(g0), a1 * gelu_fast_f(g1));
-              }
+          for (int k = 0; k < 4; ++k) stage_read(k, a[k]);
+          __syncwarp();
+          tmem_ld32(trow + HALF + c * 32, v);
+          tmem_wait_ld();
+          stage_write(v);
+          __syncwarp();
+          float bv[8], bg[8];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (nout0 + c * 32 + j * 8 + 7 < Nout)
-                  *reinterpret_cast<uint4*>(dst + c * 32 + j * 8) =
-                      make_uint4(o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]);
-              }
+          for (int i = 0; i < 8; ++i) {
+            bv[i] = p.bias ? sbias[c * 32 + tr_q * 8 + i] : 0.f;
+            bg[i] = p.bias ? sbias[HALF + c * 32 + tr_q * 8 + i] : 0.f;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float g[8];
+            stage_read(k, g);
+            if (ok_k[k] && nout0 + c * 32 + tr_q * 8 + 7 < Nout) {
+              float o[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = (a[k][i] + bv[i]) * gelu_fast_f(g[i] + bg[i]);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + gp_k[k] * p.ldo + nout0 + c * 32 + tr_q * 8) =
+                  make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
             }
           }
-        } else {
-          // ---- software-pipelined chunks: the TMEM load and the residual loads of chunk c+1 are in flight while
-          //      chunk c is converted and stored ----
-          const int nchunks = min(BN / 32, (p.N - n0 + 31) / 32);
-          const __nv_bfloat16* rs_row = p.resid ? p.resid + gp * p.ldr + n0 : nullptr;
-          auto load_resid = [&](int c, uint4 (&rr)[4]) {
-            if (rs_row && row_ok && n0 + c * 32 + 32 <= p.N) {
+          __syncwarp();
+        }
+      } else {
+        const int nchunks = min(BN / 32, (p.N - n0 + 31) / 32);
+        auto chunk = [&](int c, const uint32_t (&v)[32], const uint4 (&rr)[4], bool fast) {
+          const int nb = n0 + c * 32;
+          if (fast) {
+            stage_write(v);
+            __syncwarp();
+            if (c == half) VDB_TLE(8, it);
+            float bb[8];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) rr[j] = __ldg(reinterpret_cast<const uint4*>(rs_row + c * 32 + j * 8));
-            }
-          };
-          auto process = [&](int c, const uint32_t (&v)[32], const uint4 (&rr)[4]) {
-            if (!row_ok) return;
-            float f[32];
+            for (int i = 0; i < 8; ++i) bb[i] = p.bias ? sbias[c * 32 + tr_q * 8 + i] : 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            const int nb = n0 + c * 32;
-            const bool full = nb + 32 <= p.N;
-            if (bias_uniform) {
+            for (int k = 0; k < 4; ++k) {
+              float o[8];
+              stage_read(k, o);
+              if (ok_k[k]) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] += sbias[c * 32 + j];
-            } else if (bias_g) {
+                for (int i = 0; i < 8; ++i) o[i] += bb[i];
+                if (p.alpha != 1.f) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (nb + j < p.N) f[j] += __ldg(bias_g + nb + j);
-            }
-            if (p.alpha != 1.f) {
+                  for (int i = 0; i < 8; ++i) o[i] *= p.alpha;
+                }
+                if (p.act != ACT_NONE) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
-            }
-            if (p.act != ACT_NONE) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
-            }
-            if (rs_row) {
-              if (full) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint32_t w4[4] = {rr[j].x, rr[j].y, rr[j].z, rr[j].w};
+                  for (int i = 0; i < 8; ++i) o[i] = apply_act(o[i], p.act);
+                }
+                if (p.resid) {
+                  const uint32_t w4[4] = {rr[k].x, rr[k].y, rr[k].z, rr[k].w};
 #pragma unroll
                   for (int q = 0; q < 4; ++q) {
                     const float2 x = unpack_bf16x2(w4[q]);
-                    f[j * 8 + q * 2] += x.x;
-                    f[j * 8 + q * 2 + 1] += x.y;
+                    o[2 * q] += x.x;
+                    o[2 * q + 1] += x.y;
                   }
                 }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (nb + j < p.N) f[j] += __bfloat162float(rs_row[c * 32 + j]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + gp_k[k] * p.ldo + nb + tr_q * 8) =
+                    make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
               }
+              if (c == half && k == 0) VDB_TLE(9, it);
+            }
+            __syncwarp();   // the tile is rewritten by this warp's next chunk
+            if (c == half) VDB_TLE(10, it);
+          } else if (row_ok) {
+            // slow path (fp32 output, partial last chunk, per-row bias): one row per thread
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) f[j] += bias_uniform ? sbias[c * 32 + j] : __ldg(bias_g + nb + j);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j] * p.alpha, p.act);
+            if (p.resid) {
+              const __nv_bfloat16* rs = p.resid + gp * p.ldr + nb;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (nb + j < p.N) f[j] += __bfloat162float(rs[j]);
             }
             if (p.out_f32) {
               float* dst = reinterpret_cast<float*>(p.out) + gp * p.ldo + nb;
-              if (full) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = f[j];
-              }
+              for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = f[j];
             } else {
               __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + gp * p.ldo + nb;
-              if (full) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  *reinterpret_cast<uint4*>(dst + j * 8) =
-                      make_uint4(pack_bf16x2(f[j * 8], f[j * 8 + 1]), pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]),
-                                 pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]), pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]));
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = __float2bfloat16(f[j]);
-              }
-            }
-          };
-          uint32_t va[32], vb[32];
-          uint4 ra[4], rb[4];
-          tmem_ld32(trow, va);
-          load_resid(0, ra);
-#pragma unroll 1
-          for (int c = 0; c < nchunks; c += 2) {
-            tmem_wait_ld();                                  // va (chunk c) has landed
-            if (c + 1 < nchunks) { tmem_ld32(trow + (c + 1) * 32, vb); load_resid(c + 1, rb); }
-            process(c, va, ra);
-            if (c + 1 < nchunks) {
-              tmem_wait_ld();                                // vb (chunk c+1)
-              if (c + 2 < nchunks) { tmem_ld32(trow + (c + 2) * 32, va); load_resid(c + 2, ra); }
-              process(c + 1, vb, rb);
+              for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = __float2bfloat16(f[j]);
             }
           }
+        };
+        auto is_fast = [&](int c) { return (n0 + c * 32 + 32 <= p.N) && !p.out_f32 && (bias_uniform || !p.bias); };
+        auto load_resid = [&](int c, uint4 (&rr)[4]) {
+          if (p.resid && is_fast(c)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (ok_k[k]) rr[k] = __ldg(reinterpret_cast<const uint4*>(p.resid + gp_k[k] * p.ldr + n0 + c * 32 + tr_q * 8));
+          }
+        };
+        // this warp's chunks: half, half+2, ... (kept un-pipelined: double-buffering the 32-register TMEM chunk
+        // pushed the kernel into spills and was measured slower)
+#pragma unroll 1
+        for (int c = half; c < nchunks; c += 2) {
+          uint4 rr[4];
+          load_resid(c, rr);          // residual loads are in flight while the accumulator chunk is fetched
+          uint32_t v[32];
+          tmem_ld32(trow + c * 32, v);
+          tmem_wait_ld();
+          if (c == half) VDB_TLE(7, it);
+          chunk(c, v, rr, is_fast(c));
         }
       }
       tc_fence_before();
       __syncwarp();
+      VDB_TLE(6, it);   // epilogue: tile stored (this warp)
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
     }
   }
@@ -426,7 +497,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int kspl
 // ----------------------------------------------------------------------------------------------
 template <int BN, int STAGES>
 static int launch_igemm(const IgemmParams& p, int num_tiles, cudaStream_t stream) {
-  constexpr size_t smem = STAGES * (kABytes + BN * kBlockK * 2) + (2 * STAGES + 4) * 8 + 16 + BN * 4 + 1024;
+  constexpr size_t smem = STAGES * (kABytes + BN * kBlockK * 2) + (2 * STAGES + 4) * 8 + 16 + BN * 4 + kNumEpiWarps * 4096 + 1024;
   static bool configured = false;
   if (!configured) {
     VDB_CUDA_CHECK(cudaFuncSetAttribute(igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -450,6 +521,8 @@ static int pick_bn(int N, int act, int forced) {
   if (N <= 160) return 160;
   return 256;
 }
+
+static unsigned long long* g_timeline = nullptr;
 
 struct IgemmEpilogue {
   const float* bias = nullptr;
@@ -501,6 +574,7 @@ static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot
   // drop empty trailing splits
   p.ksplit = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.partial = reinterpret_cast<float*>(workspace);
+  p.timeline = g_timeline;
   const int num_tiles = mn_tiles * p.ksplit;
   switch (BN) {
     case 64: rc = launch_igemm<64, 8>(p, num_tiles, stream); break;
@@ -544,6 +618,9 @@ using namespace vdb;
 // C ABI
 // ---------------------------------------------------------------------------------------------
 extern "C" {
+
+// debug aid (not part of the product ABI): device buffer of 16*8 u64 receiving CTA 0's per-tile role timestamps
+void vdb_debug_igemm_timeline(void* buf) { g_timeline = reinterpret_cast<unsigned long long*>(buf); }
 
 // out[M,N] = act(alpha * ([A | A2] @ W^T + bias)) + resid     (see include/vdb200.h)
 int vdb_gemm_bf16(const void* A, long long M, long long K, long long lda, const void* A2, long long K2,
