@@ -19,10 +19,11 @@
 //   O  [B*Nq, ldo]  head h at columns h*dv .. (+dv)   (dense, feeds to_out)
 #include "common.cuh"
 #include "host_util.h"
+#include <cstdlib>
 
 namespace vdb {
 
-constexpr int kAttThreads = 192;
+
 constexpr int kBQ = 128;   // query rows per CTA
 constexpr int kBKV = 128;  // kv columns per tile
 constexpr float kRescaleThreshold = 8.0f;  // in log2 units (P stays <= 2^8)
@@ -43,8 +44,11 @@ struct alignas(64) AttnParams {
 
 // SB = S accumulator buffers in TMEM (1 or 2), PB = P buffers in smem (1 or 2). SB = PB = 1 keeps the CTA at
 // <= 110 KB smem / 256 TMEM columns so TWO CTAs share an SM: one CTA's softmax (MUFU-bound) overlaps the other's MMAs.
-template <int DK, int DVP, int KV_STAGES, int SB, int PB>
-__global__ void __launch_bounds__(kAttThreads, (SB == 1 && PB == 1) ? 2 : 1)
+// SW = softmax warps per TMEM lane quarter (1 or 2).  With SW = 2 the two warps of a quarter split every 128-column
+// S tile (64 columns each) and the O columns; they exchange the row max once per tile through shared memory.  One
+// softmax warp per SM sub-partition was measured to be instruction-latency bound (the exp pipe was ~30 % busy).
+template <int DK, int DVP, int KV_STAGES, int SB, int PB, int SW>
+__global__ void __launch_bounds__(64 + 128 * SW, (SB == 1 && PB == 1) ? 2 : 1)
 attention_kernel(const __grid_constant__ AttnParams p) {
   constexpr int KA = DK / 64;                      // 64-wide K atoms of the QK^T reduction
   constexpr uint32_t kQBytes = KA * kBQ * 128;     // Q tile
@@ -74,6 +78,8 @@ attention_kernel(const __grid_constant__ AttnParams p) {
   uint64_t* p_full = bars + 11;       // 1 (count 4: one arrive per softmax warp)
   uint64_t* pv_done = bars + 12;      // 1
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 13);
+  float* sxm = reinterpret_cast<float*>(bars + 16);   // [2 parity][2 halves][128 rows] partial row max (SW == 2)
+  float* sxl = sxm + 512;                              // [2 halves][128 rows] partial row sums (SW == 2)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -96,7 +102,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
       mbar_init(&s_full[s], 1);
     }
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 4 * SW);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
@@ -176,11 +182,17 @@ attention_kernel(const __grid_constant__ AttnParams p) {
   } else {
     // ------------------------------ softmax / correction / epilogue ------------------------------
     const int quarter = warp & 3;
+    const int hw = (warp - 2) >> 2;              // which softmax warp of the quarter (0 when SW == 1)
     const int r = quarter * 32 + lane;           // query row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const int q_idx = q0 + r;
+    constexpr int CPW = 4 / SW;                  // 32-column S chunks per warp and tile
+    constexpr int OCH = DVP / 16;                // 16-column O chunks
+    const int oc_begin = (SW == 1) ? 0 : (hw == 0 ? 0 : (OCH + 1) / 2);
+    const int oc_end = (SW == 1) ? OCH : (hw == 0 ? (OCH + 1) / 2 : OCH);
+    auto pair_sync = [&] { asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory"); };   // the quarter's two warps
     float m_ref = -INFINITY;  // reference max (raw score units)
-    float l_sum = 0.f;
+    float l_sum = 0.f;        // this thread's share of the row sum
     for (int j = 0; j < ntiles; ++j) {
       mbar_wait(&s_full[j % SB], (j / SB) & 1);
       tc_fence_after();
@@ -188,23 +200,49 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       const int kv0 = j * kBKV;
       const bool need_mask = (kv0 + kBKV > p.Nk) || p.causal;
       const int kv_lim = p.causal ? min(p.Nk, q_idx + 1) : p.Nk;  // valid kv indices are < kv_lim
-      // pass 1: row max
+      // pass 1: row max over this warp's columns.  With SW == 2 a thread owns only 64 columns, so the scores stay in
+      // registers for pass 2 and S is read from TMEM once per tile instead of twice.
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(ts + c * 32, v);
+      uint32_t keep[SW == 2 ? 64 : 1];
+      if constexpr (SW == 2) {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(ts + (hw * 2) * 32, v0);
+        tmem_ld32(ts + (hw * 2 + 1) * 32, v1);
         tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { keep[i] = v0[i]; keep[32 + i] = v1[i]; }
         if (need_mask) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (kv0 + c * 32 + i < kv_lim) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 64; ++i)
+            if (kv0 + hw * 64 + i < kv_lim) mx = fmaxf(mx, __uint_as_float(keep[i]));
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(keep[i]));
+        }
+      } else {
+#pragma unroll 1
+        for (int cc = 0; cc < CPW; ++cc) {
+          const int c = hw * CPW + cc;
+          uint32_t v[32];
+          tmem_ld32(ts + c * 32, v);
+          tmem_wait_ld();
+          if (need_mask) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (kv0 + c * 32 + i < kv_lim) mx = fmaxf(mx, __uint_as_float(v[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          }
         }
       }
-      // lazy rescale decision (warp-uniform because tcgen05.ld/st are warp collectives)
+      if (SW == 2) {   // combine with the partner warp's half of the row
+        sxm[((j & 1) * 2 + hw) * 128 + r] = mx;
+        pair_sync();
+        mx = fmaxf(mx, sxm[((j & 1) * 2 + (hw ^ 1)) * 128 + r]);
+      }
+      // lazy rescale decision (warp-uniform because tcgen05.ld/st are warp collectives; identical in both warps
+      // of a quarter because they see the same 32 rows)
       const float m_new = fmaxf(m_ref, mx);
       bool rescale = false;
       float factor = 1.f;
@@ -227,28 +265,43 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         tc_fence_after();
       }
       uint8_t* prow = sP + (j % PB) * kPBytes + r * 128;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(ts + c * 32, v);
-        tmem_wait_ld();
-        float pf[32];
+      if constexpr (SW == 2) {
+        uint8_t* patom = prow + hw * (kBQ * 128);   // this warp's 64 columns are exactly one 64-wide K atom of P
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          // (measured: routing alternate elements through ex2_poly() on the FMA pipe is SLOWER at the current
-          //  occupancy — the softmax warps are issue/latency bound, not MUFU bound; revisit once they are)
-          float e = ex2_mufu(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_scaled));
-          if (need_mask && !(kv0 + c * 32 + i < kv_lim)) e = 0.f;
-          pf[i] = e;
-          l_sum += e;
+        for (int q = 0; q < 8; ++q) {               // 8 scores -> one 16-byte chunk
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            e[i] = ex2_mufu(fmaf(__uint_as_float(keep[q * 8 + i]), p.scale_log2, -m_scaled));
+            if (need_mask && !(kv0 + hw * 64 + q * 8 + i < kv_lim)) e[i] = 0.f;
+            l_sum += e[i];
+          }
+          const uint4 pk = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+          *reinterpret_cast<uint4*>(patom + ((q ^ (r & 7)) << 4)) = pk;
         }
-        uint8_t* patom = prow + (c >> 1) * (kBQ * 128);
+      } else {
+#pragma unroll 1
+        for (int cc = 0; cc < CPW; ++cc) {
+          const int c = hw * CPW + cc;
+          uint32_t v[32];
+          tmem_ld32(ts + c * 32, v);
+          tmem_wait_ld();
+          float pf[32];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = (c & 1) * 4 + q;  // 16-byte chunk inside the 128-byte row
-          const uint4 pk = make_uint4(pack_bf16x2(pf[q * 8], pf[q * 8 + 1]), pack_bf16x2(pf[q * 8 + 2], pf[q * 8 + 3]),
-                                      pack_bf16x2(pf[q * 8 + 4], pf[q * 8 + 5]), pack_bf16x2(pf[q * 8 + 6], pf[q * 8 + 7]));
-          *reinterpret_cast<uint4*>(patom + ((chunk ^ (r & 7)) << 4)) = pk;
+          for (int i = 0; i < 32; ++i) {
+            float e = ex2_mufu(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_scaled));
+            if (need_mask && !(kv0 + c * 32 + i < kv_lim)) e = 0.f;
+            pf[i] = e;
+            l_sum += e;
+          }
+          uint8_t* patom = prow + (c >> 1) * (kBQ * 128);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = (c & 1) * 4 + q;  // 16-byte chunk inside the 128-byte row
+            const uint4 pk = make_uint4(pack_bf16x2(pf[q * 8], pf[q * 8 + 1]), pack_bf16x2(pf[q * 8 + 2], pf[q * 8 + 3]),
+                                        pack_bf16x2(pf[q * 8 + 4], pf[q * 8 + 5]), pack_bf16x2(pf[q * 8 + 6], pf[q * 8 + 7]));
+            *reinterpret_cast<uint4*>(patom + ((chunk ^ (r & 7)) << 4)) = pk;
+          }
         }
       }
       // O must be settled (PV_{j-1} retired) before it is rescaled / accumulated into again
@@ -259,7 +312,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         }
         if (rescale) {
 #pragma unroll 1
-          for (int c = 0; c < DVP / 16; ++c) {
+          for (int c = oc_begin; c < oc_end; ++c) {   // each warp of the quarter rescales its share of the O columns
             uint32_t o[16];
             tmem_ld16(tmem_O + lane_off + c * 16, o);
             tmem_wait_ld();
@@ -276,13 +329,18 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       if (lane == 0) mbar_arrive(p_full);
     }
     // epilogue: O / l -> bf16
+    if (SW == 2) {
+      sxl[hw * 128 + r] = l_sum;
+      pair_sync();
+      l_sum += sxl[(hw ^ 1) * 128 + r];
+    }
     mbar_wait(pv_done, (ntiles - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.f / l_sum;
     const bool row_ok = q_idx < p.Nq;
     __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.q_bs + q_idx) * p.ldo + head * p.dv;
 #pragma unroll 1
-    for (int c = 0; c < DVP / 16; ++c) {
+    for (int c = oc_begin; c < oc_end; ++c) {
       uint32_t o[16];
       tmem_ld16(tmem_O + lane_off + c * 16, o);
       tmem_wait_ld();
@@ -308,20 +366,20 @@ attention_kernel(const __grid_constant__ AttnParams p) {
   if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
-template <int DK, int DVP, int KV_STAGES, int SB, int PB>
+template <int DK, int DVP, int KV_STAGES, int SB, int PB, int SW>
 static int launch_attention(const AttnParams& p, int B, int H, cudaStream_t stream) {
   constexpr int KA = DK / 64;
   constexpr size_t smem = KA * kBQ * 128 + KV_STAGES * (KA * kBKV * 128 + 2 * DVP * 128) + PB * (2 * kBQ * 128) +
-                          13 * 8 + 16 + 1024;
+                          16 * 8 + (512 + 256) * 4 + 1024;
   static_assert(smem <= 227 * 1024, "attention smem budget");
   static bool configured = false;
   if (!configured) {
-    VDB_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<DK, DVP, KV_STAGES, SB, PB>,
+    VDB_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<DK, DVP, KV_STAGES, SB, PB, SW>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = true;
   }
   dim3 grid((p.Nq + kBQ - 1) / kBQ, H, B);
-  VDB_CUDA_CHECK(launch_pdl(attention_kernel<DK, DVP, KV_STAGES, SB, PB>, grid, dim3(kAttThreads), smem, stream, p));
+  VDB_CUDA_CHECK(launch_pdl(attention_kernel<DK, DVP, KV_STAGES, SB, PB, SW>, grid, dim3(64 + 128 * SW), smem, stream, p));
   count_launch();
   return VDB_OK;
 }
@@ -370,10 +428,18 @@ int vdb_attention_bf16(const void* Q, long long ldq, int q_col0, const void* K, 
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (DK == 64 && DVP == 48) return launch_attention<64, 48, 2, 1, 1>(p, B, H, st);   // 2 CTAs / SM
-  if (DK == 64 && DVP == 64) return launch_attention<64, 64, 2, 1, 1>(p, B, H, st);   // 2 CTAs / SM
-  if (DK == 128 && DVP == 80) return launch_attention<128, 80, 2, 2, 2>(p, B, H, st);
-  if (DK == 192 && DVP == 160) return launch_attention<192, 160, 1, 2, 2>(p, B, H, st);
+  static const int sw = [] { const char* e = getenv("VDB_ATT_SW"); return (e && e[0] == '1') ? 1 : 2; }();
+  if (sw == 2) {
+    if (DK == 64 && DVP == 48) return launch_attention<64, 48, 2, 1, 1, 2>(p, B, H, st);   // 2 CTAs / SM, 16 softmax warps / SM
+    if (DK == 64 && DVP == 64) return launch_attention<64, 64, 2, 1, 1, 2>(p, B, H, st);
+    if (DK == 128 && DVP == 80) return launch_attention<128, 80, 2, 2, 2, 2>(p, B, H, st);
+    if (DK == 192 && DVP == 160) return launch_attention<192, 160, 1, 2, 2, 2>(p, B, H, st);
+  } else {
+    if (DK == 64 && DVP == 48) return launch_attention<64, 48, 2, 1, 1, 1>(p, B, H, st);
+    if (DK == 64 && DVP == 64) return launch_attention<64, 64, 2, 1, 1, 1>(p, B, H, st);
+    if (DK == 128 && DVP == 80) return launch_attention<128, 80, 2, 2, 2, 1>(p, B, H, st);
+    if (DK == 192 && DVP == 160) return launch_attention<192, 160, 1, 2, 2, 1>(p, B, H, st);
+  }
   return set_error(VDB_ERR_UNSUPPORTED, "attention: no kernel for d_head %d", d_head);
 }
 
