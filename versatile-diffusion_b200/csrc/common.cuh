@@ -231,6 +231,14 @@ VDB_DEVINL float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
 }
 VDB_DEVINL float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// SiLU for bf16 outputs: x * sigmoid(x) = 0.5x * (1 + tanh(x/2)) with ONE MUFU op (tanh.approx, rel. error < 5e-4,
+// below bf16 rounding); the exp+rcp form needs two and made GroupNorm-apply MUFU-bound.
+VDB_DEVINL float silu_bf16_f(float x) {
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * x));
+  const float hx = 0.5f * x;
+  return fmaf(hx, th, hx);
+}
 VDB_DEVINL float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 // exact-erf GELU through Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): 2 MUFU + ~10 FMA instead of erff()
 VDB_DEVINL float gelu_as_f(float x) {

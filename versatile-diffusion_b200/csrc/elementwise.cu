@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
           const float2 f = unpack_bf16x2(w[q]);
           float a = f.x * scale[c0[k] + 2 * q] + shift[c0[k] + 2 * q];
           float bb = f.y * scale[c0[k] + 2 * q + 1] + shift[c0[k] + 2 * q + 1];
-          if (act == 1) { a = silu_f(a); bb = silu_f(bb); }
+          if (act == 1) { a = silu_bf16_f(a); bb = silu_bf16_f(bb); }
           o[q] = pack_bf16x2(a, bb);
         }
         *reinterpret_cast<uint4*>(yb + pp[k] * C + c0[k]) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -472,10 +472,17 @@ __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restri
                                                            const float* __restrict__ bias, int act_in, int act_out,
                                                            float* __restrict__ out) {
   extern __shared__ float xs[];  // [M, K]
-  for (int i = threadIdx.x; i < M * K; i += blockDim.x) {
-    float v = x[i];
-    if (act_in == 1) v = silu_f(v);
-    xs[i] = v;
+  {
+    // stage (activated) x: float4 loads, several in flight per thread (a scalar dependent-load loop cost ~20 us here)
+    const int n4 = (M * K) >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* xs4 = reinterpret_cast<float4*>(xs);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      float4 v = __ldg(x4 + i);
+      if (act_in == 1) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+      xs4[i] = v;
+    }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
