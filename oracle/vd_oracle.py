@@ -251,6 +251,45 @@ def ddim_sample(sd, x_T, conds, unconds, steps, scale=7.5, c_types=("text",), ra
     return (x, trace) if collect else x
 
 
+def plms_sample(sd, x_T, conds, unconds, steps, scale=7.5, c_types=("text",), ratios=None, num_ddpm=1000, **kw):
+    """PLMS (Liu et al. 2022; CompVis latent-diffusion plms.py) on the same apply_model — NOT in the reference
+    (parity unpinned): Adams-Bashforth eps history, pseudo improved-Euler first step, eta = 0 DDIM update."""
+    sched = ddim_schedule(ddpm_schedule(num_ddpm)["alphas_cumprod"], steps, 0.0)
+    ts = sched["timesteps"]
+    flip = np.flip(ts)
+    b = x_T.shape[0]
+
+    def eps(x, step):
+        t = torch.full((b,), int(step), dtype=torch.long)
+        if scale == 1.0:
+            return apply_model(sd, x, t, conds, ratios, c_types=c_types, **kw)
+        c_in = [torch.cat([u, c]) for u, c in zip(unconds, conds)]
+        e_u, e_c = apply_model(sd, torch.cat([x] * 2), torch.cat([t] * 2), c_in, ratios, c_types=c_types, **kw).chunk(2)
+        return e_u + scale * (e_c - e_u)
+
+    def update(x, e, index):
+        a_t, a_prev, s1m = float(sched["alphas"][index]), float(sched["alphas_prev"][index]), float(sched["sqrt_one_minus_alphas"][index])
+        pred_x0 = (x - s1m * e) / math.sqrt(a_t)
+        return math.sqrt(a_prev) * pred_x0 + math.sqrt(1.0 - a_prev) * e
+
+    x, old = x_T, []
+    for i, step in enumerate(flip):
+        index = len(ts) - i - 1
+        e_t = eps(x, step)
+        if len(old) == 0:
+            e_p = (e_t + eps(update(x, e_t, index), flip[min(i + 1, len(ts) - 1)])) / 2
+        elif len(old) == 1:
+            e_p = (3 * e_t - old[-1]) / 2
+        elif len(old) == 2:
+            e_p = (23 * e_t - 16 * old[-1] + 5 * old[-2]) / 12
+        else:
+            e_p = (55 * e_t - 59 * old[-1] + 37 * old[-2] - 9 * old[-3]) / 24
+        x = update(x, e_p, index)
+        old.append(e_t)
+        old = old[-3:]
+    return x
+
+
 # ------------------------------------------------------------------------------------------------
 # AutoencoderKL (kl-f8)
 # ------------------------------------------------------------------------------------------------

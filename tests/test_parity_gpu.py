@@ -156,6 +156,20 @@ def test_ddim_graph_equals_eager_and_is_reusable(mini):
     assert torch.equal(eager, g1), "graph path must be bit-identical to the eager path"
 
 
+def test_plms_sampler_vs_oracle(mini):
+    """PLMS is an addition (the reference has none): pinned to the oracle restatement of the published algorithm."""
+    from lib.model_zoo.plms import PLMSSampler
+    from oracle import vd_oracle as O
+    net, sd, gi, gold = mini
+    with torch.no_grad():
+        x, inter = PLMSSampler(net).sample(steps=6, shape=[1, 4, 16, 16], x_info={"type": "image", "xt": gi["xT"]},
+                                           c_info={"type": "text", "conditioning": gi["c"].to(DEV),
+                                                   "unconditional_conditioning": gi["u"].to(DEV),
+                                                   "unconditional_guidance_scale": 7.5}, verbose=False, eta=0.)
+        ref = O.plms_sample(sd, gi["xT"], [gi["c"]], [gi["u"]], 6, 7.5, model_channels=64)
+    _cmp(x, ref, cos_min=0.995, tol=0.1, what="6-step PLMS final latent vs oracle")
+
+
 def test_vae_decode_encode_vs_reference_golden(mini):
     net, sd, gi, gold = mini
     with torch.no_grad():

@@ -376,6 +376,7 @@ static int launch_attention(const AttnParams& p, int B, int H, cudaStream_t stre
   if (!configured) {
     VDB_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<DK, DVP, KV_STAGES, SB, PB, SW>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    prefer_max_smem(attention_kernel<DK, DVP, KV_STAGES, SB, PB, SW>);
     configured = true;
   }
   dim3 grid((p.Nq + kBQ - 1) / kBQ, H, B);

@@ -71,6 +71,21 @@ __global__ void ddim_cfg_step_kernel(const float* __restrict__ e_uncond, const f
 
 __global__ void add_int_kernel(int* p, int delta) { *p += delta; }
 
+// y = c0*x0 + c1*x1 + c2*x2 + c3*x3 (null pointers skipped) — the Adams-Bashforth eps combination of the PLMS
+// sampler (north-star addition; absent from the reference)
+__global__ void lincomb4_kernel(const float* __restrict__ x0, const float* __restrict__ x1, const float* __restrict__ x2,
+                                const float* __restrict__ x3, float c0, float c1, float c2, float c3,
+                                float* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v = c0 * x0[i];
+    if (x1) v += c1 * x1[i];
+    if (x2) v += c2 * x2[i];
+    if (x3) v += c3 * x3[i];
+    y[i] = v;
+  }
+}
+
 // y = a*x + b*z  (VD_v2_0.q_sample, vd.py:221-224: sqrt(ac_t)*x0 + sqrt(1-ac_t)*noise)
 __global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ z, float a, float b,
                              float* __restrict__ y, long long n) {
@@ -681,6 +696,7 @@ int vdb_ddim_cfg_step(const float* e_uncond, const float* e_cond, const float* x
        reinterpret_cast<uintptr_t>(x_prev_dup)) & 15)
     return set_error(VDB_ERR_INVALID, "ddim_cfg_step: pointers must be 16-byte aligned");
   const int threads = 256;
+  VDB_PREFER_MAX_SMEM(ddim_cfg_step_kernel);
   ddim_cfg_step_kernel<<<ew_blocks((n + 3) / 4, threads), threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       e_uncond, e_cond, x, noise, coef, step_idx, scale, temperature, x_prev, x_prev_dup, pred_x0, n);
   VDB_CUDA_CHECK(cudaGetLastError());
@@ -696,8 +712,18 @@ int vdb_axpby_f32(const float* x, const float* z, float a, float b, float* y, lo
   return VDB_OK;
 }
 
+int vdb_lincomb4_f32(const float* x0, const float* x1, const float* x2, const float* x3, float c0, float c1, float c2,
+                     float c3, float* y, long long n, void* stream) {
+  if (!x0 || !y || n <= 0) return set_error(VDB_ERR_INVALID, "lincomb4: null/empty argument");
+  lincomb4_kernel<<<ew_blocks(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x0, x1, x2, x3, c0, c1, c2, c3, y, n);
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
 int vdb_add_int(int* p, int delta, void* stream) {
   if (!p) return set_error(VDB_ERR_INVALID, "add_int: null");
+  VDB_PREFER_MAX_SMEM(add_int_kernel);
   add_int_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, delta);
   VDB_CUDA_CHECK(cudaGetLastError());
   count_launch();
@@ -728,6 +754,8 @@ int vdb_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int B, in
   if (!x2) C2 = 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nsplit = vdb_groupnorm_nsplit(B, HW);
+  VDB_PREFER_MAX_SMEM(gn_stats_kernel);
+  VDB_PREFER_MAX_SMEM(gn_apply_kernel);
   VDB_CUDA_CHECK(launch_pdl(gn_stats_kernel, dim3(nsplit, B), dim3(kGnThreads), 0, st,
                             reinterpret_cast<const __nv_bfloat16*>(x1), C1, reinterpret_cast<const __nv_bfloat16*>(x2), C2,
                             HW, groups, eps, scratch));
@@ -753,6 +781,9 @@ int vdb_layernorm(const void* x, long long rows, int C, const float* gamma, cons
   const int blocks = static_cast<int>(std::min<long long>((rows + 8 * R - 1) / (8 * R), num_sms() * 8LL));
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+  VDB_PREFER_MAX_SMEM((layernorm_kernel<2, 4>));
+  VDB_PREFER_MAX_SMEM((layernorm_kernel<5, 2>));
+  VDB_PREFER_MAX_SMEM((layernorm_kernel<8, 1>));
   if (V <= 64)
     VDB_CUDA_CHECK(launch_pdl(layernorm_kernel<2, 4>, dim3(blocks), dim3(threads), 0, st, xp, rows, C, gamma, beta, eps, yp));
   else if (V <= 160)
@@ -766,6 +797,7 @@ int vdb_layernorm(const void* x, long long rows, int C, const float* gamma, cons
 int vdb_upsample2x_nhwc(const void* x, int B, int H, int W, int C, void* y, void* stream) {
   if (!x || !y || (C % 8)) return set_error(VDB_ERR_INVALID, "upsample2x: null argument or C %% 8 != 0");
   const long long total = static_cast<long long>(B) * 4 * H * W * (C / 8);
+  VDB_PREFER_MAX_SMEM(upsample2x_kernel);
   upsample2x_kernel<<<ew_blocks(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, reinterpret_cast<__nv_bfloat16*>(y));
   VDB_CUDA_CHECK(cudaGetLastError());
@@ -777,6 +809,7 @@ int vdb_im2col3x3_small(const float* x, int B, int H, int W, int Cin, int Kpad, 
                         void* y, void* stream) {
   if (!x || !y || 9 * Cin > Kpad || (Kpad % 8)) return set_error(VDB_ERR_INVALID, "im2col3x3_small: bad argument");
   const long long total = static_cast<long long>(B) * H * W * Kpad;
+  VDB_PREFER_MAX_SMEM(im2col3x3_small_kernel);
   im2col3x3_small_kernel<<<ew_blocks(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, B, H, W, Cin, Kpad, in_scale, in_shift, reinterpret_cast<__nv_bfloat16*>(y));
   VDB_CUDA_CHECK(cudaGetLastError());
@@ -788,6 +821,7 @@ int vdb_permute_f32(const float* x, int B, int C, long long HW, int to_nhwc, flo
                     float* y, void* stream) {
   if (!x || !y) return set_error(VDB_ERR_INVALID, "permute_f32: null argument");
   const long long total = static_cast<long long>(B) * C * HW;
+  VDB_PREFER_MAX_SMEM(permute_f32_kernel);
   permute_f32_kernel<<<ew_blocks(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, B, C, static_cast<int>(HW), to_nhwc, mul, add, clamp01, y);
   VDB_CUDA_CHECK(cudaGetLastError());
@@ -836,6 +870,7 @@ int vdb_cast_bf16_f32(const void* x, float* y, long long n, void* stream) {
 int vdb_timestep_embedding(const long long* ts, const int* step_idx, int B, int dim, float neg_log_period, float* out,
                            void* stream) {
   if (!ts || !out || B <= 0 || dim <= 1) return set_error(VDB_ERR_INVALID, "timestep_embedding: bad argument");
+  VDB_PREFER_MAX_SMEM(timestep_embedding_kernel);
   timestep_embedding_kernel<<<ew_blocks(static_cast<long long>(B) * (dim / 2), 128), 128, 0,
                               reinterpret_cast<cudaStream_t>(stream)>>>(ts, step_idx, B, dim, neg_log_period, out);
   VDB_CUDA_CHECK(cudaGetLastError());
@@ -851,6 +886,7 @@ int vdb_linear_small(const float* x, int M, int K, const void* Wt, int N, const 
   static bool configured = false;
   if (!configured) {
     VDB_CUDA_CHECK(cudaFuncSetAttribute(linear_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    prefer_max_smem(linear_small_kernel);
     configured = true;
   }
   const int blocks = std::min((N + 31) / 32, num_sms() * 2);

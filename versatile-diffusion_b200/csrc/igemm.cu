@@ -502,6 +502,7 @@ static int launch_igemm(const IgemmParams& p, int num_tiles, cudaStream_t stream
   if (!configured) {
     VDB_CUDA_CHECK(cudaFuncSetAttribute(igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
+    prefer_max_smem(igemm_kernel<BN, STAGES>);
     configured = true;
   }
   const int grid = std::min(num_tiles, num_sms());
@@ -587,6 +588,7 @@ static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot
     const long long total = M * (N / 4);
     const int threads = 256;
     const int blocks = static_cast<int>(std::min<long long>((total + threads - 1) / threads, num_sms() * 8LL));
+    VDB_PREFER_MAX_SMEM(splitk_reduce_kernel);
     VDB_CUDA_CHECK(launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(threads), 0, stream, (const float*)p.partial,
                               p.ksplit, M, static_cast<int>(N), p.bias, p.bias_bstride, p.rows_per_batch, p.resid,
                               p.ldr, p.out, p.ldo, p.out_f32, p.act, p.alpha));

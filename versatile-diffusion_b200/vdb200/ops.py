@@ -143,6 +143,20 @@ def axpby(x, z, a, b, out=None):
     return out
 
 
+def lincomb4(xs, cs, out=None):
+    """sum_i cs[i] * xs[i] for 1..4 fp32 tensors of one shape."""
+    assert 1 <= len(xs) <= 4 and len(xs) == len(cs)
+    for t in xs:
+        _need(t, torch.float32, "x")
+    if out is None:
+        out = torch.empty_like(xs[0])
+    ptrs = [_ptr(t) for t in xs] + [0] * (4 - len(xs))
+    coef = [float(c) for c in cs] + [0.0] * (4 - len(cs))
+    check(lib.vdb_lincomb4_f32(ptrs[0], ptrs[1], ptrs[2], ptrs[3], coef[0], coef[1], coef[2], coef[3], _ptr(out),
+                               xs[0].numel(), _stream()), "lincomb4")
+    return out
+
+
 def add_int(t, delta):
     _need(t, torch.int32, "counter")
     check(lib.vdb_add_int(_ptr(t), int(delta), _stream()), "add_int")
