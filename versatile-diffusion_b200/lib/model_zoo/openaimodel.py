@@ -372,14 +372,29 @@ class UNetModel2D_Next(nn.Module):
         """time_embed MLP (reference :2629-2633) on the fp32 sinusoid [B, model_channels], B <= 16 per call."""
         ops = _ops()
         te = self.time_embed
-        if getattr(self, "_te_packed", None) is None:
-            self._te_packed = (bf16(te[0].weight), f32(te[0].bias), bf16(te[2].weight), f32(te[2].bias))
-        w0, b0, w2, b2 = self._te_packed
+        w0, b0, w2, b2 = self.time_embed_packed()
         outs = []
         for i in range(0, t_emb.shape[0], 16):
             h = ops.linear_small(t_emb[i:i + 16].contiguous(), w0, b0, act_out=ops.ACT_SILU)
             outs.append(ops.linear_small(h, w2, b2))
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+
+    def time_embed_packed(self):
+        te = self.time_embed
+        if getattr(self, "_te_packed", None) is None:
+            self._te_packed = (bf16(te[0].weight), f32(te[0].bias), bf16(te[2].weight), f32(te[2].bias))
+        return self._te_packed
+
+    def embed_table(self, t_emb, time_owner=None):
+        """Sinusoid [B, model_channels] fp32 -> EmbTable, on the tensor-core GEMM: time_embed MLP (SiLU fused into both
+        epilogues: only SiLU(emb) is ever consumed, openaimodel.py:217-223) then ALL ResBlock emb projections as one
+        [B, sum(Cout)] GEMM with the conv1 biases folded in.  (The skinny CUDA-core linear took 230 us per step here.)"""
+        ops = _ops()
+        w0, b0, w2, b2 = (time_owner or self).time_embed_packed()
+        p = self._pack_emb()
+        h = ops.gemm(ops.to_bf16(t_emb.contiguous()), w0, bias=b0, act=ops.ACT_SILU, ksplit=1)
+        s = ops.gemm(h, w2, bias=b2, act=ops.ACT_SILU, ksplit=1)          # SiLU(time_embed(t_emb)), bf16
+        return EmbTable(ops.gemm(s, p["w"], bias=p["b"], out_dtype=torch.float32, ksplit=1))
 
     def embed_all(self, emb):
         """emb [B, 4*model_channels] fp32 -> EmbTable with every ResBlock's SiLU->Linear (+conv1 bias)."""
@@ -398,7 +413,7 @@ class UNetModel2D_Next(nn.Module):
         ops = _ops()
         xh = ops.nchw_to_nhwc(x.float().contiguous())
         t_emb = timestep_embedding(timesteps, self.model_channels)
-        emb = self.embed_all(self.time_embedding(t_emb))
+        emb = self.embed_table(t_emb)
         h = unet_walk(self, [self], xh, emb, [context], [1.0])
         return ops.nhwc_to_nchw(h).to(x.dtype)
 

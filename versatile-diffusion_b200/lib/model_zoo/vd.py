@@ -155,8 +155,7 @@ class VD_v2_0(nn.Module):
 
     def eps_nhwc(self, x_nhwc, x_type, t_emb, c_types, contexts, ratios, time_from):
         """Core of apply_model*: fp32 NHWC latent [B,H,W,4] + fp32 sinusoid [B,model_channels] -> fp32 NHWC eps."""
-        emb = self.diffuser[time_from].time_embedding(t_emb)
-        table = self.diffuser[x_type].embed_all(emb)
+        table = self.diffuser[x_type].embed_table(t_emb, time_owner=self.diffuser[time_from])
         return unet_walk(self.diffuser[x_type], [self.diffuser[ct] for ct in c_types], x_nhwc, table, contexts, ratios)
 
     def _apply_model(self, x_type, x, timesteps, c_types, contexts, ratios, time_from):
