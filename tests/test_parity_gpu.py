@@ -120,6 +120,24 @@ def test_unet_forward_matches_oracle_fresh_inputs(mini):
     _cmp(out, ref, what="apply_model vs oracle (24x24, B=3, L=50)")
 
 
+def test_fresh_context_tensors_never_hit_a_stale_kv_cache(mini):
+    """K / V^T of the context are cached per CrossAttention; a NEW context tensor that the allocator places at the
+    address of a freed one (same shape, same version) must not be served the old projections."""
+    from oracle import vd_oracle as O
+    net, sd, gi, gold = mini
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, 4, 16, 16, generator=g)
+    t = torch.tensor([500, 500])
+    for i in range(3):
+        c = torch.randn(2, 77, 768, generator=g) * 0.5
+        with torch.no_grad():
+            ref = O.apply_model(sd, x, t, [c], model_channels=64)
+            c_dev = c.to(DEV)
+            out = net.apply_model({"type": "image", "x": x.to(DEV)}, t.to(DEV), {"type": "text", "c": c_dev})
+            del c_dev
+        _cmp(out, ref, what=f"apply_model with fresh context #{i}")
+
+
 @pytest.mark.parametrize("graph", [False, True])
 def test_ddim_5_steps_vs_reference_golden(mini, graph):
     from lib.model_zoo.ddim import DDIMSampler
@@ -208,8 +226,23 @@ def test_c1_full_config_vs_reference_golden():
     from oracle.make_golden import golden_inputs
     gold = dict(np.load(path))
     net, sd = build_net(mini=False)
-    del sd
     gi = golden_inputs("c1")
+    # BASELINE configs 3 / 4 at FULL size against the oracle: image-variation context (257 tokens) and the dual-context
+    # (text 0.7 + image 0.3) mix, one CFG-shaped forward each at latent 32x32
+    from oracle import vd_oracle as O
+    g = torch.Generator().manual_seed(31)
+    xx, tt = torch.randn(2, 4, 32, 32, generator=g), torch.tensor([801, 801])
+    c_img, c_txt = torch.randn(2, 257, 768, generator=g) * 0.5, torch.randn(2, 77, 768, generator=g) * 0.5
+    with torch.no_grad():
+        ref3 = O.apply_model(sd, xx, tt, [c_img], c_types=("image",))
+        out3 = net.apply_model({"type": "image", "x": xx.to(DEV)}, tt.to(DEV), {"type": "image", "c": c_img.to(DEV)})
+        _cmp(out3, ref3, what="C3 image-context eps (full-size UNet) vs oracle")
+        ref4 = O.apply_model(sd, xx, tt, [c_txt, c_img], ratios=[0.7, 0.3], c_types=("text", "image"))
+        out4 = net.apply_model_multicontext({"type": "image", "x": xx.to(DEV)}, tt.to(DEV),
+                                            [{"type": "text", "c": c_txt.to(DEV), "ratio": 0.7},
+                                             {"type": "image", "c": c_img.to(DEV), "ratio": 0.3}])
+        _cmp(out4, ref4, what="C4 dual-context eps (full-size UNet) vs oracle")
+    del sd
     with torch.no_grad():
         x_in = torch.cat([gi["xT"]] * 2).to(DEV)
         eps0 = net.apply_model({"type": "image", "x": x_in}, torch.tensor([901, 901], device=DEV),

@@ -103,7 +103,7 @@ __global__ void axpby_kernel(const float* __restrict__ x, const float* __restric
 // ---------------------------------------------------------------------------------------------
 constexpr int kGnThreads = 512;
 
-// scratch layout (floats): [kGnMaxBatch arrival counters (int), always at the front so that calls with different
+// scratch layout (floats): [2*kGnMaxBatch arrival / departure counters (int), always at the front so that calls with different
 // shapes never alias them][B*2*groups {mean, rstd}][B*nsplit*2*groups partial sums]
 constexpr int kGnMaxBatch = 1024;
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int C1,
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __nv_bfloat1
   const int cpg = C / groups;
   const int b = blockIdx.y, split = blockIdx.x, nsplit = gridDim.x, B = gridDim.y;
   int* counters = reinterpret_cast<int*>(scratch);
-  float* stats = scratch + kGnMaxBatch;
+  float* stats = scratch + 2 * kGnMaxBatch;
   float* partial = stats + static_cast<size_t>(B) * 2 * groups;
   const int pix_per = (HW + nsplit - 1) / nsplit;
   const int p_begin = split * pix_per;
@@ -267,6 +267,157 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
           o[q] = pack_bf16x2(a, bb);
         }
         *reinterpret_cast<uint4*>(yb + pp[k] * C + c0[k]) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-launch GroupNorm: statistics + apply in ONE kernel.  grid (nsplit, B) with nsplit*B <= 2 CTAs per SM so that
+// every CTA of the grid is resident; each CTA reduces its pixel range (deterministic, as gn_stats_kernel), publishes its
+// partial, waits on a per-image arrival counter for the other CTAs of the image, folds the partials (fixed order: every
+// CTA computes bit-identical mean / rstd) and normalises ITS OWN pixel range, which it just read (L2-hot).  Saves a
+// launch and the statistics kernel's tail per GroupNorm (61 per UNet call).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const __nv_bfloat16* __restrict__ x1, int C1,
+                                                              const __nv_bfloat16* __restrict__ x2, int C2, int HW,
+                                                              int groups, float eps, int act,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float* __restrict__ scratch,
+                                                              __nv_bfloat16* __restrict__ y) {
+  const int C = C1 + C2;
+  const int V = C / 8;
+  const int cpg = C / groups;
+  const int b = blockIdx.y, split = blockIdx.x, nsplit = gridDim.x, B = gridDim.y;
+  pdl_launch_dependents();
+  pdl_wait();
+  int* arrive = reinterpret_cast<int*>(scratch);
+  int* depart = arrive + kGnMaxBatch;
+  float* partial = scratch + 2 * kGnMaxBatch + static_cast<size_t>(B) * 2 * groups;
+  const int pix_per = (HW + nsplit - 1) / nsplit;
+  const int p_begin = split * pix_per;
+  const int p_end = min(HW, p_begin + pix_per);
+  __shared__ float part[kGnThreads * 16];   // phase 1: reduction scratch; phase 2: per-channel scale | shift
+  __shared__ float gmean[32], grstd[32];
+  const int lanes = kGnThreads / V;
+  const int v = threadIdx.x % V;
+  const int pl = threadIdx.x / V;
+  const bool first = v * 8 < C1;
+  const __nv_bfloat16* src = first ? x1 + static_cast<long long>(b) * HW * C1 + v * 8
+                                   : x2 + static_cast<long long>(b) * HW * C2 + (v * 8 - C1);
+  const long long Cs = first ? C1 : C2;
+  // ---- phase 1: partial sums of this CTA's pixels ----
+  if (pl < lanes) {
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+    int p = p_begin + pl;
+    for (; p + 3 * lanes < p_end; p += 4 * lanes) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(src + (p + k * lanes) * Cs));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack_bf16x2(w[i]);
+          s[2 * i] += f.x; q[2 * i] += f.x * f.x;
+          s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+        }
+      }
+    }
+    for (; p < p_end; p += lanes) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + p * Cs));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16x2(w[i]);
+        s[2 * i] += f.x; q[2 * i] += f.x * f.x;
+        s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+      }
+    }
+    float* dst = part + (static_cast<size_t>(pl) * V + v) * 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { dst[i] = s[i]; dst[8 + i] = q[i]; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kGnThreads) {
+    float s = 0.f, q = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      const float* ps = part + (static_cast<size_t>(l) * V + c / 8) * 16 + (c & 7);
+      s += ps[0]; q += ps[8];
+    }
+    float* own = part + (static_cast<size_t>(c / 8)) * 16 + (c & 7);
+    own[0] = s; own[8] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    float s = 0.f, q = 0.f;
+    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
+      const float* ps = part + (static_cast<size_t>(c / 8)) * 16 + (c & 7);
+      s += ps[0]; q += ps[8];
+    }
+    float* o = partial + (static_cast<long long>(b) * nsplit + split) * 2 * groups + 2 * threadIdx.x;
+    o[0] = s; o[1] = q;
+  }
+  // ---- publish, then wait for the other CTAs of this image (all CTAs of the grid are resident by construction) ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(&arrive[b], 1);
+    while (atomicAdd(&arrive[b], 0) < nsplit) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    float s = 0.f, q = 0.f;
+    const float* pp = partial + static_cast<long long>(b) * nsplit * 2 * groups + 2 * threadIdx.x;
+#pragma unroll 4
+    for (int i = 0; i < nsplit; ++i) { s += __ldcg(pp + static_cast<long long>(i) * 2 * groups); q += __ldcg(pp + static_cast<long long>(i) * 2 * groups + 1); }
+    const float inv_n = 1.0f / (static_cast<float>(HW) * cpg);
+    const float mean = s * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    gmean[threadIdx.x] = mean;
+    grstd[threadIdx.x] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {   // last CTA of the image to have read the partials re-arms both counters for the next launch
+    if (atomicAdd(&depart[b], 1) == nsplit - 1) { arrive[b] = 0; depart[b] = 0; }
+  }
+  float* scale = part;
+  float* shift = part + C;
+  for (int c = threadIdx.x; c < C; c += kGnThreads) {
+    const int g = c / cpg;
+    const float sc = grstd[g] * __ldg(gamma + c);
+    scale[c] = sc;
+    shift[c] = __ldg(beta + c) - gmean[g] * sc;
+  }
+  __syncthreads();
+  // ---- phase 2: normalise this CTA's pixels ----
+  if (pl < lanes) {
+    __nv_bfloat16* dstb = y + static_cast<long long>(b) * HW * C + v * 8;
+    const int c0 = v * 8;
+    for (int p = p_begin + pl; p < p_end; p += 4 * lanes) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (p + k * lanes < p_end) u[k] = __ldg(reinterpret_cast<const uint4*>(src + (p + k * lanes) * Cs));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (p + k * lanes < p_end) {
+          const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+          uint32_t o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = unpack_bf16x2(w[i]);
+            float a = f.x * scale[c0 + 2 * i] + shift[c0 + 2 * i];
+            float bb = f.y * scale[c0 + 2 * i + 1] + shift[c0 + 2 * i + 1];
+            if (act == 1) { a = silu_bf16_f(a); bb = silu_bf16_f(bb); }
+            o[i] = pack_bf16x2(a, bb);
+          }
+          *reinterpret_cast<uint4*>(dstb + static_cast<long long>(p + k * lanes) * C) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
       }
     }
   }
@@ -741,7 +892,8 @@ int vdb_groupnorm_nsplit(int B, int HW) {
 }
 long long vdb_groupnorm_scratch_floats(int B, int HW) {
   const long long ns = vdb_groupnorm_nsplit(B, HW);
-  return kGnMaxBatch + static_cast<long long>(B) * 64 + static_cast<long long>(B) * ns * 64;
+  const long long parts = std::max<long long>(static_cast<long long>(B) * ns, 2 * num_sms());  // single-launch path: <= 2 CTAs / SM
+  return 2 * kGnMaxBatch + static_cast<long long>(B) * 64 + parts * 64;
 }
 
 int vdb_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int B, int HW, int groups, const float* gamma,
@@ -753,13 +905,24 @@ int vdb_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int B, in
     return set_error(VDB_ERR_UNSUPPORTED, "groupnorm: need 32 groups, C %% 32 == 0, C/8 <= 512 (C=%d)", C);
   if (!x2) C2 = 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static const bool fused_ok = [] { const char* ev = getenv("VDB_GN_FUSED"); return !(ev && ev[0] == '0'); }();
+  if (fused_ok && B <= 2 * num_sms()) {
+    // single launch: every CTA must be resident (2 per SM by registers / shared memory), so at most 2*SMs CTAs
+    int ns = std::max(1, std::min((2 * num_sms()) / B, (HW + 31) / 32));
+    ns = std::min(ns, vdb_groupnorm_nsplit(B, HW) * 4);
+    VDB_CUDA_CHECK(launch_pdl(gn_fused_kernel, dim3(ns, B), dim3(kGnThreads), 0, st,
+                              reinterpret_cast<const __nv_bfloat16*>(x1), C1, reinterpret_cast<const __nv_bfloat16*>(x2), C2,
+                              HW, groups, eps, act, gamma, beta, scratch, reinterpret_cast<__nv_bfloat16*>(y)));
+    count_launch(1);
+    return VDB_OK;
+  }
   const int nsplit = vdb_groupnorm_nsplit(B, HW);
   VDB_PREFER_MAX_SMEM(gn_stats_kernel);
   VDB_PREFER_MAX_SMEM(gn_apply_kernel);
   VDB_CUDA_CHECK(launch_pdl(gn_stats_kernel, dim3(nsplit, B), dim3(kGnThreads), 0, st,
                             reinterpret_cast<const __nv_bfloat16*>(x1), C1, reinterpret_cast<const __nv_bfloat16*>(x2), C2,
                             HW, groups, eps, scratch));
-  const float* stats = scratch + kGnMaxBatch;
+  const float* stats = scratch + 2 * kGnMaxBatch;
   const long long work = static_cast<long long>(HW) * (C / 8);
   // ~8 vectors per thread: amortises the per-CTA scale/shift prologue
   int nblk = static_cast<int>(std::min<long long>((work + 2047) / 2048, std::max(1, (num_sms() * 8) / std::max(B, 1))));

@@ -110,12 +110,14 @@ class CrossAttention(PackedModule):
                 if ver != data._version:          # new prompt copied into the same buffer: refresh IN PLACE
                     ops.gemm(cflat, p["wk"], out=k)
                     ops.gemm(p["wv"], cflat, out=vt)
-                    self._kv_cache = (key, (k, vt, data._version))
+                    self._kv_cache = (key, (k, vt, data._version), data)
                 return k, vt, L, Lp
             k = ops.gemm(cflat, p["wk"])
             vt = ops.gemm(p["wv"], cflat)
-            self._kv_cache = (key, (k, vt, data._version))
+            self._kv_cache = (key, (k, vt, data._version), data)
             return k, vt, L, Lp
+        # the cache entry HOLDS the context tensor: while it is alive no other allocation can reuse its address, so
+        # (pointer, version, shape) identifies the contents (a freed-and-reallocated buffer would otherwise alias it)
         key = (context.data_ptr(), context._version, tuple(context.shape), context.dtype)
         if self._kv_cache is not None and self._kv_cache[0] == key:
             return self._kv_cache[1]
@@ -125,7 +127,7 @@ class CrossAttention(PackedModule):
         cpad[:, :L] = context.to(torch.bfloat16)
         cflat = cpad.view(B * Lp, Cc)
         val = (ops.gemm(cflat, p["wk"]), ops.gemm(p["wv"], cflat), L, Lp)
-        self._kv_cache = (key, val)
+        self._kv_cache = (key, val, context)
         return val
 
     def forward(self, x, context=None, resid=None, B=1):
