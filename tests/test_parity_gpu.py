@@ -172,6 +172,22 @@ def test_ddim_graph_equals_eager_and_is_reusable(mini):
     g1, g2 = run(Sg), run(Sg)
     assert torch.equal(g1, g2), "graph replay must be deterministic"
     assert torch.equal(eager, g1), "graph path must be bit-identical to the eager path"
+    # steady state (every step replayed, context projections refreshed in place) with a NEW prompt, and after an
+    # unrelated apply_model call replaced the cross-attention layers' cached projections
+    c2 = torch.randn(2, 77, 768, generator=g).to(DEV)
+
+    def run2(S):
+        with torch.no_grad():
+            return S.sample(x_info={"type": "image", "xt": xT.clone()},
+                            c_info={"type": "text", "conditioning": c2, "unconditional_conditioning": u,
+                                    "unconditional_guidance_scale": 5.0}, **args)[0]
+    g3 = run2(Sg)
+    e3 = run2(DDIMSampler(net, use_cuda_graph=False))
+    assert torch.equal(e3, g3), "replay-only path with a refreshed context must equal the eager path"
+    with torch.no_grad():
+        net.apply_model({"type": "image", "x": xT.to(DEV)}, torch.tensor([5, 5], device=DEV), {"type": "text", "c": c2})
+    g4 = run(Sg)
+    assert torch.equal(eager, g4), "graph must be rebuilt when the K / V^T buffers it captured were replaced"
 
 
 def test_plms_sampler_vs_oracle(mini):

@@ -61,6 +61,7 @@ struct alignas(64) IgemmParams {
   int act;                    // 0 none, 1 silu, 2 gelu(erf), 3 quick_gelu, 4 geglu (packed halves)
   float alpha;                // out = act(alpha * (acc + bias)) + resid
   float* partial;             // split-K: [ksplit, M, N] fp32
+  int epi_alt;                // 1: the two warps of a TMEM quarter swap chunk parity every tile (odd chunk counts)
   unsigned long long* timeline; // debug: per-tile role timestamps of CTA 0 (null = off)
 };
 
@@ -433,14 +434,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
         };
         // this warp's chunks: half, half+2, ... (kept un-pipelined: double-buffering the 32-register TMEM chunk
         // pushed the kernel into spills and was measured slower)
+        // odd chunk count (BN = 160: five): the warp that took three chunks on this tile takes two on the next one
+        const int first = (p.epi_alt & (BN / 32) & 1) ? (half ^ (it & 1)) : half;
 #pragma unroll 1
-        for (int c = half; c < nchunks; c += 2) {
+        for (int c = first; c < nchunks; c += 2) {
           uint4 rr[4];
           load_resid(c, rr);          // residual loads are in flight while the accumulator chunk is fetched
           uint32_t v[32];
           tmem_ld32(trow + c * 32, v);
           tmem_wait_ld();
-          if (c == half) VDB_TLE(7, it);
+          if (c == first) VDB_TLE(7, it);
           chunk(c, v, rr, is_fast(c));
         }
       }
@@ -542,7 +545,14 @@ struct IgemmEpilogue {
 static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot, long long ldw,
                      const IgemmEpilogue& e, int bn_forced, int ksplit_forced, void* workspace,
                      size_t ws_bytes, cudaStream_t stream) {
-  const int BN = pick_bn(static_cast<int>(N), e.act, bn_forced);
+  int BN = pick_bn(static_cast<int>(N), e.act, bn_forced);
+  if (!bn_forced && e.act != ACT_GEGLU && p.kb_total < 32) {
+    // short K and a small MN grid (the 8x8 level): narrower tiles fill more SMs and need no split-K reduction pass
+    // (M 512, N 1280, K 1280: 10.7 us with BN 64 vs 18.1 us with BN 256 + split-K 2, tools/bn_sweep.py)
+    const int tm = p.tilesW * p.tilesH * p.tilesB;
+    auto tiles = [&](int bn) { return tm * static_cast<int>((N + bn - 1) / bn); };
+    while (BN > 64 && tiles(BN) * 2 <= num_sms()) BN = (BN == 256) ? 160 : (BN == 160 ? 128 : 64);
+  }
   if (BN != 64 && BN != 128 && BN != 160 && BN != 256) return set_error(VDB_ERR_INVALID, "igemm: bad BN");
   if (e.act == ACT_GEGLU && (N % BN) != 0) return set_error(VDB_ERR_INVALID, "igemm: GEGLU needs N % 256 == 0");
   p.N = static_cast<int>(N);
@@ -576,6 +586,8 @@ static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot
   p.ksplit = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.partial = reinterpret_cast<float*>(workspace);
   p.timeline = g_timeline;
+  static const int epi_alt = [] { const char* ev = getenv("VDB_EPI_ALT"); return (ev && ev[0] == '0') ? 0 : 1; }();
+  p.epi_alt = epi_alt;
   const int num_tiles = mn_tiles * p.ksplit;
   switch (BN) {
     case 64: rc = launch_igemm<64, 8>(p, num_tiles, stream); break;

@@ -183,27 +183,36 @@ class DDIMSampler(object):
                 step(noise)
                 log(index)
         else:
-            key = (bs, B, H, W, x_type, tuple(c_types), tuple(ratios), scale, float(temperature), time_from,
+            from .diffusion_utils import pack_epoch
+            key = (pack_epoch(), bs, B, H, W, x_type, tuple(c_types), tuple(ratios), scale, float(temperature), time_from,
                    tuple((c.data.data_ptr(), tuple(c.data.shape), c.length) for c in ctxs))
-            n0 = ops.launch_count()
-            step()                      # first step eager: packs weights, sizes workspaces, warms caches
-            self.last_step_launches = ops.launch_count() - n0
-            log(total_steps - 1)
-            g = self._graphs.get(key)
-            if g is None and total_steps > 1:
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                idx_before = st['idx'].clone()
-                x_before = st['x_in'].clone()
-                with torch.cuda.graph(g):
-                    step()
-                # capture does not execute; make sure state is exactly what the eager step left
-                st['idx'].copy_(idx_before)
-                st['x_in'].copy_(x_before)
-                self._graphs = {key: g}   # keep one live graph (its private pool holds the activations)
-            for i in range(1, total_steps):
-                g.replay()
-                log(total_steps - i - 1)
+            ent = self._graphs.get(key)
+            if ent is not None and ent[1] == model.context_kv_signature(c_types, ctxs):
+                # steady state: the context projections were just refreshed in place; every step is a graph replay
+                for i in range(total_steps):
+                    ent[0].replay()
+                    log(total_steps - i - 1)
+            else:
+                n0 = ops.launch_count()
+                step()                      # first step eager: packs weights, sizes workspaces, warms caches
+                self.last_step_launches = ops.launch_count() - n0
+                log(total_steps - 1)
+                g = None
+                if total_steps > 1:
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    idx_before = st['idx'].clone()
+                    x_before = st['x_in'].clone()
+                    with torch.cuda.graph(g):
+                        step()
+                    # capture does not execute; make sure state is exactly what the eager step left
+                    st['idx'].copy_(idx_before)
+                    st['x_in'].copy_(x_before)
+                    # keep one live graph (its private pool holds the activations) + the K / V^T buffers it reads
+                    self._graphs = {key: (g, model.context_kv_signature(c_types, ctxs))}
+                for i in range(1, total_steps):
+                    g.replay()
+                    log(total_steps - i - 1)
 
         pred_xt = ops.nhwc_to_nchw(st['x_in'][:bs].contiguous()).to(dtype)
         x_info['x'] = pred_xt

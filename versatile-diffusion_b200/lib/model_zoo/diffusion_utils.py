@@ -110,6 +110,15 @@ def linear(*args, **kwargs):
 # ------------------------------------------------------------------------------------------------
 # packing support shared by every kernel-backed module
 # ------------------------------------------------------------------------------------------------
+_pack_epoch = [0]
+
+
+def pack_epoch():
+    """Bumped whenever any module drops its kernel-layout weights (.to / .half / load_state_dict / explicit
+    invalidate_packed): captured CUDA graphs hold pointers to the packed copies, so samplers key their graphs on it."""
+    return _pack_epoch[0]
+
+
 class PackedMixin(object):
     """Lazily repacked kernel-side weights for an nn.Module.
 
@@ -128,6 +137,7 @@ class PackedMixin(object):
 
     def invalidate_packed(self):
         self._packed = None
+        _pack_epoch[0] += 1
 
     def packed(self):
         if self._packed is None:

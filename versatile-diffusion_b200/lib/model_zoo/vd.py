@@ -158,6 +158,20 @@ class VD_v2_0(nn.Module):
         table = self.diffuser[x_type].embed_table(t_emb, time_owner=self.diffuser[time_from])
         return unet_walk(self.diffuser[x_type], [self.diffuser[ct] for ct in c_types], x_nhwc, table, contexts, ratios)
 
+    def context_kv_signature(self, c_types, contexts):
+        """Projects every context through the K / V^T weights of the cross-attention layers that will read it (a
+        cache hit when the context is unchanged, an IN-PLACE refresh when a persistent context buffer was refilled)
+        and returns the device addresses of those projections.  A captured DDIM-step graph reads exactly these
+        buffers, so the sampler replays it only while the signature is unchanged."""
+        from .attention import CrossAttention
+        sig = []
+        for ct, ctx in zip(c_types, contexts):
+            for m in self.diffuser[ct].context_blocks.modules():
+                if isinstance(m, CrossAttention) and not m.is_self:
+                    k, vt = m.context_kv(ctx)[:2]
+                    sig.append((k.data_ptr(), vt.data_ptr()))
+        return tuple(sig)
+
     def _apply_model(self, x_type, x, timesteps, c_types, contexts, ratios, time_from):
         require_cuda(x, "VD_v2_0.apply_model")
         ops = _ops()
