@@ -1,3 +1,5 @@
+"""Per-tile role timeline of CTA 0 of one GEMM launch.  Needs a library built with -DVDB_TIMELINE (the stamps are
+compiled out of the product build): make -C versatile-diffusion_b200/csrc EXTRA=-DVDB_TIMELINE"""
 import os, sys, ctypes
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "versatile-diffusion_b200"))
 import torch

@@ -267,17 +267,30 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       uint8_t* prow = sP + (j % PB) * kPBytes + r * 128;
       if constexpr (SW == 2) {
         uint8_t* patom = prow + hw * (kBQ * 128);   // this warp's 64 columns are exactly one 64-wide K atom of P
+        // the scale / subtract and the row sum run as packed fp32 pairs (FFMA2 / FADD2): the softmax warps are
+        // issue-limited next to the MUFU pipe, and the pairs halve those two instruction streams
+        const unsigned long long sc2 = pack_f2(p.scale_log2, p.scale_log2), nm2 = pack_f2(-m_scaled, -m_scaled);
+        unsigned long long l2 = pack_f2(0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {               // 8 scores -> one 16-byte chunk
           float e[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            e[i] = ex2_mufu(fmaf(__uint_as_float(keep[q * 8 + i]), p.scale_log2, -m_scaled));
+          for (int i = 0; i < 8; i += 2) {
+            float xa, xb;
+            unpack_f2(fma_f2(pack_f2(__uint_as_float(keep[q * 8 + i]), __uint_as_float(keep[q * 8 + i + 1])), sc2, nm2), xa, xb);
+            e[i] = ex2_mufu(xa);
+            e[i + 1] = ex2_mufu(xb);
             if (need_mask && !(kv0 + hw * 64 + q * 8 + i < kv_lim)) e[i] = 0.f;
-            l_sum += e[i];
+            if (need_mask && !(kv0 + hw * 64 + q * 8 + i + 1 < kv_lim)) e[i + 1] = 0.f;
+            l2 = add_f2(l2, pack_f2(e[i], e[i + 1]));
           }
           const uint4 pk = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
           *reinterpret_cast<uint4*>(patom + ((q ^ (r & 7)) << 4)) = pk;
+        }
+        {
+          float la, lb;
+          unpack_f2(l2, la, lb);
+          l_sum += la + lb;
         }
       } else {
 #pragma unroll 1

@@ -370,11 +370,23 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const __nv_bfloat1
     __threadfence();
   }
   __syncthreads();
+  // fold the image's nsplit partial rows (64 floats each: sum | sumsq per group) with the whole CTA: 8 row-lanes x 64
+  // columns of coalesced L2 loads, then a fixed-order sum over the lanes -- every CTA of the image computes
+  // bit-identical statistics.  (One thread per group walking all rows was ~4 us of serialised L2 latency.)
+  {
+    float* red = part + 6144;                       // [8][64]; scale | shift below use part[0, 2C), C <= 2560
+    const int j = threadIdx.x & 63, sl = threadIdx.x >> 6;
+    const float* pp = partial + static_cast<long long>(b) * nsplit * 64 + j;
+    float acc = 0.f;
+    for (int i = sl; i < nsplit; i += kGnThreads / 64) acc += __ldcg(pp + static_cast<long long>(i) * 64);
+    red[sl * 64 + j] = acc;
+  }
+  __syncthreads();
   if (threadIdx.x < groups) {
+    const float* red = part + 6144;
     float s = 0.f, q = 0.f;
-    const float* pp = partial + static_cast<long long>(b) * nsplit * 2 * groups + 2 * threadIdx.x;
-#pragma unroll 4
-    for (int i = 0; i < nsplit; ++i) { s += __ldcg(pp + static_cast<long long>(i) * 2 * groups); q += __ldcg(pp + static_cast<long long>(i) * 2 * groups + 1); }
+#pragma unroll
+    for (int l = 0; l < kGnThreads / 64; ++l) { s += red[l * 64 + 2 * threadIdx.x]; q += red[l * 64 + 2 * threadIdx.x + 1]; }
     const float inv_n = 1.0f / (static_cast<float>(HW) * cpg);
     const float mean = s * inv_n;
     const float var = fmaxf(q * inv_n - mean * mean, 0.f);
@@ -906,7 +918,7 @@ int vdb_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int B, in
   if (!x2) C2 = 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static const bool fused_ok = [] { const char* ev = getenv("VDB_GN_FUSED"); return !(ev && ev[0] == '0'); }();
-  if (fused_ok && B <= 2 * num_sms()) {
+  if (fused_ok && B <= 2 * num_sms() && C <= 3072) {   // (shared-memory plan of the single-launch kernel)
     // single launch: every CTA must be resident (2 per SM by registers / shared memory), so at most 2*SMs CTAs
     int ns = std::max(1, std::min((2 * num_sms()) / B, (HW + 31) / 32));
     ns = std::min(ns, vdb_groupnorm_nsplit(B, HW) * 4);

@@ -24,9 +24,8 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // bf16 elements = 128 B = one swizzle row
 constexpr int kMaxA = 6;     // A tensor maps per launch
 constexpr int kMaxSeg = 12;  // K segments per launch
-constexpr int kNumEpiWarps = 8;
-constexpr int kNumEpiThreads = kNumEpiWarps * 32;
-constexpr int kNumThreads = 64 + kNumEpiThreads;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+// threads = 64 + 32 * EW: warp 0 TMA, warp 1 MMA, EW epilogue warps (8, or 16 for the short-K GEMMs whose tiles
+// are bound by the epilogue's instruction latency rather than by the mainloop)
 constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
 
 struct ASeg {
@@ -39,7 +38,7 @@ struct ASeg {
 
 struct alignas(64) IgemmParams {
   CUtensorMap tmA[kMaxA];  // 4D (C, W, H, B) bf16, box (64, TW, TH, TB), SWIZZLE_128B
-  CUtensorMap tmB;         // 2D (Ktot, N) bf16, box (64, BN), SWIZZLE_128B
+  CUtensorMap tmB;         // 2D (Ktot, N) bf16, box (64, BN), SWIZZLE_128B (CTA-pair launches: box (64, BN/2))
   ASeg seg[kMaxSeg];
   int nseg;
   int kb_total;      // total k-blocks over all segments
@@ -72,8 +71,28 @@ VDB_DEVINL unsigned long long gtime() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#ifdef VDB_TIMELINE   // debug build only (tools/gemm_timeline.py): per-tile role timestamps of CTA 0
 #define VDB_TL(slot, it) do { if (p.timeline && blockIdx.x == 0 && (it) < 8) p.timeline[(it) * 16 + (slot)] = gtime(); } while (0)
 #define VDB_TLE(slot, it) do { if (warp == 2 && lane == 0) VDB_TL(slot, it); } while (0)
+#else
+#define VDB_TL(slot, it) do { } while (0)
+#define VDB_TLE(slot, it) do { } while (0)
+#endif
+
+// mbarrier wait with a watchdog (CTA-pair kernels): a protocol error between the two CTAs traps after ~2 s instead
+// of hanging the device
+VDB_DEVINL void mbar_wait_wd(uint64_t* bar, uint32_t parity, int who) {
+  uint32_t n = 0;
+  unsigned long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++n == 4096) {
+      t0 = gtime();
+    } else if (n > 4096 && (n & 1023) == 0 && gtime() - t0 > 2000000000ull) {
+      printf("igemm pair watchdog: block %d thread %d wait %d parity %u\n", blockIdx.x, threadIdx.x, who, parity);
+      __trap();
+    }
+  }
+}
 
 VDB_DEVINL float apply_act(float v, int act) {
   switch (act) {
@@ -84,12 +103,29 @@ VDB_DEVINL float apply_act(float v, int act) {
   }
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
-  constexpr uint32_t kBBytes = BN * kBlockK * 2;
+// CTAS == 2: the kernel runs as CTA pairs (2-cluster, cta_group::2).  A pair owns a 256 x BN output tile: CTA r stages
+// its own 128 rows of A and rows [r*BN/2, (r+1)*BN/2) of the B tile, so the L2 -> shared-memory traffic per FLOP
+// drops by ~28 % (BN 160) / 33 % (BN 256) against two independent CTAs (the conv mainloop is bound by that traffic:
+// profiles/r01_ncu_hot_v5.txt) and the smaller stage buys two more pipeline stages.  Rank 0 issues the MMAs; every
+// TMA of the pair completes on rank 0's full barrier; commits multicast to both CTAs; each CTA drains its own 128
+// accumulator lanes with the same epilogue.
+// MODE selects the epilogue that is compiled in: 0 = every path (split-K partials, GEGLU, fp32 / ragged / per-row-bias
+// tiles), 1 = only the bf16 fast path (act none, alpha 1, N % 32 == 0, one bias row per tile) with the residual of the
+// NEXT chunk prefetched, 2 = only GEGLU.  The generic kernel is ~6300 SASS instructions; ncu's source view of the
+// K = 320 GEMMs showed 9 % instruction-fetch stalls and 10 % branch-resolve stalls in the epilogue warps, and the
+// residual's first use exposed its full load latency (profiles/r01_ncu_gemm320_v6.txt).
+template <int BN, int STAGES, int CTAS, int EW, int MODE>
+__global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+  constexpr int kNumEpiWarps = EW;
+  constexpr int kNumEpiThreads = EW * 32;
+  constexpr int kWPQ = EW / 4;           // epilogue warps per TMEM lane quarter
+  static_assert(EW == 8 || EW == 12 || EW == 16, "");   // 12 / 16 were measured: no gain
+  constexpr uint32_t kBBytes = (BN / CTAS) * kBlockK * 2;    // this CTA's share of the B tile
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static_assert(kBBytes % 1024 == 0, "B stage must keep 1024B alignment");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
+  static_assert(CTAS == 1 || CTAS == 2, "");
+  const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -102,7 +138,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* sbias = reinterpret_cast<float*>(tmem_holder + 4);   // [BN] bias of the current output tile
   float* sstage = sbias + BN;                                  // kNumEpiWarps x [32][32] fp32 swizzled transposition tiles
-  auto epi_bar_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiThreads) : "memory"); };   // the epilogue warps only
+  auto epi_bar_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory"); };   // the epilogue warps only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -118,50 +154,73 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], kNumEpiWarps);
+      mbar_init(&tmem_empty[s], kNumEpiWarps * CTAS);   // pair: the peer's epilogue warps arrive remotely
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_holder);
+  if (warp == 2) {
+    if constexpr (CTAS == 2) tmem_alloc_pair<512>(tmem_holder); else tmem_alloc<512>(tmem_holder);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();   // pair: the peer's barriers are initialised too
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
   pdl_launch_dependents();
   pdl_wait();   // everything above overlapped the previous kernel's tail; global inputs are valid from here
 
+  // scheduling unit = CTAS consecutive M tiles x one N tile; CTA r of a pair takes M tile 2*unit + r (host: tilesM even)
   const int tilesM = p.tilesW * p.tilesH * p.tilesB;
-  const int num_tiles = tilesM * p.tilesN * p.ksplit;
+  const int unitsM = tilesM / CTAS;
+  const int num_tiles = unitsM * p.tilesN * p.ksplit;
+  const int t_first = blockIdx.x / CTAS, t_step = gridDim.x / CTAS;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m_idx = t % tilesM;
-        const int rest = t / tilesM;
-        const int n_idx = rest % p.tilesN;
-        const int ks = rest / p.tilesN;
-        const int wt = m_idx % p.tilesW;
-        const int ht = (m_idx / p.tilesW) % p.tilesH;
-        const int bt = m_idx / (p.tilesW * p.tilesH);
+      const bool flat = (p.tilesH == 1) && (p.tilesB == 1);
+      const int step_m = t_step % unitsM, step_r = t_step / unitsM;
+      int unit_m = t_first % unitsM, rest = t_first / unitsM;
+      for (int t = t_first; t < num_tiles; t += t_step) {
+        const int m_idx = unit_m * CTAS + static_cast<int>(cta_rank);
+        int n_idx = rest, ks = 0;
+        if (p.ksplit > 1) { n_idx = rest % p.tilesN; ks = rest / p.tilesN; }
+        int wt = m_idx, ht = 0, bt = 0;
+        if (!flat) {
+          wt = m_idx % p.tilesW;
+          const int q = m_idx / p.tilesW;
+          ht = q % p.tilesH;
+          bt = q / p.tilesH;
+        }
+        unit_m += step_m; rest += step_r;
+        if (unit_m >= unitsM) { unit_m -= unitsM; ++rest; }
         const int w0 = wt * p.TW, h0 = ht * p.TH, b0 = bt * p.TB;
-        const int n0 = n_idx * BN;
+        const int n0 = n_idx * BN + static_cast<int>(cta_rank) * (BN / CTAS);
         const int kb_begin = ks * p.kb_per_split;
         const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
         int kb = 0;
-        VDB_TL(0, (t - blockIdx.x) / gridDim.x);   // producer: starts issuing this tile
+        VDB_TL(0, (t - t_first) / t_step);   // producer: starts issuing this tile
         for (int s = 0; s < p.nseg; ++s) {
           const ASeg sg = p.seg[s];
           if (kb + sg.nkb <= kb_begin) { kb += sg.nkb; continue; }
           for (int j = 0; j < sg.nkb; ++j, ++kb) {
             if (kb < kb_begin) continue;
             if (kb >= kb_end) break;
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-            tma_load_4d(smemA + stage * kABytes, &p.tmA[sg.tmap], &full_bar[stage],
-                        sg.c0 + j * kBlockK, w0 + sg.dw, h0 + sg.dh, b0);
-            tma_load_2d(smemB + stage * kBBytes, &p.tmB, &full_bar[stage], kb * kBlockK, n0);
+            if constexpr (CTAS == 2) mbar_wait_wd(&empty_bar[stage], phase ^ 1, 0); else mbar_wait(&empty_bar[stage], phase ^ 1);
+            if constexpr (CTAS == 2) {
+              // rank 0 arms its barrier for the bytes of BOTH CTAs (the peer's may land first: the transaction
+              // count is signed and the phase cannot complete before this arrival)
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+              const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);   // rank 0's barrier
+              tma_load_4d_pair(smemA + stage * kABytes, &p.tmA[sg.tmap], leader_full,
+                               sg.c0 + j * kBlockK, w0 + sg.dw, h0 + sg.dh, b0);
+              tma_load_2d_pair(smemB + stage * kBBytes, &p.tmB, leader_full, kb * kBlockK, n0);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+              tma_load_4d(smemA + stage * kABytes, &p.tmA[sg.tmap], &full_bar[stage],
+                          sg.c0 + j * kBlockK, w0 + sg.dw, h0 + sg.dh, b0);
+              tma_load_2d(smemB + stage * kBBytes, &p.tmB, &full_bar[stage], kb * kBlockK, n0);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           if (kb >= kb_end) break;
@@ -170,35 +229,36 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM * CTAS, BN);
       uint32_t stage = 0, phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int ks = (t / tilesM) / p.tilesN;
+      for (int t = t_first; t < num_tiles; t += t_step, ++it) {
+        const int ks = (p.ksplit > 1) ? (t / unitsM) / p.tilesN : 0;
         const int kb_begin = ks * p.kb_per_split;
         const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         VDB_TL(1, it);                             // MMA: wants the accumulator stage
-        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        if constexpr (CTAS == 2) mbar_wait_wd(&tmem_empty[as], aphase ^ 1, 1); else mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         VDB_TL(2, it);                             // MMA: got it
         const uint32_t tmem_d = tmem_base + as * 256;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          if constexpr (CTAS == 2) mbar_wait_wd(&full_bar[stage], phase, 2); else mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t adesc = make_desc_sw128(smem_u32(smemA + stage * kABytes));
           const uint64_t bdesc = make_desc_sw128(smem_u32(smemB + stage * kBBytes));
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
-            umma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            if constexpr (CTAS == 2) umma_bf16_ss_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            else umma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if constexpr (CTAS == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[as]);
+        if constexpr (CTAS == 2) umma_commit_pair(&tmem_full[as]); else umma_commit(&tmem_full[as]);
         VDB_TL(3, it);                             // MMA: all MMAs of the tile issued
       }
     }
@@ -211,7 +271,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
     // transposed, so every global access is 8 rows x 64 contiguous bytes per instruction (4 lanes per row), and
     // bias / activation / residual / bf16 conversion run on 8 fixed columns per lane (bias lives in registers).
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;      // which of the two warps of the quarter
+    const int half = (warp - 2) >> 2;      // which of the kWPQ warps of the quarter
     const int r = quarter * 32 + lane;
     const int tr_row = lane >> 2, tr_q = lane & 3;   // transposed role: rows tr_row + 8k, columns tr_q*8 .. +7
     float* stage = sstage + (warp - 2) * 1024;       // [32 rows][32 fp32], 16-byte chunk j of row i at (j ^ (i & 7))
@@ -230,49 +290,60 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
     };
     int it = 0;
     const float* sbias_src = nullptr;   // which bias row/offset currently sits in sbias
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int m_idx = t % tilesM;
-      const int rest = t / tilesM;
-      const int n_idx = rest % p.tilesN;
-      const int ks = rest / p.tilesN;
-      const int wt = m_idx % p.tilesW;
-      const int ht = (m_idx / p.tilesW) % p.tilesH;
-      const int bt = m_idx / (p.tilesW * p.tilesH);
-      const int tw = r % p.TW;
-      const int th = (r / p.TW) % p.TH;
-      const int tb = r / (p.TW * p.TH);
+    const uint32_t leader_tmem_empty[2] = {(CTAS == 2) ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u,
+                                           (CTAS == 2) ? mapa_u32(smem_u32(&tmem_empty[1]), 0) : 0u};
+    // The per-tile bookkeeping sits on the critical path of epilogue-bound GEMMs (it was ~0.75 us of every ~3.6 us
+    // tile): the tile index advances incrementally (no divisions in the GEMM view), row indices are 32-bit, and
+    // everything that depends only on the thread is hoisted.
+    const int tw = r % p.TW;
+    const int th = (r / p.TW) % p.TH;
+    const int tb = r / (p.TW * p.TH);
+    const bool flat = (p.tilesH == 1) && (p.tilesB == 1);   // GEMM view: M tiles along W only
+    const int step_m = t_step % unitsM, step_r = t_step / unitsM;
+    int unit_m = t_first % unitsM, rest = t_first / unitsM;
+    for (int t = t_first; t < num_tiles; t += t_step, ++it) {
+      const int m_idx = unit_m * CTAS + static_cast<int>(cta_rank);
+      int n_idx = rest, ks = 0;
+      if (p.ksplit > 1) { n_idx = rest % p.tilesN; ks = rest / p.tilesN; }
+      int wt = m_idx, ht = 0, bt = 0;
+      if (!flat) {
+        wt = m_idx % p.tilesW;
+        const int q = m_idx / p.tilesW;
+        ht = q % p.tilesH;
+        bt = q / p.tilesH;
+      }
+      unit_m += step_m; rest += step_r;
+      if (unit_m >= unitsM) { unit_m -= unitsM; ++rest; }
       const int w = wt * p.TW + tw, h = ht * p.TH + th, b = bt * p.TB + tb;
       const bool row_ok = (w < p.Wo) && (h < p.Ho) && (b < p.Bo);
-      const long long gp = (static_cast<long long>(b) * p.Ho + h) * p.Wo + w;
-      const long long gp_first = (static_cast<long long>(bt * p.TB) * p.Ho + ht * p.TH) * p.Wo + wt * p.TW;
+      const int gp = (b * p.Ho + h) * p.Wo + w;     // output pixel (row of the GEMM); host guarantees M < 2^31
+      const int gp_first = ((bt * p.TB) * p.Ho + ht * p.TH) * p.Wo + wt * p.TW;
       const int n0 = n_idx * BN;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
 
       // per-tile row bookkeeping for the transposed role (independent of the accumulator: done before the wait)
-      long long gp_k[4];
+      int gp_k[4];
       bool ok_k[4];
       {
         const unsigned okmask = __ballot_sync(0xffffffffu, row_ok);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int src = k * 8 + tr_row;
-          const unsigned lo = __shfl_sync(0xffffffffu, static_cast<unsigned>(gp & 0xffffffffu), src);
-          const unsigned hi = __shfl_sync(0xffffffffu, static_cast<unsigned>(static_cast<unsigned long long>(gp) >> 32), src);
-          gp_k[k] = static_cast<long long>((static_cast<unsigned long long>(hi) << 32) | lo);
+          gp_k[k] = __shfl_sync(0xffffffffu, gp, src);
           ok_k[k] = (okmask >> src) & 1u;
         }
       }
       // bias tile -> shared memory (one global read per tile); one row serves the tile unless the bias is per-batch
       // and the tile's first / last rows belong to different batch items
-      const long long gp_last = (static_cast<long long>(bt * p.TB + p.TB - 1) * p.Ho + ht * p.TH + p.TH - 1) * p.Wo +
-                                wt * p.TW + p.TW - 1;
-      const bool bias_uniform = p.bias && p.ksplit == 1 &&
-                                (p.bias_bstride == 0 || gp_first / p.rows_per_batch == gp_last / p.rows_per_batch);
+      const int gp_last = ((bt * p.TB + p.TB - 1) * p.Ho + ht * p.TH + p.TH - 1) * p.Wo + wt * p.TW + p.TW - 1;
+      const bool bias_uniform = (MODE != 0) ? (p.bias != nullptr)    // host: a tile never straddles two bias rows
+                                            : (p.bias && p.ksplit == 1 &&
+                                               (p.bias_bstride == 0 || gp_first / p.rows_per_batch == gp_last / p.rows_per_batch));
       if (bias_uniform) {
         // consecutive tiles of a CTA usually share the N tile (M is the fast tile index): reload only on change,
         // otherwise the ~0.7 us global-load latency + two barriers sit between every two tiles
-        const float* brow = p.bias + (p.bias_bstride ? (gp_first / p.rows_per_batch) * p.bias_bstride : 0) + n0;
+        const float* brow = p.bias + (p.bias_bstride ? static_cast<long long>(gp_first / p.rows_per_batch) * p.bias_bstride : 0) + n0;
         if (brow != sbias_src) {              // uniform across the epilogue threads
           epi_bar_sync();                     // previous tile's readers are done with sbias
           for (int i = threadIdx.x - 64; i < BN; i += kNumEpiThreads) sbias[i] = (n0 + i < p.N) ? __ldg(brow + i) : 0.f;
@@ -281,46 +352,35 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
         }
       }
       const float* bias_g = (p.bias && !bias_uniform)
-                                ? p.bias + (p.bias_bstride ? (gp / p.rows_per_batch) * p.bias_bstride : 0) : nullptr;
+                                ? p.bias + (p.bias_bstride ? static_cast<long long>(gp / p.rows_per_batch) * p.bias_bstride : 0) : nullptr;
+
+      // MODE 1: this warp's chunk range and the residual rows of its first chunk, requested BEFORE the accumulator wait
+      const int f_nchunks = min(BN / 32, (p.N - n0) / 32);
+      const bool has_resid = p.resid != nullptr;
+      const int f_first = (((BN / 32) % kWPQ) != 0) ? ((half + it) % kWPQ) : half;
+      auto load_resid_fast = [&](int c, uint4 (&rr)[4]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (ok_k[k]) rr[k] = __ldg(reinterpret_cast<const uint4*>(p.resid + static_cast<long long>(gp_k[k]) * p.ldr + n0 + c * 32 + tr_q * 8));
+      };
+      uint4 rr_first[4];
+      if constexpr (MODE == 1) {
+        if (has_resid && f_first < f_nchunks) load_resid_fast(f_first, rr_first);
+      }
 
       VDB_TLE(4, it);   // epilogue: waiting for the accumulator
-      mbar_wait(&tmem_full[as], aphase);
+      if constexpr (CTAS == 2) mbar_wait_wd(&tmem_full[as], aphase, 3); else mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       VDB_TLE(5, it);   // epilogue: accumulator complete
       const uint32_t trow = tmem_base + as * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
 
-      if (p.ksplit > 1) {
-        // fp32 partials, reduced (+bias/act/residual) by splitk_reduce_kernel
-        const long long Mtot = static_cast<long long>(p.Bo) * p.Ho * p.Wo;
-        float* dst = p.partial + (static_cast<long long>(ks) * Mtot + gp) * p.N + n0;
-#pragma unroll 1
-        for (int c = half; c < BN / 32; c += 2) {
-          if (n0 + c * 32 >= p.N) break;
-          uint32_t v[32];
-          tmem_ld32(trow + c * 32, v);
-          tmem_wait_ld();
-          if (row_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const int n = n0 + c * 32 + j;
-              if (n + 3 < p.N) {
-                *reinterpret_cast<float4*>(dst + c * 32 + j) =
-                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-              } else {
-                for (int q = 0; q < 4; ++q)
-                  if (n + q < p.N) dst[c * 32 + j + q] = __uint_as_float(v[j + q]);
-              }
-            }
-          }
-        }
-      } else if (p.act == ACT_GEGLU) {
+      auto geglu_tile = [&] {
         // packed tile: columns [0,BN/2) = value rows, [BN/2,BN) = gate rows of the same outputs
         constexpr int HALF = BN / 2;
         const int nout0 = n_idx * HALF;
         const int Nout = p.N / 2;
 #pragma unroll 1
-        for (int c = half; c < HALF / 32; c += 2) {
+        for (int c = (((HALF / 32) % kWPQ) != 0) ? ((half + it) % kWPQ) : half; c < HALF / 32; c += kWPQ) {
           uint32_t v[32];
           float a[4][8];
           tmem_ld32(trow + c * 32, v);
@@ -348,12 +408,84 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
               float o[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) o[i] = (a[k][i] + bv[i]) * gelu_fast_f(g[i] + bg[i]);
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + gp_k[k] * p.ldo + nout0 + c * 32 + tr_q * 8) =
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(gp_k[k]) * p.ldo + nout0 + c * 32 + tr_q * 8) =
                   make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
             }
           }
           __syncwarp();
         }
+      };
+      if constexpr (MODE == 1) {
+        // lean fast path: every chunk is a full 32-column bf16 chunk with one bias row; the residual rows of the
+        // next chunk are requested before this chunk is processed (their first use otherwise exposes ~1 us)
+        uint4 rr[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rr[k] = rr_first[k];
+#pragma unroll 1
+        for (int c = f_first; c < f_nchunks; c += kWPQ) {
+          uint32_t v[32];
+          tmem_ld32(trow + c * 32, v);
+          uint4 rn[4];
+          if (has_resid && c + kWPQ < f_nchunks) load_resid_fast(c + kWPQ, rn);
+          tmem_wait_ld();
+          stage_write(v);
+          __syncwarp();
+          float bb[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bb[i] = p.bias ? sbias[c * 32 + tr_q * 8 + i] : 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float o[8];
+            stage_read(k, o);
+            if (ok_k[k]) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] += bb[i];
+              if (has_resid) {
+                const uint32_t w4[4] = {rr[k].x, rr[k].y, rr[k].z, rr[k].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 x = unpack_bf16x2(w4[q]);
+                  o[2 * q] += x.x;
+                  o[2 * q + 1] += x.y;
+                }
+              }
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(gp_k[k]) * p.ldo + n0 + c * 32 + tr_q * 8) =
+                  make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+            }
+          }
+          __syncwarp();   // the staging tile is rewritten by this warp's next chunk
+#pragma unroll
+          for (int k = 0; k < 4; ++k) rr[k] = rn[k];
+        }
+      } else if constexpr (MODE == 2) {
+        geglu_tile();
+      } else if (p.ksplit > 1) {
+        // fp32 partials, reduced (+bias/act/residual) by splitk_reduce_kernel
+        const long long Mtot = static_cast<long long>(p.Bo) * p.Ho * p.Wo;
+        float* dst = p.partial + (static_cast<long long>(ks) * Mtot + gp) * p.N + n0;
+#pragma unroll 1
+        for (int c = half; c < BN / 32; c += kWPQ) {
+          if (n0 + c * 32 >= p.N) break;
+          uint32_t v[32];
+          tmem_ld32(trow + c * 32, v);
+          tmem_wait_ld();
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const int n = n0 + c * 32 + j;
+              if (n + 3 < p.N) {
+                *reinterpret_cast<float4*>(dst + c * 32 + j) =
+                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              } else {
+                for (int q = 0; q < 4; ++q)
+                  if (n + q < p.N) dst[c * 32 + j + q] = __uint_as_float(v[j + q]);
+              }
+            }
+          }
+        }
+      } else if (p.act == ACT_GEGLU) {
+        geglu_tile();
       } else {
         const int nchunks = min(BN / 32, (p.N - n0 + 31) / 32);
         auto chunk = [&](int c, const uint32_t (&v)[32], const uint4 (&rr)[4], bool fast) {
@@ -389,7 +521,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
                     o[2 * q + 1] += x.y;
                   }
                 }
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + gp_k[k] * p.ldo + nb + tr_q * 8) =
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(gp_k[k]) * p.ldo + nb + tr_q * 8) =
                     make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
               }
               if (c == half && k == 0) VDB_TLE(9, it);
@@ -409,16 +541,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j] * p.alpha, p.act);
             if (p.resid) {
-              const __nv_bfloat16* rs = p.resid + gp * p.ldr + nb;
+              const __nv_bfloat16* rs = p.resid + static_cast<long long>(gp) * p.ldr + nb;
 #pragma unroll
               for (int j = 0; j < 32; ++j) if (nb + j < p.N) f[j] += __bfloat162float(rs[j]);
             }
             if (p.out_f32) {
-              float* dst = reinterpret_cast<float*>(p.out) + gp * p.ldo + nb;
+              float* dst = reinterpret_cast<float*>(p.out) + static_cast<long long>(gp) * p.ldo + nb;
 #pragma unroll
               for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = f[j];
             } else {
-              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + gp * p.ldo + nb;
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(gp) * p.ldo + nb;
 #pragma unroll
               for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = __float2bfloat16(f[j]);
             }
@@ -429,15 +561,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
           if (p.resid && is_fast(c)) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              if (ok_k[k]) rr[k] = __ldg(reinterpret_cast<const uint4*>(p.resid + gp_k[k] * p.ldr + n0 + c * 32 + tr_q * 8));
+              if (ok_k[k]) rr[k] = __ldg(reinterpret_cast<const uint4*>(p.resid + static_cast<long long>(gp_k[k]) * p.ldr + n0 + c * 32 + tr_q * 8));
           }
         };
         // this warp's chunks: half, half+2, ... (kept un-pipelined: double-buffering the 32-register TMEM chunk
         // pushed the kernel into spills and was measured slower)
-        // odd chunk count (BN = 160: five): the warp that took three chunks on this tile takes two on the next one
-        const int first = (p.epi_alt & (BN / 32) & 1) ? (half ^ (it & 1)) : half;
+        // chunk count not a multiple of the warps per quarter (BN = 160: five): rotate who takes the extra chunk
+        const int first = (p.epi_alt && ((BN / 32) % kWPQ) != 0) ? ((half + it) % kWPQ) : half;
 #pragma unroll 1
-        for (int c = first; c < nchunks; c += 2) {
+        for (int c = first; c < nchunks; c += kWPQ) {
           uint4 rr[4];
           load_resid(c, rr);          // residual loads are in flight while the accumulator chunk is fetched
           uint32_t v[32];
@@ -450,13 +582,22 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_kernel(const __grid_cons
       tc_fence_before();
       __syncwarp();
       VDB_TLE(6, it);   // epilogue: tile stored (this warp)
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (lane == 0) {
+        if constexpr (CTAS == 2) mbar_arrive_cluster(leader_tmem_empty[as]);   // the MMA issuer lives in rank 0
+        else mbar_arrive(&tmem_empty[as]);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
+  if constexpr (CTAS == 2) {
+    __syncwarp();
+    cluster_sync_all();   // the peer may still be reading this CTA's operands / signalling its barriers
+    if (warp == 2) tmem_dealloc_pair<512>(tmem_base);
+  } else {
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<512>(tmem_base);
+  }
 }
 
 // split-K reduction + epilogue: out[m, n] = act(alpha * (sum_s partial[s, m, n] + bias)) + resid
@@ -498,18 +639,27 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int kspl
 // ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
-static int launch_igemm(const IgemmParams& p, int num_tiles, cudaStream_t stream) {
-  constexpr size_t smem = STAGES * (kABytes + BN * kBlockK * 2) + (2 * STAGES + 4) * 8 + 16 + BN * 4 + kNumEpiWarps * 4096 + 1024;
+template <int BN, int STAGES, int CTAS, int EW, int MODE>
+static int launch_igemm(const IgemmParams& p, int num_units, cudaStream_t stream) {
+  constexpr size_t smem = STAGES * (kABytes + (BN / CTAS) * kBlockK * 2) + (2 * STAGES + 4) * 8 + 16 + BN * 4 +
+                          EW * 4096 + 1024;
+  static_assert(smem <= 227 * 1024, "igemm shared-memory budget");
+  constexpr int threads = 64 + 32 * EW;
   static bool configured = false;
   if (!configured) {
-    VDB_CUDA_CHECK(cudaFuncSetAttribute(igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VDB_CUDA_CHECK(cudaFuncSetAttribute(igemm_kernel<BN, STAGES, CTAS, EW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
-    prefer_max_smem(igemm_kernel<BN, STAGES>);
+    prefer_max_smem(igemm_kernel<BN, STAGES, CTAS, EW, MODE>);
     configured = true;
   }
-  const int grid = std::min(num_tiles, num_sms());
-  VDB_CUDA_CHECK(launch_pdl(igemm_kernel<BN, STAGES>, dim3(grid), dim3(kNumThreads), smem, stream, p));
+  if (CTAS == 2) {
+    // persistent CTA pairs: one 2-cluster per TPC
+    const int grid = 2 * std::min(num_units, num_sms() / 2);
+    VDB_CUDA_CHECK(launch_cluster2(igemm_kernel<BN, STAGES, CTAS, EW, MODE>, dim3(grid), dim3(threads), smem, stream, p));
+  } else {
+    const int grid = std::min(num_units, num_sms());
+    VDB_CUDA_CHECK(launch_pdl(igemm_kernel<BN, STAGES, CTAS, EW, MODE>, dim3(grid), dim3(threads), smem, stream, p));
+  }
   count_launch();
   return VDB_OK;
 }
@@ -527,6 +677,7 @@ static int pick_bn(int N, int act, int forced) {
 }
 
 static unsigned long long* g_timeline = nullptr;
+static long long g_pair_launches = 0;
 
 struct IgemmEpilogue {
   const float* bias = nullptr;
@@ -562,10 +713,8 @@ static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot
   p.out = e.out; p.ldo = e.ldo; p.out_f32 = e.out_f32; p.act = e.act; p.alpha = e.alpha;
   if (!e.out_f32 && (e.ldo % 8)) return set_error(VDB_ERR_INVALID, "igemm: ldo must be a multiple of 8 for bf16 out");
   if (e.resid && (e.ldr % 8)) return set_error(VDB_ERR_INVALID, "igemm: ldr must be a multiple of 8");
-  int rc = make_tmap_2d(&p.tmB, Wt, static_cast<uint64_t>(Ktot), static_cast<uint64_t>(N),
-                        static_cast<uint64_t>(ldw) * 2, kBlockK, BN);
-  if (rc) return rc;
   const long long M = static_cast<long long>(p.Bo) * p.Ho * p.Wo;
+  if (M >= (1LL << 30)) return set_error(VDB_ERR_UNSUPPORTED, "igemm: more than 2^30 output rows");
   const int tilesM = p.tilesW * p.tilesH * p.tilesB;
   const int mn_tiles = tilesM * p.tilesN;
   // split-K heuristic: fill the machine when the MN grid is small and K is deep
@@ -588,12 +737,47 @@ static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot
   p.timeline = g_timeline;
   static const int epi_alt = [] { const char* ev = getenv("VDB_EPI_ALT"); return (ev && ev[0] == '0') ? 0 : 1; }();
   p.epi_alt = epi_alt;
+  // CTA pairs (cta_group::2) whenever the M tiles pair up and there is no split-K pass
+  static const int pair_mode = [] { const char* ev = getenv("VDB_PAIR"); return ev ? atoi(ev) : 0; }();
+  const bool pair = pair_mode != 0 && p.ksplit == 1 && (tilesM % 2) == 0 && BN >= 128;
+  int rc = make_tmap_2d(&p.tmB, Wt, static_cast<uint64_t>(Ktot), static_cast<uint64_t>(N),
+                        static_cast<uint64_t>(ldw) * 2, kBlockK, pair ? BN / 2 : BN);
+  if (rc) return rc;
   const int num_tiles = mn_tiles * p.ksplit;
-  switch (BN) {
-    case 64: rc = launch_igemm<64, 8>(p, num_tiles, stream); break;
-    case 128: rc = launch_igemm<128, 6>(p, num_tiles, stream); break;
-    case 160: rc = launch_igemm<160, 5>(p, num_tiles, stream); break;
-    default: rc = launch_igemm<256, 4>(p, num_tiles, stream); break;
+  // epilogue specialisation (see igemm_kernel): 1 = plain bf16 fast path, 2 = GEGLU, 0 = everything else
+  static const int spec = [] { const char* ev = getenv("VDB_IGEMM_SPEC"); return (ev && ev[0] == '0') ? 0 : 1; }();
+  int mode = 0;
+  // one bias row per tile: shared bias, or per-image rows with tiles that never straddle two images
+  const bool one_bias_row = e.bias == nullptr || e.bias_bstride == 0 ||
+                            (p.TB == 1 && (static_cast<long long>(p.Ho) * p.Wo == p.rows_per_batch ||
+                                           (p.Ho == 1 && p.Bo == 1 && p.rows_per_batch % kBlockM == 0)));
+  if (spec && !pair && p.ksplit == 1 && !e.out_f32 && one_bias_row) {
+    if (e.act == ACT_GEGLU && BN == 256) mode = 2;
+    else if (e.act == ACT_NONE && e.alpha == 1.f && (N % 32) == 0) mode = 1;
+  }
+  if (pair) {
+    ++g_pair_launches;
+    switch (BN) {
+      case 128: rc = launch_igemm<128, 7, 2, 8, 0>(p, num_tiles / 2, stream); break;
+      case 160: rc = launch_igemm<160, 7, 2, 8, 0>(p, num_tiles / 2, stream); break;
+      default: rc = launch_igemm<256, 6, 2, 8, 0>(p, num_tiles / 2, stream); break;
+    }
+  } else if (mode == 2) {
+    rc = launch_igemm<256, 4, 1, 8, 2>(p, num_tiles, stream);
+  } else if (mode == 1) {
+    switch (BN) {
+      case 64: rc = launch_igemm<64, 8, 1, 8, 1>(p, num_tiles, stream); break;
+      case 128: rc = launch_igemm<128, 6, 1, 8, 1>(p, num_tiles, stream); break;
+      case 160: rc = launch_igemm<160, 5, 1, 8, 1>(p, num_tiles, stream); break;
+      default: rc = launch_igemm<256, 4, 1, 8, 1>(p, num_tiles, stream); break;
+    }
+  } else {
+    switch (BN) {
+      case 64: rc = launch_igemm<64, 8, 1, 8, 0>(p, num_tiles, stream); break;
+      case 128: rc = launch_igemm<128, 6, 1, 8, 0>(p, num_tiles, stream); break;
+      case 160: rc = launch_igemm<160, 5, 1, 8, 0>(p, num_tiles, stream); break;
+      default: rc = launch_igemm<256, 4, 1, 8, 0>(p, num_tiles, stream); break;
+    }
   }
   if (rc) return rc;
   if (p.ksplit > 1) {
@@ -635,6 +819,8 @@ extern "C" {
 
 // debug aid (not part of the product ABI): device buffer of 16*8 u64 receiving CTA 0's per-tile role timestamps
 void vdb_debug_igemm_timeline(void* buf) { g_timeline = reinterpret_cast<unsigned long long*>(buf); }
+// debug aid: how many igemm launches ran as CTA pairs (cta_group::2)
+long long vdb_debug_pair_launches(void) { return g_pair_launches; }
 
 // out[M,N] = act(alpha * ([A | A2] @ W^T + bias)) + resid     (see include/vdb200.h)
 int vdb_gemm_bf16(const void* A, long long M, long long K, long long lda, const void* A2, long long K2,
