@@ -245,7 +245,12 @@ def test_attention(B, H, Nq, Nk, d, causal):
 
 @pytest.mark.parametrize("B,HW,C1,C2,act,eps", [(2, 4096, 320, 0, 1, 1e-5), (2, 1024, 640, 320, 1, 1e-5),
                                               (3, 64, 1280, 1280, 1, 1e-5), (2, 256, 1280, 640, 0, 1e-6),
-                                              (1, 65536, 128, 0, 1, 1e-6), (2, 4096, 512, 0, 0, 1e-6)])
+                                              (1, 65536, 128, 0, 1, 1e-6), (2, 4096, 512, 0, 0, 1e-6),
+                                              # UNet batch (B = 8): few CTAs per image -> the generic two-read path at the
+                                              # large layers, the register-resident path at the small ones
+                                              (8, 4096, 320, 0, 1, 1e-5), (8, 1024, 640, 640, 1, 1e-5),
+                                              (8, 256, 1280, 1280, 1, 1e-5), (8, 64, 1280, 0, 1, 1e-5),
+                                              (8, 100, 320, 0, 0, 1e-6)])
 def test_groupnorm(B, HW, C1, C2, act, eps):
     ops = _ops()
     x1 = rnd(B, HW, C1, seed=1) + 0.5

@@ -25,7 +25,7 @@ namespace vdb {
 
 
 constexpr int kBQ = 128;   // query rows per CTA
-constexpr int kBKV = 128;  // kv columns per tile
+constexpr int kMaxKvStages = 4;
 constexpr float kRescaleThreshold = 8.0f;  // in log2 units (P stays <= 2^8)
 
 struct alignas(64) AttnParams {
@@ -44,21 +44,40 @@ struct alignas(64) AttnParams {
 
 // SB = S accumulator buffers in TMEM (1 or 2), PB = P buffers in smem (1 or 2). SB = PB = 1 keeps the CTA at
 // <= 110 KB smem / 256 TMEM columns so TWO CTAs share an SM: one CTA's softmax (MUFU-bound) overlaps the other's MMAs.
-// SW = softmax warps per TMEM lane quarter (1 or 2).  With SW = 2 the two warps of a quarter split every 128-column
-// S tile (64 columns each) and the O columns; they exchange the row max once per tile through shared memory.  One
+// SW = softmax warps per TMEM lane quarter (1 or 2).  With SW = 2 the two warps of a quarter split every BKV-column
+// S tile (BKV/2 columns each) and the O columns; they exchange the row max once per tile through shared memory.  One
 // softmax warp per SM sub-partition was measured to be instruction-latency bound (the exp pipe was ~30 % busy).
-template <int DK, int DVP, int KV_STAGES, int SB, int PB, int SW>
-__global__ void __launch_bounds__(64 + 128 * SW, (SB == 1 && PB == 1) ? 2 : 1)
+// BKV = kv columns per tile (64 or 128).  BKV = 64 halves the S / P buffers, so S and P can BOTH be double buffered
+// inside 256 TMEM columns / < 113 KB shared memory and two CTAs still share an SM: with a single S buffer the softmax
+// warps of a CTA sat in mbar_wait(s_full) for 29 % of all warp samples (profiles/r01_ncu_hot_lines_v7.txt) because
+// S_{j+1} can only be issued once every warp is done with S_j.
+template <int DK, int DVP, int BKV>
+constexpr size_t attention_smem_bytes(int kv_stages, int pb) {
+  return (DK / 64) * kBQ * 128 + kv_stages * ((DK / 64) * BKV * 128 + (BKV / 64) * DVP * 128) + pb * ((BKV / 64) * kBQ * 128) +
+         24 * 8 + (512 + 256) * 4 + 1024;
+}
+template <int DK, int DVP, int BKV, int KV_STAGES, int SB, int PB>
+constexpr bool attention_two_per_sm() {
+  return (SB * BKV + (DVP <= 64 ? 64 : (DVP <= 128 ? 128 : 256)) <= 256) &&
+         attention_smem_bytes<DK, DVP, BKV>(KV_STAGES, PB) <= 113 * 1024;
+}
+
+template <int DK, int DVP, int BKV, int KV_STAGES, int SB, int PB, int SW>
+__global__ void __launch_bounds__(64 + 128 * SW, attention_two_per_sm<DK, DVP, BKV, KV_STAGES, SB, PB>() ? 2 : 1)
 attention_kernel(const __grid_constant__ AttnParams p) {
+  constexpr int kBKV = BKV;
   constexpr int KA = DK / 64;                      // 64-wide K atoms of the QK^T reduction
+  constexpr int KVA = BKV / 64;                    // 64-kv atoms per tile (K dimension of the PV product)
   constexpr uint32_t kQBytes = KA * kBQ * 128;     // Q tile
   constexpr uint32_t kKBytes = KA * kBKV * 128;    // one K stage
   constexpr uint32_t kVAtom = DVP * 128;           // one 64-kv atom of V^T
-  constexpr uint32_t kVBytes = 2 * kVAtom;         // one V stage (128 kv)
-  constexpr uint32_t kPBytes = 2 * kBQ * 128;      // one P buffer (128 x 128 bf16)
+  constexpr uint32_t kVBytes = KVA * kVAtom;       // one V stage (BKV kv)
+  constexpr uint32_t kPBytes = KVA * kBQ * 128;    // one P buffer (128 x BKV bf16)
   constexpr uint32_t kOCols = DVP <= 64 ? 64 : (DVP <= 128 ? 128 : 256);
-  constexpr uint32_t kTmemCols = (SB * 128 + kOCols <= 256) ? 256 : 512;
-  static_assert(SB * 128 + DVP <= 512, "TMEM budget");
+  constexpr uint32_t kTmemCols = (SB * BKV + kOCols <= 256) ? 256 : 512;
+  static_assert(BKV == 64 || BKV == 128, "kv tile");
+  static_assert(KV_STAGES >= 1 && KV_STAGES <= kMaxKvStages, "kv stages");
+  static_assert(SB * BKV + DVP <= 512, "TMEM budget");
   static_assert(kVAtom % 1024 == 0, "V atom must keep 1024B alignment");
   static_assert(DVP % 16 == 0 && DVP <= 256, "invalid UMMA N for PV");
 
@@ -70,15 +89,18 @@ attention_kernel(const __grid_constant__ AttnParams p) {
   uint8_t* sP = sV + KV_STAGES * kVBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + PB * kPBytes);
   uint64_t* q_full = bars;            // 1
-  uint64_t* k_full = bars + 1;        // [2]
-  uint64_t* k_empty = bars + 3;       // [2]
-  uint64_t* v_full = bars + 5;        // [2]
-  uint64_t* v_empty = bars + 7;       // [2]
-  uint64_t* s_full = bars + 9;        // [2]
-  uint64_t* p_full = bars + 11;       // 1 (count 4: one arrive per softmax warp)
-  uint64_t* pv_done = bars + 12;      // 1
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 13);
-  float* sxm = reinterpret_cast<float*>(bars + 16);   // [2 parity][2 halves][128 rows] partial row max (SW == 2)
+  uint64_t* k_full = bars + 1;        // [kMaxKvStages]
+  uint64_t* k_empty = bars + 5;       // [kMaxKvStages]
+  uint64_t* v_full = bars + 9;        // [kMaxKvStages]
+  uint64_t* v_empty = bars + 13;      // [kMaxKvStages]
+  uint64_t* s_full = bars + 17;       // [2]
+  uint64_t* p_full = bars + 19;       // [PF] (count 4 * SW: one arrive per softmax warp)
+  uint64_t* pv_done = bars + 21;      // 1
+  // BKV == 64 skips the pv_done wait on tiles without a rescale, so a fast softmax warp may arrive for tile j+1 before
+  // a slow one arrived for tile j (never further ahead: S_{j+2} is issued after p_full(j) completes): two barriers.
+  constexpr int PF = (BKV == 64) ? 2 : 1;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 22);
+  float* sxm = reinterpret_cast<float*>(bars + 24);   // [2 parity][2 halves][128 rows] partial row max (SW == 2)
   float* sxl = sxm + 512;                              // [2 halves][128 rows] partial row sums (SW == 2)
 
   const int warp = threadIdx.x >> 5;
@@ -97,12 +119,12 @@ attention_kernel(const __grid_constant__ AttnParams p) {
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < KV_STAGES; ++s) {
       mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
-      mbar_init(&s_full[s], 1);
     }
-    mbar_init(p_full, 4 * SW);
+    for (int s = 0; s < 2; ++s) mbar_init(&s_full[s], 1);
+    for (int s = 0; s < PF; ++s) mbar_init(&p_full[s], 4 * SW);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
@@ -113,8 +135,8 @@ attention_kernel(const __grid_constant__ AttnParams p) {
   const uint32_t tmem_base = *tmem_holder;
   pdl_launch_dependents();
   pdl_wait();
-  const uint32_t tmem_S = tmem_base;             // SB x 128 columns
-  const uint32_t tmem_O = tmem_base + SB * 128;  // DVP columns
+  const uint32_t tmem_S = tmem_base;             // SB x BKV columns
+  const uint32_t tmem_O = tmem_base + SB * BKV;  // DVP columns
 
   if (warp == 0) {
     if (lane == 0) {
@@ -133,7 +155,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
                       b * p.kv_bs + j * kBKV);
         mbar_wait(&v_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&v_full[st], kVBytes);
-        for (int a = 0; a < 2; ++a)
+        for (int a = 0; a < KVA; ++a)
           tma_load_2d(sV + st * kVBytes + a * kVAtom, &p.tmV, &v_full[st], b * p.kv_bs + j * kBKV + a * 64, head * DVP);
       }
     }
@@ -145,7 +167,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         const int st = j % KV_STAGES;
         mbar_wait(&k_full[st], (j / KV_STAGES) & 1);
         tc_fence_after();
-        const uint32_t d = tmem_S + (j % SB) * 128;
+        const uint32_t d = tmem_S + (j % SB) * BKV;
 #pragma unroll
         for (int a = 0; a < KA; ++a) {
           const uint64_t qd = make_desc_sw128(smem_u32(sQ + a * kBQ * 128));
@@ -161,13 +183,13 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       if (SB == 2 && ntiles > 1) issue_S(1);
       for (int j = 0; j < ntiles; ++j) {
         const int st = j % KV_STAGES;
-        mbar_wait(p_full, j & 1);                 // P_j written, O rescaled, S_j consumed
+        mbar_wait(&p_full[j % PF], (j / PF) & 1);   // P_j written, O rescaled, S_j consumed
         if (SB == 1 && j + 1 < ntiles) issue_S(j + 1);   // single S buffer: free now; queue it ahead of PV_j
         mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
         tc_fence_after();
         const uint8_t* pb = sP + (j % PB) * kPBytes;
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < KVA; ++a) {
           const uint64_t pd = make_desc_sw128(smem_u32(pb + a * kBQ * 128));
           const uint64_t vd = make_desc_sw128(smem_u32(sV + st * kVBytes + a * kVAtom));
 #pragma unroll
@@ -186,7 +208,8 @@ attention_kernel(const __grid_constant__ AttnParams p) {
     const int r = quarter * 32 + lane;           // query row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const int q_idx = q0 + r;
-    constexpr int CPW = 4 / SW;                  // 32-column S chunks per warp and tile
+    constexpr int CPW = (BKV / 32) / SW;         // 32-column S chunks per warp and tile
+    constexpr int WC = BKV / SW;                 // S columns per warp and tile
     constexpr int OCH = DVP / 16;                // 16-column O chunks
     const int oc_begin = (SW == 1) ? 0 : (hw == 0 ? 0 : (OCH + 1) / 2);
     const int oc_end = (SW == 1) ? OCH : (hw == 0 ? (OCH + 1) / 2 : OCH);
@@ -196,28 +219,36 @@ attention_kernel(const __grid_constant__ AttnParams p) {
     for (int j = 0; j < ntiles; ++j) {
       mbar_wait(&s_full[j % SB], (j / SB) & 1);
       tc_fence_after();
-      const uint32_t ts = tmem_S + (j % SB) * 128 + lane_off;
+      const uint32_t ts = tmem_S + (j % SB) * BKV + lane_off;
       const int kv0 = j * kBKV;
       const bool need_mask = (kv0 + kBKV > p.Nk) || p.causal;
       const int kv_lim = p.causal ? min(p.Nk, q_idx + 1) : p.Nk;  // valid kv indices are < kv_lim
       // pass 1: row max over this warp's columns.  With SW == 2 a thread owns only 64 columns, so the scores stay in
       // registers for pass 2 and S is read from TMEM once per tile instead of twice.
       float mx = -INFINITY;
-      uint32_t keep[SW == 2 ? 64 : 1];
+      uint32_t keep[SW == 2 ? WC : 1];
       if constexpr (SW == 2) {
-        uint32_t v0[32], v1[32];
-        tmem_ld32(ts + (hw * 2) * 32, v0);
-        tmem_ld32(ts + (hw * 2 + 1) * 32, v1);
-        tmem_wait_ld();
+        if constexpr (WC == 64) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(ts + hw * WC, v0);
+          tmem_ld32(ts + hw * WC + 32, v1);
+          tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { keep[i] = v0[i]; keep[32 + i] = v1[i]; }
+          for (int i = 0; i < 32; ++i) { keep[i] = v0[i]; keep[32 + i] = v1[i]; }
+        } else {
+          uint32_t v0[32];
+          tmem_ld32(ts + hw * WC, v0);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) keep[i] = v0[i];
+        }
         if (need_mask) {
 #pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if (kv0 + hw * 64 + i < kv_lim) mx = fmaxf(mx, __uint_as_float(keep[i]));
+          for (int i = 0; i < WC; ++i)
+            if (kv0 + hw * WC + i < kv_lim) mx = fmaxf(mx, __uint_as_float(keep[i]));
         } else {
 #pragma unroll
-          for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(keep[i]));
+          for (int i = 0; i < WC; ++i) mx = fmaxf(mx, __uint_as_float(keep[i]));
         }
       } else {
 #pragma unroll 1
@@ -266,13 +297,15 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       }
       uint8_t* prow = sP + (j % PB) * kPBytes + r * 128;
       if constexpr (SW == 2) {
-        uint8_t* patom = prow + hw * (kBQ * 128);   // this warp's 64 columns are exactly one 64-wide K atom of P
+        // this warp's columns [hw*WC, +WC): one whole 64-wide K atom of P (WC == 64) or half of the only atom (WC == 32)
+        uint8_t* patom = prow + ((hw * WC) / 64) * (kBQ * 128);
+        const int chunk0 = ((hw * WC) % 64) / 8;    // first 16-byte chunk inside the 128-byte row
         // the scale / subtract and the row sum run as packed fp32 pairs (FFMA2 / FADD2): the softmax warps are
         // issue-limited next to the MUFU pipe, and the pairs halve those two instruction streams
         const unsigned long long sc2 = pack_f2(p.scale_log2, p.scale_log2), nm2 = pack_f2(-m_scaled, -m_scaled);
         unsigned long long l2 = pack_f2(0.f, 0.f);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {               // 8 scores -> one 16-byte chunk
+        for (int q = 0; q < WC / 8; ++q) {          // 8 scores -> one 16-byte chunk
           float e[8];
 #pragma unroll
           for (int i = 0; i < 8; i += 2) {
@@ -280,12 +313,12 @@ attention_kernel(const __grid_constant__ AttnParams p) {
             unpack_f2(fma_f2(pack_f2(__uint_as_float(keep[q * 8 + i]), __uint_as_float(keep[q * 8 + i + 1])), sc2, nm2), xa, xb);
             e[i] = ex2_mufu(xa);
             e[i + 1] = ex2_mufu(xb);
-            if (need_mask && !(kv0 + hw * 64 + q * 8 + i < kv_lim)) e[i] = 0.f;
-            if (need_mask && !(kv0 + hw * 64 + q * 8 + i + 1 < kv_lim)) e[i + 1] = 0.f;
+            if (need_mask && !(kv0 + hw * WC + q * 8 + i < kv_lim)) e[i] = 0.f;
+            if (need_mask && !(kv0 + hw * WC + q * 8 + i + 1 < kv_lim)) e[i + 1] = 0.f;
             l2 = add_f2(l2, pack_f2(e[i], e[i + 1]));
           }
           const uint4 pk = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
-          *reinterpret_cast<uint4*>(patom + ((q ^ (r & 7)) << 4)) = pk;
+          *reinterpret_cast<uint4*>(patom + (((chunk0 + q) ^ (r & 7)) << 4)) = pk;
         }
         {
           float la, lb;
@@ -318,8 +351,11 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         }
       }
       // O must be settled (PV_{j-1} retired) before it is rescaled / accumulated into again
+      // (BKV == 64 variant: the wait is only needed when O is actually rescaled.  The P buffer this tile wrote was last
+      //  read by PV_{j-2}, which retired before S_j — MMAs of a CTA complete in issue order and s_full(j) tracks every
+      //  MMA issued before it — so a tile without a rescale never has to see PV_{j-1} finish.)
       if (j > 0) {
-        if (PB == 2) {
+        if (PB == 2 && (BKV != 64 || rescale || j == ntiles - 1)) {   // (last tile: keeps the epilogue's parity wait sound)
           mbar_wait(pv_done, (j - 1) & 1);
           tc_fence_after();
         }
@@ -339,7 +375,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the MMA's async-proxy reads
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[j % PF]);
     }
     // epilogue: O / l -> bf16
     if (SW == 2) {
@@ -379,21 +415,31 @@ attention_kernel(const __grid_constant__ AttnParams p) {
   if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
-template <int DK, int DVP, int KV_STAGES, int SB, int PB, int SW>
-static int launch_attention(const AttnParams& p, int B, int H, cudaStream_t stream) {
-  constexpr int KA = DK / 64;
-  constexpr size_t smem = KA * kBQ * 128 + KV_STAGES * (KA * kBKV * 128 + 2 * DVP * 128) + PB * (2 * kBQ * 128) +
-                          16 * 8 + (512 + 256) * 4 + 1024;
+struct AttnArgs {   // what the C ABI received; the tensor maps depend on the kernel variant's kv tile
+  const void *Q, *K, *Vt;
+  long long ldq, ldk, ldv;
+  int B, H, q_bstride, kv_bstride;
+};
+
+template <int DK, int DVP, int BKV, int KV_STAGES, int SB, int PB, int SW>
+static int launch_attention(AttnParams& p, const AttnArgs& a, cudaStream_t stream) {
+  constexpr size_t smem = attention_smem_bytes<DK, DVP, BKV>(KV_STAGES, PB);
   static_assert(smem <= 227 * 1024, "attention smem budget");
+  auto kernel = attention_kernel<DK, DVP, BKV, KV_STAGES, SB, PB, SW>;
   static bool configured = false;
   if (!configured) {
-    VDB_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<DK, DVP, KV_STAGES, SB, PB, SW>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    prefer_max_smem(attention_kernel<DK, DVP, KV_STAGES, SB, PB, SW>);
+    VDB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    prefer_max_smem(kernel);
     configured = true;
   }
-  dim3 grid((p.Nq + kBQ - 1) / kBQ, H, B);
-  VDB_CUDA_CHECK(launch_pdl(attention_kernel<DK, DVP, KV_STAGES, SB, PB, SW>, grid, dim3(64 + 128 * SW), smem, stream, p));
+  int rc = make_tmap_2d(&p.tmQ, a.Q, static_cast<uint64_t>(a.ldq), static_cast<uint64_t>(a.B) * a.q_bstride, a.ldq * 2, 64, kBQ);
+  if (rc) return rc;
+  rc = make_tmap_2d(&p.tmK, a.K, static_cast<uint64_t>(a.ldk), static_cast<uint64_t>(a.B) * a.kv_bstride, a.ldk * 2, 64, BKV);
+  if (rc) return rc;
+  rc = make_tmap_2d(&p.tmV, a.Vt, static_cast<uint64_t>(a.B) * a.kv_bstride, static_cast<uint64_t>(a.H) * DVP, a.ldv * 2, 64, DVP);
+  if (rc) return rc;
+  dim3 grid((p.Nq + kBQ - 1) / kBQ, a.H, a.B);
+  VDB_CUDA_CHECK(launch_pdl(kernel, grid, dim3(64 + 128 * SW), smem, stream, p));
   count_launch();
   return VDB_OK;
 }
@@ -431,28 +477,29 @@ int vdb_attention_bf16(const void* Q, long long ldq, int q_col0, const void* K, 
                      q_bstride, kv_bstride);
   AttnParams p;
   memset(&p, 0, sizeof(p));
-  int rc = make_tmap_2d(&p.tmQ, Q, static_cast<uint64_t>(ldq), static_cast<uint64_t>(B) * q_bstride, ldq * 2, 64, kBQ);
-  if (rc) return rc;
-  rc = make_tmap_2d(&p.tmK, K, static_cast<uint64_t>(ldk), static_cast<uint64_t>(B) * kv_bstride, ldk * 2, 64, kBKV);
-  if (rc) return rc;
-  rc = make_tmap_2d(&p.tmV, Vt, static_cast<uint64_t>(B) * kv_bstride, static_cast<uint64_t>(H) * DVP, ldv * 2, 64, DVP);
-  if (rc) return rc;
+  const AttnArgs a{Q, K, Vt, ldq, ldk, ldv, B, H, q_bstride, kv_bstride};
   p.Nq = Nq; p.Nk = Nk; p.q_bs = q_bstride; p.kv_bs = kv_bstride; p.q_col0 = q_col0; p.k_col0 = k_col0; p.dv = d_head; p.causal = causal;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static const int sw = [] { const char* e = getenv("VDB_ATT_SW"); return (e && e[0] == '1') ? 1 : 2; }();
+  // VDB_ATT_BKV=64: 64-column kv tiles with double-buffered S and P, still two CTAs per SM (d_head <= 64 only)
+  static const int bkv = [] { const char* e = getenv("VDB_ATT_BKV"); return (e && atoi(e) == 64) ? 64 : 128; }();
   if (sw == 2) {
-    if (DK == 64 && DVP == 48) return launch_attention<64, 48, 2, 1, 1, 2>(p, B, H, st);   // 2 CTAs / SM, 16 softmax warps / SM
-    if (DK == 64 && DVP == 64) return launch_attention<64, 64, 2, 1, 1, 2>(p, B, H, st);
-    if (DK == 128 && DVP == 80) return launch_attention<128, 80, 2, 2, 2, 2>(p, B, H, st);
-    if (DK == 192 && DVP == 160) return launch_attention<192, 160, 1, 2, 2, 2>(p, B, H, st);
+    if (bkv == 64 && Nk > 64) {
+      if (DK == 64 && DVP == 48) return launch_attention<64, 48, 64, 4, 2, 2, 2>(p, a, st);
+      if (DK == 64 && DVP == 64) return launch_attention<64, 64, 64, 3, 2, 2, 2>(p, a, st);
+    }
+    if (DK == 64 && DVP == 48) return launch_attention<64, 48, 128, 2, 1, 1, 2>(p, a, st);   // 2 CTAs / SM, 16 softmax warps / SM
+    if (DK == 64 && DVP == 64) return launch_attention<64, 64, 128, 2, 1, 1, 2>(p, a, st);
+    if (DK == 128 && DVP == 80) return launch_attention<128, 80, 128, 2, 2, 2, 2>(p, a, st);
+    if (DK == 192 && DVP == 160) return launch_attention<192, 160, 128, 1, 2, 2, 2>(p, a, st);
   } else {
-    if (DK == 64 && DVP == 48) return launch_attention<64, 48, 2, 1, 1, 1>(p, B, H, st);
-    if (DK == 64 && DVP == 64) return launch_attention<64, 64, 2, 1, 1, 1>(p, B, H, st);
-    if (DK == 128 && DVP == 80) return launch_attention<128, 80, 2, 2, 2, 1>(p, B, H, st);
-    if (DK == 192 && DVP == 160) return launch_attention<192, 160, 1, 2, 2, 1>(p, B, H, st);
+    if (DK == 64 && DVP == 48) return launch_attention<64, 48, 128, 2, 1, 1, 1>(p, a, st);
+    if (DK == 64 && DVP == 64) return launch_attention<64, 64, 128, 2, 1, 1, 1>(p, a, st);
+    if (DK == 128 && DVP == 80) return launch_attention<128, 80, 128, 2, 2, 2, 1>(p, a, st);
+    if (DK == 192 && DVP == 160) return launch_attention<192, 160, 128, 1, 2, 2, 1>(p, a, st);
   }
   return set_error(VDB_ERR_UNSUPPORTED, "attention: no kernel for d_head %d", d_head);
 }

@@ -273,18 +273,29 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
 }
 
 // ---------------------------------------------------------------------------------------------
-// Single-launch GroupNorm: statistics + apply in ONE kernel.  grid (nsplit, B) with nsplit*B <= 2 CTAs per SM so that
-// every CTA of the grid is resident; each CTA reduces its pixel range (deterministic, as gn_stats_kernel), publishes its
-// partial, waits on a per-image arrival counter for the other CTAs of the image, folds the partials (fixed order: every
-// CTA computes bit-identical mean / rstd) and normalises ITS OWN pixel range, which it just read (L2-hot).  Saves a
-// launch and the statistics kernel's tail per GroupNorm (61 per UNet call).
+// Single-launch GroupNorm: statistics + apply in ONE kernel.  grid (nsplit, B) with nsplit*B <= the number of CTAs that
+// are resident at once (occupancy query on the host), so that every CTA of the grid is resident; each CTA reduces its
+// pixel range (deterministic, as gn_stats_kernel), publishes its partial, waits on a per-image arrival counter for
+// the other CTAs of the image, folds the partials (fixed order: every CTA computes bit-identical mean / rstd) and
+// normalises ITS OWN pixel range.  Saves a launch and the statistics kernel's tail per GroupNorm (61 per UNet call).
+//   NV == 0: generic.  The pixel range is read twice (the second time L2-hot), 8 independent 16-byte loads in flight
+//            per thread in both passes.
+//   NV  > 0: a thread owns at most NV pixels (host: ceil(HW / nsplit) <= NV * lanes).  They are loaded ONCE, up front,
+//            and stay in registers across the grid-wide wait: the small-resolution layers (8x8 .. 32x32, 45 of the 61
+//            GroupNorms of a UNet call) were pure latency chains -- ~21 us each for 1-5 MB tensors, with the loads of
+//            both passes serialised in batches of four (profiles/r01_launch_shares_v7.txt).
+// gamma / beta are requested before the wait (they do not depend on the statistics), so the only global round trips
+// after it are the partial rows.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const __nv_bfloat16* __restrict__ x1, int C1,
-                                                              const __nv_bfloat16* __restrict__ x2, int C2, int HW,
-                                                              int groups, float eps, int act,
-                                                              const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, float* __restrict__ scratch,
-                                                              __nv_bfloat16* __restrict__ y) {
+template <int NV>
+__global__ void __launch_bounds__(kGnThreads, 2) gn_fused_kernel(const __nv_bfloat16* __restrict__ x1, int C1,
+                                                                 const __nv_bfloat16* __restrict__ x2, int C2, int HW,
+                                                                 int groups, float eps, int act,
+                                                                 const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, float* __restrict__ scratch,
+                                                                 __nv_bfloat16* __restrict__ y) {
+  constexpr int UNR = 8;   // generic path: independent loads in flight per thread
+  constexpr int kMaxCPT = 6;   // channels per thread for the scale / shift table: C <= 3072
   const int C = C1 + C2;
   const int V = C / 8;
   const int cpg = C / groups;
@@ -302,39 +313,42 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const __nv_bfloat1
   const int lanes = kGnThreads / V;
   const int v = threadIdx.x % V;
   const int pl = threadIdx.x / V;
+  const bool active = pl < lanes;
   const bool first = v * 8 < C1;
   const __nv_bfloat16* src = first ? x1 + static_cast<long long>(b) * HW * C1 + v * 8
                                    : x2 + static_cast<long long>(b) * HW * C2 + (v * 8 - C1);
   const long long Cs = first ? C1 : C2;
+  auto accumulate = [](const uint4& u, float (&s)[8], float (&q)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack_bf16x2(w[i]);
+      s[2 * i] += f.x; q[2 * i] += f.x * f.x;
+      s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+    }
+  };
   // ---- phase 1: partial sums of this CTA's pixels ----
-  if (pl < lanes) {
+  uint4 keep[NV > 0 ? NV : 1];
+  if (active) {
     float s[8], q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
-    int p = p_begin + pl;
-    for (; p + 3 * lanes < p_end; p += 4 * lanes) {
-      uint4 u[4];
+    if constexpr (NV > 0) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(src + (p + k * lanes) * Cs));
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = unpack_bf16x2(w[i]);
-          s[2 * i] += f.x; q[2 * i] += f.x * f.x;
-          s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
-        }
+      for (int k = 0; k < NV; ++k) {
+        const int p = p_begin + pl + k * lanes;
+        keep[k] = (p < p_end) ? __ldg(reinterpret_cast<const uint4*>(src + p * Cs)) : make_uint4(0u, 0u, 0u, 0u);
       }
-    }
-    for (; p < p_end; p += lanes) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + p * Cs));
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = unpack_bf16x2(w[i]);
-        s[2 * i] += f.x; q[2 * i] += f.x * f.x;
-        s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+      for (int k = 0; k < NV; ++k) accumulate(keep[k], s, q);   // (pixels past the range contribute zeros)
+    } else {
+      for (int p = p_begin + pl; p < p_end; p += UNR * lanes) {
+        uint4 u[UNR];
+#pragma unroll
+        for (int k = 0; k < UNR; ++k)
+          u[k] = (p + k * lanes < p_end) ? __ldg(reinterpret_cast<const uint4*>(src + (p + k * lanes) * Cs)) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) accumulate(u[k], s, q);
       }
     }
     float* dst = part + (static_cast<size_t>(pl) * V + v) * 16;
@@ -361,12 +375,24 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const __nv_bfloat1
     float* o = partial + (static_cast<long long>(b) * nsplit + split) * 2 * groups + 2 * threadIdx.x;
     o[0] = s; o[1] = q;
   }
+  // gamma / beta of the channels this thread will turn into scale / shift: in flight across the wait below
+  float gam[kMaxCPT], bet[kMaxCPT];
+#pragma unroll
+  for (int k = 0; k < kMaxCPT; ++k) {
+    const int c = threadIdx.x + k * kGnThreads;
+    gam[k] = (c < C) ? __ldg(gamma + c) : 0.f;
+    bet[k] = (c < C) ? __ldg(beta + c) : 0.f;
+  }
   // ---- publish, then wait for the other CTAs of this image (all CTAs of the grid are resident by construction) ----
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     atomicAdd(&arrive[b], 1);
-    while (atomicAdd(&arrive[b], 0) < nsplit) __nanosleep(64);
+    int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(arrive + b) : "memory");
+      if (seen < nsplit) __nanosleep(32);
+    } while (seen < nsplit);
     __threadfence();
   }
   __syncthreads();
@@ -374,7 +400,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const __nv_bfloat1
   // columns of coalesced L2 loads, then a fixed-order sum over the lanes -- every CTA of the image computes
   // bit-identical statistics.  (One thread per group walking all rows was ~4 us of serialised L2 latency.)
   {
-    float* red = part + 6144;                       // [8][64]; scale | shift below use part[0, 2C), C <= 2560
+    float* red = part + 6144;                       // [8][64]; scale | shift below use part[0, 2C), C <= 3072
     const int j = threadIdx.x & 63, sl = threadIdx.x >> 6;
     const float* pp = partial + static_cast<long long>(b) * nsplit * 64 + j;
     float acc = 0.f;
@@ -399,37 +425,49 @@ __global__ void __launch_bounds__(kGnThreads) gn_fused_kernel(const __nv_bfloat1
   }
   float* scale = part;
   float* shift = part + C;
-  for (int c = threadIdx.x; c < C; c += kGnThreads) {
-    const int g = c / cpg;
-    const float sc = grstd[g] * __ldg(gamma + c);
-    scale[c] = sc;
-    shift[c] = __ldg(beta + c) - gmean[g] * sc;
+#pragma unroll
+  for (int k = 0; k < kMaxCPT; ++k) {
+    const int c = threadIdx.x + k * kGnThreads;
+    if (c < C) {
+      const int g = c / cpg;
+      const float sc = grstd[g] * gam[k];
+      scale[c] = sc;
+      shift[c] = bet[k] - gmean[g] * sc;
+    }
   }
   __syncthreads();
   // ---- phase 2: normalise this CTA's pixels ----
-  if (pl < lanes) {
+  if (active) {
     __nv_bfloat16* dstb = y + static_cast<long long>(b) * HW * C + v * 8;
     const int c0 = v * 8;
-    for (int p = p_begin + pl; p < p_end; p += 4 * lanes) {
-      uint4 u[4];
+    auto apply_store = [&](const uint4& u, int p) {
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      uint32_t o[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (p + k * lanes < p_end) u[k] = __ldg(reinterpret_cast<const uint4*>(src + (p + k * lanes) * Cs));
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16x2(w[i]);
+        float a = f.x * scale[c0 + 2 * i] + shift[c0 + 2 * i];
+        float bb = f.y * scale[c0 + 2 * i + 1] + shift[c0 + 2 * i + 1];
+        if (act == 1) { a = silu_bf16_f(a); bb = silu_bf16_f(bb); }
+        o[i] = pack_bf16x2(a, bb);
+      }
+      *reinterpret_cast<uint4*>(dstb + static_cast<long long>(p) * C) = make_uint4(o[0], o[1], o[2], o[3]);
+    };
+    if constexpr (NV > 0) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (p + k * lanes < p_end) {
-          const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-          uint32_t o[4];
+      for (int k = 0; k < NV; ++k) {
+        const int p = p_begin + pl + k * lanes;
+        if (p < p_end) apply_store(keep[k], p);
+      }
+    } else {
+      for (int p = p_begin + pl; p < p_end; p += UNR * lanes) {
+        uint4 u[UNR];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = unpack_bf16x2(w[i]);
-            float a = f.x * scale[c0 + 2 * i] + shift[c0 + 2 * i];
-            float bb = f.y * scale[c0 + 2 * i + 1] + shift[c0 + 2 * i + 1];
-            if (act == 1) { a = silu_bf16_f(a); bb = silu_bf16_f(bb); }
-            o[i] = pack_bf16x2(a, bb);
-          }
-          *reinterpret_cast<uint4*>(dstb + static_cast<long long>(p + k * lanes) * C) = make_uint4(o[0], o[1], o[2], o[3]);
-        }
+        for (int k = 0; k < UNR; ++k)
+          if (p + k * lanes < p_end) u[k] = __ldg(reinterpret_cast<const uint4*>(src + (p + k * lanes) * Cs));
+#pragma unroll
+        for (int k = 0; k < UNR; ++k)
+          if (p + k * lanes < p_end) apply_store(u[k], p + k * lanes);
       }
     }
   }
@@ -918,13 +956,28 @@ int vdb_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int B, in
   if (!x2) C2 = 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static const bool fused_ok = [] { const char* ev = getenv("VDB_GN_FUSED"); return !(ev && ev[0] == '0'); }();
-  if (fused_ok && B <= 2 * num_sms() && C <= 3072) {   // (shared-memory plan of the single-launch kernel)
-    // single launch: every CTA must be resident (2 per SM by registers / shared memory), so at most 2*SMs CTAs
-    int ns = std::max(1, std::min((2 * num_sms()) / B, (HW + 31) / 32));
-    ns = std::min(ns, vdb_groupnorm_nsplit(B, HW) * 4);
-    VDB_CUDA_CHECK(launch_pdl(gn_fused_kernel, dim3(ns, B), dim3(kGnThreads), 0, st,
-                              reinterpret_cast<const __nv_bfloat16*>(x1), C1, reinterpret_cast<const __nv_bfloat16*>(x2), C2,
-                              HW, groups, eps, act, gamma, beta, scratch, reinterpret_cast<__nv_bfloat16*>(y)));
+  // register-resident variant for the small layers (VDB_GN_REG=0 turns it off)
+  static const bool reg_ok = [] { const char* ev = getenv("VDB_GN_REG"); return !(ev && ev[0] == '0'); }();
+  // every CTA of the single-launch kernel must be resident: ask the runtime how many fit (registers / shared memory)
+  static const int occ0 = [] { int n = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gn_fused_kernel<0>, kGnThreads, 0); return n; }();
+  static const int occ4 = [] { int n = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gn_fused_kernel<4>, kGnThreads, 0); return n; }();
+  const int max_resident = std::min(2, std::min(occ0, occ4)) * num_sms();   // (the scratch is sized for 2 CTAs / SM)
+  if (fused_ok && max_resident >= B && C <= 3072) {   // (shared-memory plan of the single-launch kernel)
+    const int max_ns = max_resident / B;
+    const int lanes = kGnThreads / (C / 8);
+    const int ns4 = (HW + 4 * lanes - 1) / (4 * lanes);   // splits needed for <= 4 pixels per thread
+    const __nv_bfloat16* x1b = reinterpret_cast<const __nv_bfloat16*>(x1);
+    const __nv_bfloat16* x2b = reinterpret_cast<const __nv_bfloat16*>(x2);
+    __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y);
+    if (reg_ok && ns4 <= max_ns) {
+      const int ns = std::max(1, std::min(max_ns, std::max(ns4, (HW + 7) / 8)));
+      VDB_CUDA_CHECK(launch_pdl(gn_fused_kernel<4>, dim3(ns, B), dim3(kGnThreads), 0, st, x1b, C1, x2b, C2, HW, groups, eps,
+                                act, gamma, beta, scratch, yb));
+    } else {
+      const int ns = std::max(1, std::min(max_ns, (HW + 31) / 32));
+      VDB_CUDA_CHECK(launch_pdl(gn_fused_kernel<0>, dim3(ns, B), dim3(kGnThreads), 0, st, x1b, C1, x2b, C2, HW, groups, eps,
+                                act, gamma, beta, scratch, yb));
+    }
     count_launch(1);
     return VDB_OK;
   }
