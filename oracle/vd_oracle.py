@@ -234,13 +234,27 @@ def p_sample_ddim(sd, x, conds, unconds, t, index, sched, scale, c_types=("text"
     return x_prev, pred_x0, e_t
 
 
+def q_sample(x_start, t, noise, num_ddpm=1000):
+    """VD_v2_0.q_sample, vd.py:221-224: sqrt(ac_t) * x0 + sqrt(1 - ac_t) * noise (per-row t)."""
+    sch = ddpm_schedule(num_ddpm)     # sqrt taken in fp64, stored fp32 — as the reference's registered buffers
+    shape = (-1,) + (1,) * (x_start.dim() - 1)
+    return (sch["sqrt_alphas_cumprod"][t].reshape(shape) * x_start +
+            sch["sqrt_one_minus_alphas_cumprod"][t].reshape(shape) * noise)
+
+
 def ddim_sample(sd, x_T, conds, unconds, steps, scale=7.5, c_types=("text",), ratios=None, eta=0.0,
-                num_ddpm=1000, collect=False, **kw):
-    """DDIMSampler.sample / ddim_sampling, ddim.py:58-127 with x_T injected (eta must be 0 here)."""
+                num_ddpm=1000, collect=False, x0=None, x0_forward_timesteps=None, x0_noise=None, **kw):
+    """DDIMSampler.sample / ddim_sampling, ddim.py:58-127 with x_T injected (eta must be 0 here).
+    img2img start (ddim.py:97-103): x0 is noised to ddim_timesteps[x0_forward_timesteps] with q_sample and only the
+    first x0_forward_timesteps DDIM timesteps are walked (x_T is ignored)."""
     assert eta == 0.0
     sched = ddim_schedule(ddpm_schedule(num_ddpm)["alphas_cumprod"], steps, eta)
     ts = sched["timesteps"]
     x = x_T
+    if x0 is not None:
+        t0 = torch.full((x0.shape[0],), int(ts[x0_forward_timesteps]), dtype=torch.long)
+        ts = ts[:x0_forward_timesteps]
+        x = q_sample(x0, t0, x0_noise, num_ddpm)
     trace = []
     for i, step in enumerate(np.flip(ts)):
         index = len(ts) - i - 1

@@ -120,6 +120,21 @@ with torch.no_grad():
     da, db = net.vae_decode(z, 'image'), O.vae_decode(sd, z)
 assert (a - b).abs().max() <= 2e-4 * a.abs().max(), (a - b).abs().max()
 assert (da - db).abs().max() <= 1e-4
+# img2img start (ddim.py:97-103): the reference draws q_sample's noise with randn_like -> same seed on both sides
+import lib.model_zoo.ddim as rd
+S = rd.DDIMSampler(net)
+x0 = torch.randn(1, 4, 16, 16, generator=g) * 0.8
+cc, uu = torch.randn(1, 33, 768, generator=g) * 0.5, torch.randn(1, 33, 768, generator=g) * 0.5
+torch.manual_seed(123)
+with torch.no_grad():
+    xa, inter = S.sample(steps=8, shape=[1, 4, 16, 16], x_info={'type': 'image', 'x0': x0, 'x0_forward_timesteps': 5},
+                         c_info={'type': 'image', 'conditioning': cc, 'unconditional_conditioning': uu,
+                                 'unconditional_guidance_scale': 7.5}, verbose=False, eta=0.)
+    torch.manual_seed(123)
+    nz = torch.randn_like(x0)
+    xb = O.ddim_sample(sd, None, [cc], [uu], 8, 7.5, c_types=('image',), model_channels=64, x0=x0, x0_forward_timesteps=5,
+                       x0_noise=nz)
+assert (xa - xb).abs().max() <= 5e-4 * xa.abs().max(), (xa - xb).abs().max()
 print('LIVE-OK')
 """ % ROOT
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)

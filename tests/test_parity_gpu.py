@@ -204,6 +204,36 @@ def test_plms_sampler_vs_oracle(mini):
     _cmp(x, ref, cos_min=0.995, tol=0.1, what="6-step PLMS final latent vs oracle")
 
 
+def test_img2img_start_vs_oracle(mini):
+    """app.py's i2i flow (ddim.py:97-103): x0 -> q_sample at ddim_timesteps[k] -> the first k DDIM steps."""
+    from lib.model_zoo.ddim import DDIMSampler
+    from oracle import vd_oracle as O
+    net, sd, gi, gold = mini
+    g = torch.Generator().manual_seed(11)
+    x0 = torch.randn(1, 4, 16, 16, generator=g) * 0.8
+    noise = torch.randn(1, 4, 16, 16, generator=g)
+    steps, k = 8, 5
+    # q_sample itself (explicit noise) against the closed form
+    t0 = torch.tensor([int(O.ddim_schedule(O.ddpm_schedule(1000)["alphas_cumprod"], steps)["timesteps"][k])])
+    _cmp(net.q_sample(x0.to(DEV), t0.to(DEV), noise=noise.to(DEV)), O.q_sample(x0, t0, noise), cos_min=0.999999, tol=1e-5,
+         what="q_sample")
+    orig = net.q_sample
+    net.q_sample = lambda x_start, t, noise_=None: orig(x_start, t, noise=noise.to(x_start.device))   # inject the draw
+    try:
+        with torch.no_grad():
+            x, inter = DDIMSampler(net).sample(steps=steps, shape=[1, 4, 16, 16],
+                                               x_info={"type": "image", "x0": x0.to(DEV), "x0_forward_timesteps": k},
+                                               c_info={"type": "text", "conditioning": gi["c"].to(DEV),
+                                                       "unconditional_conditioning": gi["u"].to(DEV),
+                                                       "unconditional_guidance_scale": 7.5}, verbose=False, eta=0., log_every_t=1)
+    finally:
+        net.q_sample = orig
+    assert len(inter["pred_x0"]) == k, "the img2img walk covers exactly x0_forward_timesteps steps"
+    ref = O.ddim_sample(sd, None, [gi["c"]], [gi["u"]], steps, 7.5, model_channels=64, x0=x0, x0_forward_timesteps=k,
+                        x0_noise=noise)
+    _cmp(x, ref, cos_min=0.995, tol=0.1, what="img2img 5-of-8-step DDIM latent vs oracle")
+
+
 def test_vae_decode_encode_vs_reference_golden(mini):
     net, sd, gi, gold = mini
     with torch.no_grad():

@@ -57,13 +57,14 @@ constexpr size_t attention_smem_bytes(int kv_stages, int pb) {
          24 * 8 + (512 + 256) * 4 + 1024;
 }
 template <int DK, int DVP, int BKV, int KV_STAGES, int SB, int PB>
-constexpr bool attention_two_per_sm() {
-  return (SB * BKV + (DVP <= 64 ? 64 : (DVP <= 128 ? 128 : 256)) <= 256) &&
-         attention_smem_bytes<DK, DVP, BKV>(KV_STAGES, PB) <= 113 * 1024;
+constexpr int attention_ctas_per_sm() {   // by TMEM columns (512 per SM) and shared memory (227 KB + 1 KB reserved per CTA)
+  constexpr int cols = SB * BKV + (DVP <= 64 ? 64 : (DVP <= 128 ? 128 : 256));
+  constexpr size_t smem = attention_smem_bytes<DK, DVP, BKV>(KV_STAGES, PB);
+  return (cols <= 128 && smem <= 75 * 1024) ? 3 : ((cols <= 256 && smem <= 113 * 1024) ? 2 : 1);
 }
 
 template <int DK, int DVP, int BKV, int KV_STAGES, int SB, int PB, int SW>
-__global__ void __launch_bounds__(64 + 128 * SW, attention_two_per_sm<DK, DVP, BKV, KV_STAGES, SB, PB>() ? 2 : 1)
+__global__ void __launch_bounds__(64 + 128 * SW, attention_ctas_per_sm<DK, DVP, BKV, KV_STAGES, SB, PB>())
 attention_kernel(const __grid_constant__ AttnParams p) {
   constexpr int kBKV = BKV;
   constexpr int KA = DK / 64;                      // 64-wide K atoms of the QK^T reduction
@@ -74,7 +75,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
   constexpr uint32_t kVBytes = KVA * kVAtom;       // one V stage (BKV kv)
   constexpr uint32_t kPBytes = KVA * kBQ * 128;    // one P buffer (128 x BKV bf16)
   constexpr uint32_t kOCols = DVP <= 64 ? 64 : (DVP <= 128 ? 128 : 256);
-  constexpr uint32_t kTmemCols = (SB * BKV + kOCols <= 256) ? 256 : 512;
+  constexpr uint32_t kTmemCols = (SB * BKV + kOCols <= 128) ? 128 : ((SB * BKV + kOCols <= 256) ? 256 : 512);
   static_assert(BKV == 64 || BKV == 128, "kv tile");
   static_assert(KV_STAGES >= 1 && KV_STAGES <= kMaxKvStages, "kv stages");
   static_assert(SB * BKV + DVP <= 512, "TMEM budget");
@@ -484,12 +485,22 @@ int vdb_attention_bf16(const void* Q, long long ldq, int q_col0, const void* K, 
   p.ldo = ldo;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static const int sw = [] { const char* e = getenv("VDB_ATT_SW"); return (e && e[0] == '1') ? 1 : 2; }();
-  // VDB_ATT_BKV=64: 64-column kv tiles with double-buffered S and P, still two CTAs per SM (d_head <= 64 only)
-  static const int bkv = [] { const char* e = getenv("VDB_ATT_BKV"); return (e && atoi(e) == 64) ? 64 : 128; }();
+  // 64-column kv tiles for d_head <= 64 (profiles/r01_variants_v8.txt, r01_ncu_attention_variants_v8.txt):
+  //   VDB_ATT_BKV=64   double-buffered S and P, two CTAs per SM            (self-attention N = 4096: 470 us vs 458 us default)
+  //   VDB_ATT_BKV=643  single S / P buffers in 128 TMEM columns and < 75 KB shared memory: THREE CTAs (24 softmax warps)
+  //                    per SM (N = 4096: 491 us; but 31.3 vs 36.8 us on the 77-key text context, whose second 64 keys
+  //                    of a 128-column tile are masked padding)
+  //   VDB_ATT_BKV=128  the 128-column kernel everywhere
+  // default: the three-CTA kernel for short contexts (65..512 keys), the 128-column kernel otherwise
+  static const int bkv = [] { const char* e = getenv("VDB_ATT_BKV"); const int v = e ? atoi(e) : 0; return (v == 64 || v == 643 || v == 128) ? v : 0; }();
   if (sw == 2) {
     if (bkv == 64 && Nk > 64) {
       if (DK == 64 && DVP == 48) return launch_attention<64, 48, 64, 4, 2, 2, 2>(p, a, st);
       if (DK == 64 && DVP == 64) return launch_attention<64, 64, 64, 3, 2, 2, 2>(p, a, st);
+    }
+    if ((bkv == 643 && Nk > 64) || (bkv == 0 && Nk > 64 && Nk <= 512)) {
+      if (DK == 64 && DVP == 48) return launch_attention<64, 48, 64, 2, 1, 1, 2>(p, a, st);
+      if (DK == 64 && DVP == 64) return launch_attention<64, 64, 64, 2, 1, 1, 2>(p, a, st);
     }
     if (DK == 64 && DVP == 48) return launch_attention<64, 48, 128, 2, 1, 1, 2>(p, a, st);   // 2 CTAs / SM, 16 softmax warps / SM
     if (DK == 64 && DVP == 64) return launch_attention<64, 64, 128, 2, 1, 1, 2>(p, a, st);

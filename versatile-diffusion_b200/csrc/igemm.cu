@@ -105,15 +105,16 @@ VDB_DEVINL float apply_act(float v, int act) {
 
 // CTAS == 2: the kernel runs as CTA pairs (2-cluster, cta_group::2).  A pair owns a 256 x BN output tile: CTA r stages
 // its own 128 rows of A and rows [r*BN/2, (r+1)*BN/2) of the B tile, so the L2 -> shared-memory traffic per FLOP
-// drops by ~28 % (BN 160) / 33 % (BN 256) against two independent CTAs (the conv mainloop is bound by that traffic:
-// profiles/r01_ncu_hot_v5.txt) and the smaller stage buys two more pipeline stages.  Rank 0 issues the MMAs; every
+// drops by ~28 % (BN 160) / 33 % (BN 256) against two independent CTAs and the smaller stage buys two more pipeline
+// stages.  MEASURED SLOWER than single CTAs on every UNet shape (conv 64x64 320->320: 73.9 vs 60.2 us in-graph,
+// GEMM 32768x320x320: 22.7 vs 16.7 us; profiles/r01_variants_v8.txt), so it stays opt-in (VDB_PAIR=1).  Rank 0 issues the MMAs; every
 // TMA of the pair completes on rank 0's full barrier; commits multicast to both CTAs; each CTA drains its own 128
 // accumulator lanes with the same epilogue.
 // MODE selects the epilogue that is compiled in: 0 = every path (split-K partials, GEGLU, fp32 / ragged / per-row-bias
 // tiles), 1 = only the bf16 fast path (act none, alpha 1, N % 32 == 0, one bias row per tile) with the residual of the
 // NEXT chunk prefetched, 2 = only GEGLU.  The generic kernel is ~6300 SASS instructions; ncu's source view of the
 // K = 320 GEMMs showed 9 % instruction-fetch stalls and 10 % branch-resolve stalls in the epilogue warps, and the
-// residual's first use exposed its full load latency (profiles/r01_ncu_gemm320_v6.txt).
+// residual's first use exposed its full load latency (hot lines of the current build: profiles/r01_ncu_hot_lines_v7.txt).
 template <int BN, int STAGES, int CTAS, int EW, int MODE>
 __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   constexpr int kNumEpiWarps = EW;

@@ -60,19 +60,12 @@ def extract_into_tensor(a, t, x_shape):
 
 
 def timestep_embedding(timesteps, dim, max_period=10000, repeat_only=False):
-    """[cos | sin] sinusoid (reference :131-151). CUDA tensors go through the vdb200 kernel."""
+    """[cos | sin] sinusoid (reference :131-151) on the vdb200 kernel; CPU tensors raise (no CPU path in the product)."""
     if repeat_only:
         return timesteps[:, None].expand(-1, dim)
-    if timesteps.is_cuda:
-        from vdb200 import ops
-        return ops.timestep_embedding(timesteps.long().contiguous(), dim, max_period)
-    half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(start=0, end=half, dtype=torch.float32) / half)
-    args = timesteps[:, None].float() * freqs[None]
-    emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
-    if dim % 2:
-        emb = torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1)
-    return emb
+    require_cuda(timesteps, "timestep_embedding")
+    from vdb200 import ops
+    return ops.timestep_embedding(timesteps.long().contiguous(), dim, max_period)
 
 
 def noise_like(x, repeat=False):

@@ -115,9 +115,7 @@ class VD_v2_0(nn.Module):
     def q_sample(self, x_start, t, noise=None):
         """sqrt(ac_t)*x0 + sqrt(1-ac_t)*noise (vd.py:221-224); per-row t -> one axpby launch per distinct row."""
         noise = torch.randn_like(x_start) if noise is None else noise
-        if not x_start.is_cuda:
-            return (extract_into_tensor(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start +
-                    extract_into_tensor(self.sqrt_one_minus_alphas_cumprod, t, x_start.shape) * noise)
+        require_cuda(x_start, "VD_v2_0.q_sample")
         ops = _ops()
         xs, nz = x_start.float().contiguous(), noise.float().contiguous()
         out = torch.empty_like(xs)
