@@ -40,7 +40,20 @@ struct alignas(64) AttnParams {
   float scale_log2;  // d^-1/2 * log2(e)
   __nv_bfloat16* out;
   long long ldo;
+  unsigned long long* timeline;   // debug (-DVDB_TIMELINE): per-tile role timestamps of CTA (0,0,0); null = off
+  int stagger_ns;                 // > 0: CTAs of every second wave start this much later (experiment: see below)
+  int num_sms;
 };
+
+// Debug build only (tools/attention_timeline.py): globaltimer stamps of one softmax warp (warp 2: lane quarter 2, first
+// half of the columns) and of the MMA issuer, 16 slots per kv tile, first 16 tiles of CTA (0,0,0).
+//   softmax: 0 wants S_j, 1 S_j ready, 2 scores in registers + own max, 3 max exchanged, 4 exp2 + P stored,
+//            5 O settled / rescaled, 6 arrived on p_full          MMA: 8 wants P_j, 9 P_j ready, 10 next S issued, 11 PV_j issued
+#ifdef VDB_TIMELINE
+#define VDB_ATL(slot, j, who) do { if (p.timeline && (who) && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (j) < 16) p.timeline[(j) * 16 + (slot)] = gtime(); } while (0)
+#else
+#define VDB_ATL(slot, j, who) do { } while (0)
+#endif
 
 // SB = S accumulator buffers in TMEM (1 or 2), PB = P buffers in smem (1 or 2). SB = PB = 1 keeps the CTA at
 // <= 110 KB smem / 256 TMEM columns so TWO CTAs share an SM: one CTA's softmax (MUFU-bound) overlaps the other's MMAs.
@@ -136,6 +149,17 @@ attention_kernel(const __grid_constant__ AttnParams p) {
   const uint32_t tmem_base = *tmem_holder;
   pdl_launch_dependents();
   pdl_wait();
+  // Experiment (VDB_ATT_STAGGER / vdb_debug_attention_stagger): the role timeline shows the CTAs that share an SM running their
+  // exp2 phases at the SAME time (the MUFU pipe is saturated for ~55 % of a tile and idle for the rest); CTAs launched together
+  // stay in phase because contention slows both equally.  Delaying every second wave of CTAs at start puts co-resident CTAs
+  // in anti-phase.
+  if (p.stagger_ns > 0) {
+    const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if ((lin / static_cast<unsigned>(p.num_sms)) & 1u) {
+      const unsigned long long t0 = gtime();
+      while (gtime() - t0 < static_cast<unsigned long long>(p.stagger_ns)) __nanosleep(64);
+    }
+  }
   const uint32_t tmem_S = tmem_base;             // SB x BKV columns
   const uint32_t tmem_O = tmem_base + SB * BKV;  // DVP columns
 
@@ -184,8 +208,11 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       if (SB == 2 && ntiles > 1) issue_S(1);
       for (int j = 0; j < ntiles; ++j) {
         const int st = j % KV_STAGES;
+        VDB_ATL(8, j, true);
         mbar_wait(&p_full[j % PF], (j / PF) & 1);   // P_j written, O rescaled, S_j consumed
+        VDB_ATL(9, j, true);
         if (SB == 1 && j + 1 < ntiles) issue_S(j + 1);   // single S buffer: free now; queue it ahead of PV_j
+        VDB_ATL(10, j, true);
         mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
         tc_fence_after();
         const uint8_t* pb = sP + (j % PB) * kPBytes;
@@ -199,6 +226,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         }
         umma_commit(&v_empty[st]);
         umma_commit(pv_done);
+        VDB_ATL(11, j, true);
         if (SB == 2 && j + 2 < ntiles) issue_S(j + 2);
       }
     }
@@ -217,9 +245,13 @@ attention_kernel(const __grid_constant__ AttnParams p) {
     auto pair_sync = [&] { asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory"); };   // the quarter's two warps
     float m_ref = -INFINITY;  // reference max (raw score units)
     float l_sum = 0.f;        // this thread's share of the row sum
+    const bool tl_warp = (warp == 2) && (lane == 0);   // (debug timeline)
+    (void)tl_warp;
     for (int j = 0; j < ntiles; ++j) {
+      VDB_ATL(0, j, tl_warp);
       mbar_wait(&s_full[j % SB], (j / SB) & 1);
       tc_fence_after();
+      VDB_ATL(1, j, tl_warp);
       const uint32_t ts = tmem_S + (j % SB) * BKV + lane_off;
       const int kv0 = j * kBKV;
       const bool need_mask = (kv0 + kBKV > p.Nk) || p.causal;
@@ -268,11 +300,13 @@ attention_kernel(const __grid_constant__ AttnParams p) {
           }
         }
       }
+      VDB_ATL(2, j, tl_warp);
       if (SW == 2) {   // combine with the partner warp's half of the row
         sxm[((j & 1) * 2 + hw) * 128 + r] = mx;
         pair_sync();
         mx = fmaxf(mx, sxm[((j & 1) * 2 + (hw ^ 1)) * 128 + r]);
       }
+      VDB_ATL(3, j, tl_warp);
       // lazy rescale decision (warp-uniform because tcgen05.ld/st are warp collectives; identical in both warps
       // of a quarter because they see the same 32 rows)
       const float m_new = fmaxf(m_ref, mx);
@@ -351,6 +385,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
           }
         }
       }
+      VDB_ATL(4, j, tl_warp);
       // O must be settled (PV_{j-1} retired) before it is rescaled / accumulated into again
       // (BKV == 64 variant: the wait is only needed when O is actually rescaled.  The P buffer this tile wrote was last
       //  read by PV_{j-2}, which retired before S_j — MMAs of a CTA complete in issue order and s_full(j) tracks every
@@ -373,10 +408,12 @@ attention_kernel(const __grid_constant__ AttnParams p) {
           tmem_wait_st();
         }
       }
+      VDB_ATL(5, j, tl_warp);
       fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the MMA's async-proxy reads
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[j % PF]);
+      VDB_ATL(6, j, tl_warp);
     }
     // epilogue: O / l -> bf16
     if (SW == 2) {
@@ -449,7 +486,16 @@ static int launch_attention(AttnParams& p, const AttnArgs& a, cudaStream_t strea
 
 using namespace vdb;
 
+static unsigned long long* g_att_timeline = nullptr;
+static int g_att_stagger = -1;   // -1: use VDB_ATT_STAGGER
+
 extern "C" {
+
+// debug aid (not part of the product ABI; stamps exist only in a -DVDB_TIMELINE build): 16 x 16 u64 device buffer
+void vdb_debug_attention_timeline(void* buf) { g_att_timeline = reinterpret_cast<unsigned long long*>(buf); }
+
+// debug aid: start delay (ns) of every second wave of attention CTAs; -1 = take VDB_ATT_STAGGER (default 0 = off)
+void vdb_debug_attention_stagger(int ns) { g_att_stagger = ns; }
 
 // Padded head sizes the projection GEMMs must produce for a given d_head (see include/vdb200.h).
 int vdb_attention_dk_pad(int d_head) { return d_head <= 64 ? 64 : (d_head <= 128 ? 128 : (d_head <= 192 ? 192 : -1)); }
@@ -483,6 +529,10 @@ int vdb_attention_bf16(const void* Q, long long ldq, int q_col0, const void* K, 
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
+  p.timeline = g_att_timeline;
+  static const int stagger_env = [] { const char* e = getenv("VDB_ATT_STAGGER"); return e ? atoi(e) : 0; }();
+  p.stagger_ns = g_att_stagger >= 0 ? g_att_stagger : stagger_env;
+  p.num_sms = num_sms();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static const int sw = [] { const char* e = getenv("VDB_ATT_SW"); return (e && e[0] == '1') ? 1 : 2; }();
   // 64-column kv tiles for d_head <= 64 (profiles/r01_variants_v8.txt, r01_ncu_attention_variants_v8.txt):

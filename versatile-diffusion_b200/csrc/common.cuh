@@ -264,6 +264,13 @@ VDB_DEVINL void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
 VDB_DEVINL void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 VDB_DEVINL void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// nanosecond wall clock shared by all SMs (debug timelines, watchdogs)
+VDB_DEVINL unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // ----------------------------------------------------------------------------
 // programmatic dependent launch: a kernel launched with the PDL attribute may start while its predecessor
 // drains; it must not touch dependent global memory before pdl_wait(). No-ops for ordinary launches.
