@@ -41,8 +41,6 @@ struct alignas(64) AttnParams {
   __nv_bfloat16* out;
   long long ldo;
   unsigned long long* timeline;   // debug (-DVDB_TIMELINE): per-tile role timestamps of CTA (0,0,0); null = off
-  int stagger_ns;                 // > 0: CTAs of every second wave start this much later (experiment: see below)
-  int num_sms;
 };
 
 // Debug build only (tools/attention_timeline.py): globaltimer stamps of one softmax warp (warp 2: lane quarter 2, first
@@ -149,17 +147,6 @@ attention_kernel(const __grid_constant__ AttnParams p) {
   const uint32_t tmem_base = *tmem_holder;
   pdl_launch_dependents();
   pdl_wait();
-  // Experiment (VDB_ATT_STAGGER / vdb_debug_attention_stagger): the role timeline shows the CTAs that share an SM running their
-  // exp2 phases at the SAME time (the MUFU pipe is saturated for ~55 % of a tile and idle for the rest); CTAs launched together
-  // stay in phase because contention slows both equally.  Delaying every second wave of CTAs at start puts co-resident CTAs
-  // in anti-phase.
-  if (p.stagger_ns > 0) {
-    const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    if ((lin / static_cast<unsigned>(p.num_sms)) & 1u) {
-      const unsigned long long t0 = gtime();
-      while (gtime() - t0 < static_cast<unsigned long long>(p.stagger_ns)) __nanosleep(64);
-    }
-  }
   const uint32_t tmem_S = tmem_base;             // SB x BKV columns
   const uint32_t tmem_O = tmem_base + SB * BKV;  // DVP columns
 
@@ -487,15 +474,11 @@ static int launch_attention(AttnParams& p, const AttnArgs& a, cudaStream_t strea
 using namespace vdb;
 
 static unsigned long long* g_att_timeline = nullptr;
-static int g_att_stagger = -1;   // -1: use VDB_ATT_STAGGER
 
 extern "C" {
 
 // debug aid (not part of the product ABI; stamps exist only in a -DVDB_TIMELINE build): 16 x 16 u64 device buffer
 void vdb_debug_attention_timeline(void* buf) { g_att_timeline = reinterpret_cast<unsigned long long*>(buf); }
-
-// debug aid: start delay (ns) of every second wave of attention CTAs; -1 = take VDB_ATT_STAGGER (default 0 = off)
-void vdb_debug_attention_stagger(int ns) { g_att_stagger = ns; }
 
 // Padded head sizes the projection GEMMs must produce for a given d_head (see include/vdb200.h).
 int vdb_attention_dk_pad(int d_head) { return d_head <= 64 ? 64 : (d_head <= 128 ? 128 : (d_head <= 192 ? 192 : -1)); }
@@ -530,9 +513,6 @@ int vdb_attention_bf16(const void* Q, long long ldq, int q_col0, const void* K, 
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.timeline = g_att_timeline;
-  static const int stagger_env = [] { const char* e = getenv("VDB_ATT_STAGGER"); return e ? atoi(e) : 0; }();
-  p.stagger_ns = g_att_stagger >= 0 ? g_att_stagger : stagger_env;
-  p.num_sms = num_sms();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static const int sw = [] { const char* e = getenv("VDB_ATT_SW"); return (e && e[0] == '1') ? 1 : 2; }();
   // 64-column kv tiles for d_head <= 64 (profiles/r01_variants_v8.txt, r01_ncu_attention_variants_v8.txt):
