@@ -99,6 +99,38 @@ def test_to_returns_none_and_no_cpu_path():
                                         "unconditional_guidance_scale": 7.5}, verbose=False)
 
 
+def test_every_entry_point_refuses_cpu_tensors():
+    """No CPU fallback anywhere in the product: q_sample, timestep_embedding, the VAE and the raw ops all raise."""
+    from lib.model_zoo.diffusion_utils import timestep_embedding
+    from vdb200 import ops
+    net = build(True)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        net.q_sample(torch.zeros(1, 4, 8, 8), torch.zeros(1, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        timestep_embedding(torch.tensor([1, 21]), 320)
+    with pytest.raises((RuntimeError, ValueError)):
+        net.vae_decode(torch.zeros(1, 4, 8, 8), "image")
+    with pytest.raises((RuntimeError, ValueError)):
+        net.vae_encode(torch.zeros(1, 3, 64, 64), "image")
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        ops.layernorm(torch.zeros(4, 320, dtype=torch.bfloat16), torch.ones(320), torch.zeros(320))
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        ops.gemm(torch.zeros(128, 64, dtype=torch.bfloat16), torch.zeros(64, 64, dtype=torch.bfloat16))
+
+
+def test_missing_library_fails_at_import(tmp_path):
+    """The binding must fail loudly when libvdb200.so is absent (no silent library / eager fallback)."""
+    import subprocess
+    import sys
+    pkg = os.path.join(ROOT, "versatile-diffusion_b200")
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "try:\n    import vdb200\n    print('IMPORTED')\n"
+            "except (ImportError, OSError) as e:\n    print('REFUSED', type(e).__name__)\n") % pkg
+    env = dict(os.environ, VDB200_LIB=str(tmp_path / "nope" / "libvdb200.so"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert "REFUSED" in out.stdout and "IMPORTED" not in out.stdout, out.stdout + out.stderr[-500:]
+
+
 def test_packed_weights_invalidate_on_load_and_cast():
     net = build(True)
     rb = net.diffuser["image"].data_blocks[1][0]
