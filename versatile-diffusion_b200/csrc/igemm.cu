@@ -61,6 +61,7 @@ struct alignas(64) IgemmParams {
   float alpha;                // out = act(alpha * (acc + bias)) + resid
   float* partial;             // split-K: [ksplit, M, N] fp32
   int epi_alt;                // 1: the two warps of a TMEM quarter swap chunk parity every tile (odd chunk counts)
+  int nfast;                  // 1: N is the fast tile index (tile t -> n = t % tilesN, m = t / tilesN); needs ksplit == 1
   unsigned long long* timeline; // debug: per-tile role timestamps of CTA 0 (null = off)
 };
 
@@ -177,10 +178,16 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
       const bool flat = (p.tilesH == 1) && (p.tilesB == 1);
       const int step_m = t_step % unitsM, step_r = t_step / unitsM;
       int unit_m = t_first % unitsM, rest = t_first / unitsM;
+      // N-fast order (opt-in): the N tiles of one M tile run on neighbouring CTAs at the same time, so an A operand larger
+      // than L2 is fetched from DRAM once instead of once per N tile
+      const int nf_step_n = p.nfast ? t_step % p.tilesN : 0, nf_step_m = p.nfast ? t_step / p.tilesN : 0;
+      int nf_n = p.nfast ? t_first % p.tilesN : 0, nf_m = p.nfast ? t_first / p.tilesN : 0;
       for (int t = t_first; t < num_tiles; t += t_step) {
-        const int m_idx = unit_m * CTAS + static_cast<int>(cta_rank);
-        int n_idx = rest, ks = 0;
+        const int m_idx = (p.nfast ? nf_m : unit_m) * CTAS + static_cast<int>(cta_rank);
+        int n_idx = p.nfast ? nf_n : rest, ks = 0;
         if (p.ksplit > 1) { n_idx = rest % p.tilesN; ks = rest / p.tilesN; }
+        nf_n += nf_step_n; nf_m += nf_step_m;
+        if (p.nfast && nf_n >= p.tilesN) { nf_n -= p.tilesN; ++nf_m; }
         int wt = m_idx, ht = 0, bt = 0;
         if (!flat) {
           wt = m_idx % p.tilesW;
@@ -297,10 +304,14 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
     const bool flat = (p.tilesH == 1) && (p.tilesB == 1);   // GEMM view: M tiles along W only
     const int step_m = t_step % unitsM, step_r = t_step / unitsM;
     int unit_m = t_first % unitsM, rest = t_first / unitsM;
+    const int nf_step_n = p.nfast ? t_step % p.tilesN : 0, nf_step_m = p.nfast ? t_step / p.tilesN : 0;   // (see the producer)
+    int nf_n = p.nfast ? t_first % p.tilesN : 0, nf_m = p.nfast ? t_first / p.tilesN : 0;
     for (int t = t_first; t < num_tiles; t += t_step, ++it) {
-      const int m_idx = unit_m * CTAS + static_cast<int>(cta_rank);
-      int n_idx = rest, ks = 0;
+      const int m_idx = (p.nfast ? nf_m : unit_m) * CTAS + static_cast<int>(cta_rank);
+      int n_idx = p.nfast ? nf_n : rest, ks = 0;
       if (p.ksplit > 1) { n_idx = rest % p.tilesN; ks = rest / p.tilesN; }
+      nf_n += nf_step_n; nf_m += nf_step_m;
+      if (p.nfast && nf_n >= p.tilesN) { nf_n -= p.tilesN; ++nf_m; }
       int wt = m_idx, ht = 0, bt = 0;
       if (!flat) {
         wt = m_idx % p.tilesW;
@@ -736,6 +747,17 @@ static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot
   // CTA pairs (cta_group::2) whenever the M tiles pair up and there is no split-K pass
   static const int pair_mode = [] { const char* ev = getenv("VDB_PAIR"); return ev ? atoi(ev) : 0; }();
   const bool pair = pair_mode != 0 && p.ksplit == 1 && (tilesM % 2) == 0 && BN >= 128;
+  // N-fast tile order (VDB_NFAST=1, opt-in until measured): only when every CTA keeps its N tile from one of its tiles to
+  // the next (grid % tilesN == 0: the bias tile cached in shared memory stays valid) and A is too big to survive in L2
+  // between two M sweeps (FF-out at the 64x64 level re-reads its 84 MB A operand: 170.7 MB of DRAM traffic against
+  // 127 MB algorithmic, profiles/r01_ncu_full_v8.txt)
+  static const int nfast_mode = [] { const char* ev = getenv("VDB_NFAST"); return ev ? atoi(ev) : 0; }();
+  {
+    const int grid = std::min(mn_tiles * p.ksplit, num_sms());
+    const double a_bytes = static_cast<double>(M) * static_cast<double>(Ktot) * 2.0;
+    p.nfast = (nfast_mode != 0 && !pair && p.ksplit == 1 && p.tilesN > 1 && (grid % p.tilesN) == 0 &&
+               (nfast_mode == 2 || a_bytes > 48e6)) ? 1 : 0;
+  }
   int rc = make_tmap_2d(&p.tmB, Wt, static_cast<uint64_t>(Ktot), static_cast<uint64_t>(N),
                         static_cast<uint64_t>(ldw) * 2, kBlockK, pair ? BN / 2 : BN);
   if (rc) return rc;
