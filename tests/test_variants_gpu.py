@@ -1,0 +1,34 @@
+"""Opt-in kernel variants (environment switches read once per process) against the same kernel parity tests, each in its own
+process.  Skipped unless VDB_TEST_VARIANTS=1: variants that have not been measured/validated on a B200 yet stay out of the
+default GPU suite (the default kernels are covered by test_kernels_gpu.py / test_parity_gpu.py)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+VARIANTS = [
+    ({"VDB_ATT_BKV": "64"}, "attention"),          # 64-column kv tiles, double-buffered S / P           (validated, round 1)
+    ({"VDB_ATT_BKV": "643"}, "attention"),         # three CTAs per SM                                     (validated, round 1)
+    ({"VDB_ATT_BKV": "128"}, "attention"),         # the 128-column kernel for every context length        (validated, round 1)
+    ({"VDB_ATT_PP": "2"}, "attention"),            # ping-pong, two query tiles per CTA                    (NOT yet run on a GPU)
+    ({"VDB_ATT_PP": "3"}, "attention"),            # ping-pong, three query tiles per CTA                  (NOT yet run on a GPU)
+    ({"VDB_GN_REG": "0"}, "groupnorm"),            # generic two-read single-launch GroupNorm              (validated, round 1)
+    ({"VDB_GN_FUSED": "0"}, "groupnorm"),          # statistics + apply kernels                            (validated, round 1)
+    ({"VDB_PAIR": "1"}, "gemm or conv3x3"),        # CTA pairs (cta_group::2)                              (validated, round 1)
+    ({"VDB_NFAST": "2"}, "gemm or conv3x3"),       # N-fast tile order wherever it is legal                (NOT yet run on a GPU)
+    ({"VDB_IGEMM_SPEC": "0"}, "gemm or conv3x3"),  # generic epilogue only
+]
+
+
+@pytest.mark.skipif(os.environ.get("VDB_TEST_VARIANTS") != "1", reason="set VDB_TEST_VARIANTS=1 to run the opt-in kernel variants")
+@pytest.mark.parametrize("env,select", VARIANTS, ids=lambda v: "_".join(f"{k}={x}" for k, x in v.items()) if isinstance(v, dict) else None)
+def test_variant(env, select):
+    e = dict(os.environ, **env)
+    out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "--timeout", "120",
+                          os.path.join(ROOT, "tests", "test_kernels_gpu.py"), "-k", select],
+                         capture_output=True, text=True, env=e, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1000:]
