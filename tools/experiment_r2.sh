@@ -20,9 +20,9 @@ if [ "$PP3" = "0" ]; then
   VDB_ATT_PP=3 VDB_NFAST=$([ "$NF" = "0" ] && echo 1 || echo 0) T=240 run bench_pp3 python bench.py --no-cpu-baseline
 fi
 grep -E "^===|passed|failed|\"value\"" $O/exp_$TAG.log | cut -c1-260
-python - <<'PY'
-import json, glob
-for f in sorted(glob.glob("gpurun_out/mb_*_'"$TAG"'.json")):
+python - "$TAG" <<'PY'
+import json, glob, sys
+for f in sorted(glob.glob("gpurun_out/mb_*_%s.json" % sys.argv[1])):
     for r in json.load(open(f))["results"]:
         if r["name"].startswith(("attention N4096 M4096", "gemm 32768x320x1280")): print(f, r["name"], r.get("graph_us"))
 PY
