@@ -18,6 +18,8 @@ VARIANTS = [
     ({"VDB_ATT_PP": "3"}, "attention"),            # ping-pong, three query tiles per CTA                  (NOT yet run on a GPU)
     ({"VDB_GN_REG": "0"}, "groupnorm"),            # generic two-read single-launch GroupNorm              (validated, round 1)
     ({"VDB_GN_FUSED": "0"}, "groupnorm"),          # statistics + apply kernels                            (validated, round 1)
+    ({"VDB_GN_CLUSTER": "5"}, "groupnorm"),        # thread-block-cluster GroupNorm, pixels kept in smem    (NOT yet run on a GPU)
+    ({"VDB_GN_CLUSTER": "7"}, "groupnorm"),        # cluster GroupNorm, two-read path                       (NOT yet run on a GPU)
     ({"VDB_PAIR": "1"}, "gemm or conv3x3"),        # CTA pairs (cta_group::2)                              (validated, round 1)
     ({"VDB_NFAST": "2"}, "gemm or conv3x3"),       # N-fast tile order wherever it is legal                (NOT yet run on a GPU)
     ({"VDB_IGEMM_SPEC": "0"}, "gemm or conv3x3"),  # generic epilogue only

@@ -10,19 +10,23 @@ PT="python -m pytest -q -p no:cacheprovider --timeout 100 tests/test_kernels_gpu
 VDB_ATT_PP=3 T=90 run t_pp3 $PT -k "attention"; PP3=$?
 VDB_ATT_PP=2 T=90 run t_pp2 $PT -k "attention"; PP2=$?
 VDB_NFAST=2 T=120 run t_nfast $PT -k "gemm or conv3x3"; NF=$?
-run mb_default python tools/microbench.py attention,gemm $O/mb_default_$TAG.json
+VDB_GN_CLUSTER=5 T=90 run t_gncl $PT -k "groupnorm"; GC=$?
+VDB_GN_CLUSTER=7 T=90 run t_gncl_nokeep $PT -k "groupnorm"
+run mb_default python tools/microbench.py attention,gemm,groupnorm $O/mb_default_$TAG.json
+[ "$GC" = "0" ] && VDB_GN_CLUSTER=1 run mb_gncl python tools/microbench.py groupnorm $O/mb_gncl_$TAG.json
+[ "$GC" = "0" ] && VDB_GN_CLUSTER=3 run mb_gncl_nokeep python tools/microbench.py groupnorm $O/mb_gncl_nokeep_$TAG.json
 [ "$PP3" = "0" ] && VDB_ATT_PP=3 run mb_pp3 python tools/microbench.py attention $O/mb_pp3_$TAG.json
 [ "$PP2" = "0" ] && VDB_ATT_PP=2 run mb_pp2 python tools/microbench.py attention $O/mb_pp2_$TAG.json
 [ "$NF" = "0" ] && VDB_NFAST=1 run mb_nfast python tools/microbench.py gemm $O/mb_nfast_$TAG.json
 if [ "$PP3" = "0" ]; then
   VDB_ATT_PP=3 T=120 run ncu_pp3 ncu --set full --clock-control none --import-source on -k regex:attention_pp_kernel --launch-skip 3 --launch-count 1 \
     -f -o $O/att_pp3_$TAG python tools/microbench.py attention $O/mb_ncu_pp3.json
-  VDB_ATT_PP=3 VDB_NFAST=$([ "$NF" = "0" ] && echo 1 || echo 0) T=240 run bench_pp3 python bench.py --no-cpu-baseline
+  VDB_ATT_PP=3 VDB_NFAST=$([ "$NF" = "0" ] && echo 1 || echo 0) VDB_GN_CLUSTER=$([ "$GC" = "0" ] && echo 1 || echo 0) T=240 run bench_all python bench.py --no-cpu-baseline
 fi
 grep -E "^===|passed|failed|\"value\"" $O/exp_$TAG.log | cut -c1-260
 python - "$TAG" <<'PY'
 import json, glob, sys
 for f in sorted(glob.glob("gpurun_out/mb_*_%s.json" % sys.argv[1])):
     for r in json.load(open(f))["results"]:
-        if r["name"].startswith(("attention N4096 M4096", "gemm 32768x320x1280")): print(f, r["name"], r.get("graph_us"))
+        if r["name"].startswith(("attention N4096 M4096", "gemm 32768x320x1280", "groupnorm")): print(f, r["name"], r.get("graph_us"))
 PY
