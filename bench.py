@@ -229,6 +229,51 @@ def run_product(args):
         return
     cpu = cpu_baseline_sample(net) if world == 1 and not args.no_cpu_baseline else None
     peaks = measured_peaks()
+    # ---- roofline refinement (last GPU work of the run, single GPU only): the SAME igemm launches of two eager DDIM steps,
+    # re-issued back to back inside one CUDA graph and timed with CUDA events -> the kernel's launch duration without the host
+    # launch path that the per-launch events above include.  Any failure leaves the eager figures in place.
+    if world == 1 and roof is not None and not args.no_graph_roofline:
+        try:
+            with torch.no_grad():
+                eager = DDIMSampler(net, use_cuda_graph=False)
+                ops.record_start()
+                eager.sample(steps=2, shape=[BS, 4, LAT, LAT], x_info={"type": "image", "xt": xT_d},
+                             c_info={"type": "text", "conditioning": c_d, "unconditional_conditioning": u_d,
+                                     "unconditional_guidance_scale": SCALE}, verbose=False, eta=0.)
+                recs = ops.record_stop()
+                torch.cuda.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    ops.replay(recs)
+                gr.replay()
+                torch.cuda.synchronize()
+                best = None
+                for _ in range(3):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    gr.replay()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    t = e0.elapsed_time(e1)
+                    best = t if best is None else min(best, t)
+            g_fl, g_n = sum(r[3] for r in recs), len(recs)
+            eager_ms = roof["avg_launch_ms"] * roof["launches"]
+            if g_n == roof["launches"] and best and 0.2 * eager_ms < best <= 1.05 * eager_ms:
+                g_tflops = g_fl / best / 1e9
+                roof["achieved_eager_events"] = roof["achieved"]
+                roof["frac_eager_events"] = roof["frac"]
+                roof["avg_launch_ms_eager_events"] = roof["avg_launch_ms"]
+                roof["achieved"] = round(g_tflops, 1)
+                roof["frac"] = round(g_tflops / peaks["tflops_sustained"], 4)
+                roof["avg_launch_ms"] = round(best / g_n, 4)
+                roof["how"] = ("the %d igemm launches of two eager DDIM steps re-issued back to back inside one CUDA graph, CUDA events "
+                               "around the replay on the launching stream (best of 3); '*_eager_events' = per-launch events in the eager "
+                               "step, which include the host launch latency" % g_n)
+            else:
+                roof["graph_replay"] = "discarded (launches %s vs %s, %.3f ms vs eager %.3f ms)" % (g_n, roof["launches"], best or -1.0, eager_ms)
+            del recs, gr
+        except BaseException as ex:  # noqa: the bench line must still be printed
+            roof["graph_replay"] = "failed: %s" % (str(ex)[:200],)
     line = {
         "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
@@ -340,6 +385,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph-roofline", action="store_true", help="keep the per-launch eager event timing of the roofline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

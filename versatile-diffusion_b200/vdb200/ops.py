@@ -95,6 +95,31 @@ def profile_stop():
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# optional recording of the tensor-core GEMM / conv launches (bench.py: replay of exactly these launches inside a CUDA
+# graph, so the roofline leg can time the kernel without the host launch path).  Each record keeps its tensors alive.
+# ------------------------------------------------------------------------------------------------
+_RECORD = None
+
+
+def record_start():
+    global _RECORD
+    _RECORD = []
+
+
+def record_stop():
+    """-> [(C function, arguments without the stream, tensors kept alive, algorithmic FLOPs)]"""
+    global _RECORD
+    rec, _RECORD = _RECORD, None
+    return rec or []
+
+
+def replay(records):
+    """Re-issue recorded launches on the current stream (capturable)."""
+    for fn, cargs, _keep, _flops in records:
+        check(fn(*cargs, _stream()), "replay")
+
+
 _gn_scratch_buf = {}
 
 
@@ -178,12 +203,15 @@ def gemm(a, w, bias=None, resid=None, out=None, act=ACT_NONE, a2=None, out_dtype
     ws, ws_bytes = None, 0
     if ksplit != 1 and M <= 8192:   # split-K only ever triggers for small MN grids
         ws, ws_bytes = workspace(a.device), WORKSPACE_BYTES
+    cargs = (_ptr(a), M, K, a.stride(0), _ptr(a2), K2, a2.stride(0) if a2 is not None else 0,
+             _ptr(w), N, w.stride(0), _ptr(bias), int(bias_bstride), int(rows_per_batch),
+             _ptr(resid), resid.stride(0) if resid is not None else 0, _ptr(out), out.stride(0),
+             1 if out_dtype == torch.float32 else 0, int(act), float(alpha), int(bn), int(ksplit),
+             _ptr(ws), ws_bytes)
     with _Span("gemm", 2.0 * M * N * (K + K2), 2.0 * (M * (K + K2) + N * (K + K2) + M * n_out)):
-        check(lib.vdb_gemm_bf16(_ptr(a), M, K, a.stride(0), _ptr(a2), K2, a2.stride(0) if a2 is not None else 0,
-                                _ptr(w), N, w.stride(0), _ptr(bias), int(bias_bstride), int(rows_per_batch),
-                                _ptr(resid), resid.stride(0) if resid is not None else 0, _ptr(out), out.stride(0),
-                                1 if out_dtype == torch.float32 else 0, int(act), float(alpha), int(bn), int(ksplit),
-                                _ptr(ws), ws_bytes, _stream()), "gemm_bf16")
+        check(lib.vdb_gemm_bf16(*cargs, _stream()), "gemm_bf16")
+    if _RECORD is not None:
+        _RECORD.append((lib.vdb_gemm_bf16, cargs, (a, a2, w, bias, resid, out, ws), 2.0 * M * N * (K + K2)))
     return out
 
 
@@ -205,12 +233,14 @@ def conv3x3(x, w, bias=None, resid=None, out=None, mode=0, skip1=None, skip2=Non
     if ksplit != 1 and M <= 8192:
         ws, ws_bytes = workspace(x.device), WORKSPACE_BYTES
     ktot = 9 * Cc + cs1 + cs2
+    cargs = (_ptr(x), B, H, W, Cc, int(mode), _ptr(w), N, w.stride(0), _ptr(skip1), cs1,
+             _ptr(skip2), cs2, _ptr(bias), int(bias_bstride), _ptr(resid),
+             resid.shape[-1] if resid is not None else 0, _ptr(out), out.shape[-1],
+             1 if out_dtype == torch.float32 else 0, int(act), int(bn), int(ksplit), _ptr(ws), ws_bytes)
     with _Span("conv3x3", 2.0 * M * N * ktot, 2.0 * (B * H * W * Cc + M * (cs1 + cs2) + N * ktot + M * N)):
-        check(lib.vdb_conv3x3_bf16(_ptr(x), B, H, W, Cc, int(mode), _ptr(w), N, w.stride(0), _ptr(skip1), cs1,
-                                   _ptr(skip2), cs2, _ptr(bias), int(bias_bstride), _ptr(resid),
-                                   resid.shape[-1] if resid is not None else 0, _ptr(out), out.shape[-1],
-                                   1 if out_dtype == torch.float32 else 0, int(act), int(bn), int(ksplit), _ptr(ws),
-                                   ws_bytes, _stream()), "conv3x3_bf16")
+        check(lib.vdb_conv3x3_bf16(*cargs, _stream()), "conv3x3_bf16")
+    if _RECORD is not None:
+        _RECORD.append((lib.vdb_conv3x3_bf16, cargs, (x, w, skip1, skip2, bias, resid, out, ws), 2.0 * M * N * ktot))
     return out
 
 
