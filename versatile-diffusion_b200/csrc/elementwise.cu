@@ -273,6 +273,16 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
 }
 
 // ---------------------------------------------------------------------------------------------
+// Debug build only (-DVDB_TIMELINE, tools/gn_timeline.py): globaltimer stamps of thread 0 of CTA (0,0) of the single-launch
+// GroupNorm: 0 start, 1 statistics loads + accumulation done, 2 partial published, 3 every CTA of the image arrived,
+// 4 statistics folded, 5 scale / shift table ready, 6 normalised + stored.
+__device__ unsigned long long* g_gn_timeline_dev = nullptr;
+#ifdef VDB_TIMELINE
+#define VDB_GTL(slot) do { if (g_gn_timeline_dev && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_gn_timeline_dev[slot] = gtime(); } while (0)
+#else
+#define VDB_GTL(slot) do { } while (0)
+#endif
+
 // Single-launch GroupNorm: statistics + apply in ONE kernel.  grid (nsplit, B) with nsplit*B <= the number of CTAs that
 // are resident at once (occupancy query on the host), so that every CTA of the grid is resident; each CTA reduces its
 // pixel range (deterministic, as gn_stats_kernel), publishes its partial, waits on a per-image arrival counter for
@@ -302,6 +312,7 @@ __global__ void __launch_bounds__(kGnThreads, 2) gn_fused_kernel(const __nv_bflo
   const int b = blockIdx.y, split = blockIdx.x, nsplit = gridDim.x, B = gridDim.y;
   pdl_launch_dependents();
   pdl_wait();
+  VDB_GTL(0);
   int* arrive = reinterpret_cast<int*>(scratch);
   int* depart = arrive + kGnMaxBatch;
   float* partial = scratch + 2 * kGnMaxBatch + static_cast<size_t>(B) * 2 * groups;
@@ -356,6 +367,7 @@ __global__ void __launch_bounds__(kGnThreads, 2) gn_fused_kernel(const __nv_bflo
     for (int i = 0; i < 8; ++i) { dst[i] = s[i]; dst[8 + i] = q[i]; }
   }
   __syncthreads();
+  VDB_GTL(1);
   for (int c = threadIdx.x; c < C; c += kGnThreads) {
     float s = 0.f, q = 0.f;
     for (int l = 0; l < lanes; ++l) {
@@ -386,6 +398,7 @@ __global__ void __launch_bounds__(kGnThreads, 2) gn_fused_kernel(const __nv_bflo
   // ---- publish, then wait for the other CTAs of this image (all CTAs of the grid are resident by construction) ----
   __threadfence();
   __syncthreads();
+  VDB_GTL(2);
   if (threadIdx.x == 0) {
     atomicAdd(&arrive[b], 1);
     int seen;
@@ -396,6 +409,7 @@ __global__ void __launch_bounds__(kGnThreads, 2) gn_fused_kernel(const __nv_bflo
     __threadfence();
   }
   __syncthreads();
+  VDB_GTL(3);
   // fold the image's nsplit partial rows (64 floats each: sum | sumsq per group) with the whole CTA: 8 row-lanes x 64
   // columns of coalesced L2 loads, then a fixed-order sum over the lanes -- every CTA of the image computes
   // bit-identical statistics.  (One thread per group walking all rows was ~4 us of serialised L2 latency.)
@@ -420,6 +434,7 @@ __global__ void __launch_bounds__(kGnThreads, 2) gn_fused_kernel(const __nv_bflo
     grstd[threadIdx.x] = rsqrtf(var + eps);
   }
   __syncthreads();
+  VDB_GTL(4);
   if (threadIdx.x == 0) {   // last CTA of the image to have read the partials re-arms both counters for the next launch
     if (atomicAdd(&depart[b], 1) == nsplit - 1) { arrive[b] = 0; depart[b] = 0; }
   }
@@ -436,6 +451,7 @@ __global__ void __launch_bounds__(kGnThreads, 2) gn_fused_kernel(const __nv_bflo
     }
   }
   __syncthreads();
+  VDB_GTL(5);
   // ---- phase 2: normalise this CTA's pixels ----
   if (active) {
     __nv_bfloat16* dstb = y + static_cast<long long>(b) * HW * C + v * 8;
@@ -471,6 +487,7 @@ __global__ void __launch_bounds__(kGnThreads, 2) gn_fused_kernel(const __nv_bflo
       }
     }
   }
+  VDB_GTL(6);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1096,6 +1113,12 @@ int vdb_add_int(int* p, int delta, void* stream) {
   VDB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return VDB_OK;
+}
+
+// debug aid (stamps exist only in a -DVDB_TIMELINE build): 8 x u64 device buffer receiving the single-launch GroupNorm's phases
+void vdb_debug_gn_timeline(void* buf) {
+  unsigned long long* p = reinterpret_cast<unsigned long long*>(buf);
+  cudaMemcpyToSymbol(vdb::g_gn_timeline_dev, &p, sizeof(p));
 }
 
 // scratch: ZERO-INITIALISED device buffer of vdb_groupnorm_scratch_floats(B, HW) floats (reusable across calls on
