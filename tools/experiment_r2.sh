@@ -23,6 +23,13 @@ if [ "$PP3" = "0" ]; then
     -f -o $O/att_pp3_$TAG python tools/microbench.py attention $O/mb_ncu_pp3.json
   VDB_ATT_PP=3 VDB_NFAST=$([ "$NF" = "0" ] && echo 1 || echo 0) VDB_GN_CLUSTER=$([ "$GC" = "0" ] && echo 1 || echo 0) T=240 run bench_all python bench.py --no-cpu-baseline
 fi
+if [ -f tools/bin/libvdb200_tl.so ]; then   # built HERE beforehand with tools/build_timeline_lib.sh (nvcc is on the box too, but slower)
+  export VDB200_LIB=$PWD/tools/bin/libvdb200_tl.so
+  T=40 run tl_gn_4096_320 python tools/gn_timeline.py 4096 320
+  T=40 run tl_gn_1024_640 python tools/gn_timeline.py 1024 640
+  T=40 run tl_gn_64_1280 python tools/gn_timeline.py 64 1280
+  unset VDB200_LIB
+fi
 grep -E "^===|passed|failed|\"value\"" $O/exp_$TAG.log | cut -c1-260
 python - "$TAG" <<'PY'
 import json, glob, sys
