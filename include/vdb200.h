@@ -69,6 +69,10 @@ int vdb_gemm_bf16(const void* A, long long M, long long K, long long lda, const 
 /* ---- tcgen05 implicit-GEMM 3x3 conv on NHWC — ResBlock convs openaimodel.py:203,229; Downsample
  *      :150-152; Upsample.conv :105; VAE autokl_modules.py:48-76,93-111 ---------------------------
  * mode 0: stride 1 pad 1; mode 1: stride 2 pad 1; mode 2: stride 2 with pad (0,1,0,1) (VAE).
+ * mode 3 + 2*py + px: parity (py,px) of "nearest 2x upsample then 3x3 conv" (Upsample.forward, openaimodel.py:107-117;
+ *      autokl_modules.py:54-58) evaluated on the SOURCE image with the 9 taps folded into 2x2: X = source [B,H,W,C],
+ *      out = [B,H,W,N] (that parity sub-lattice), Wt = [N, 4*C] (ty,tx,c) pre-summed on the host; no skip inputs.
+ *      vdb_interleave2x2_nhwc assembles the four parities into [B,2H,2W,N].
  * Wt [N, 9*C + Cs1 + Cs2], K order (ky,kx,c) then the 1x1 skip_connection columns whose inputs
  * skip1/skip2 (raw NHWC at output resolution; the two halves of torch.cat([h, hs.pop()]),
  * vd.py:372) are accumulated into the same TMEM tile (ResBlock.skip_connection, openaimodel.py:240).
@@ -109,6 +113,9 @@ int vdb_layernorm(const void* x, long long rows, int C, const float* gamma, cons
 
 /* ---- nearest 2x upsample NHWC — Upsample.forward openaimodel.py:114, autokl_modules.py:54 -------- */
 int vdb_upsample2x_nhwc(const void* x, int B, int H, int W, int C, void* y, void* stream);
+
+/* [4 parities (py,px)][B,H,W,C] bf16 -> [B,2H,2W,C]: out[b,2y+py,2x+px,:] = src[py*2+px][b,y,x,:] (see conv mode 3..6). */
+int vdb_interleave2x2_nhwc(const void* src, int B, int H, int W, int C, void* y, void* stream);
 
 /* ---- im2col for tiny-Cin 3x3 convs (latent 4ch / RGB 3ch inputs): fp32 NHWC -> bf16 [B*H*W, Kpad]
  *      (x*in_scale + in_shift applied first: AutoencoderKL.encode's x*2-1, autokl.py:34) ----------- */

@@ -10,6 +10,7 @@ PT="python -m pytest -q -p no:cacheprovider --timeout 100 tests/test_kernels_gpu
 VDB_ATT_PP=3 T=90 run t_pp3 $PT -k "attention"; PP3=$?
 VDB_ATT_PP=2 T=90 run t_pp2 $PT -k "attention"; PP2=$?
 VDB_NFAST=2 T=120 run t_nfast $PT -k "gemm or conv3x3"; NF=$?
+VDB_TEST_VARIANTS=1 T=400 run t_upfold python -m pytest -q -p no:cacheprovider tests/test_variants_gpu.py -k "folded"; UF=$?
 VDB_GN_CLUSTER=5 T=90 run t_gncl $PT -k "groupnorm"; GC=$?
 VDB_GN_CLUSTER=7 T=90 run t_gncl_nokeep $PT -k "groupnorm"
 run mb_default python tools/microbench.py attention,gemm,groupnorm $O/mb_default_$TAG.json
@@ -21,8 +22,15 @@ run mb_default python tools/microbench.py attention,gemm,groupnorm $O/mb_default
 if [ "$PP3" = "0" ]; then
   VDB_ATT_PP=3 T=120 run ncu_pp3 ncu --set full --clock-control none --import-source on -k regex:attention_pp_kernel --launch-skip 3 --launch-count 1 \
     -f -o $O/att_pp3_$TAG python tools/microbench.py attention $O/mb_ncu_pp3.json
-  VDB_ATT_PP=3 VDB_NFAST=$([ "$NF" = "0" ] && echo 1 || echo 0) VDB_GN_CLUSTER=$([ "$GC" = "0" ] && echo 1 || echo 0) T=240 run bench_all python bench.py --no-cpu-baseline
 fi
+# one bench with every variant that passed its parity leg
+FLAGS=""
+[ "$PP3" = "0" ] && FLAGS="$FLAGS VDB_ATT_PP=3"
+[ "$NF" = "0" ] && FLAGS="$FLAGS VDB_NFAST=1"
+[ "$GC" = "0" ] && FLAGS="$FLAGS VDB_GN_CLUSTER=1"
+[ "$UF" = "0" ] && FLAGS="$FLAGS VDB_UPFOLD=1"
+echo "=== bench flags:$FLAGS" >> $O/exp_$TAG.log
+T=240 run bench_all env $FLAGS python bench.py --no-cpu-baseline
 if [ -f tools/bin/libvdb200_tl.so ]; then   # built HERE beforehand with tools/build_timeline_lib.sh (nvcc is on the box too, but slower)
   export VDB200_LIB=$PWD/tools/bin/libvdb200_tl.so
   T=40 run tl_gn_4096_320 python tools/gn_timeline.py 4096 320

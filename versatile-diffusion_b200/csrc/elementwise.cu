@@ -731,6 +731,27 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   }
 }
 
+// [4 parities (py, px)][B, H, W, C] bf16 -> [B, 2H, 2W, C]: out[b, 2y+py, 2x+px, :] = src[py*2+px][b, y, x, :]
+// (assembles the four parity sub-lattices produced by the folded-upsample conv modes)
+__global__ void interleave2x2_kernel(const __nv_bfloat16* __restrict__ src, int B, int H, int W, int C,
+                                     __nv_bfloat16* __restrict__ y) {
+  const int V = C / 8;
+  const long long per = static_cast<long long>(B) * H * W * V;      // vectors per parity tensor
+  const long long total = 4 * per;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // iterate in OUTPUT order so that the stores are fully coalesced
+    const int v = static_cast<int>(i % V);
+    long long p = i / V;
+    const int xo = static_cast<int>(p % (2 * W)); p /= 2 * W;
+    const int yo = static_cast<int>(p % (2 * H));
+    const long long b = p / (2 * H);
+    const int par = (yo & 1) * 2 + (xo & 1);
+    const long long sidx = par * per + ((b * H + (yo >> 1)) * W + (xo >> 1)) * V + v;
+    reinterpret_cast<uint4*>(y)[i] = __ldg(reinterpret_cast<const uint4*>(src) + sidx);
+  }
+}
+
 // nearest-neighbour 2x upsample of NHWC bf16           (openaimodel.py:114, autokl_modules.py:54)
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C,
                                   __nv_bfloat16* __restrict__ y) {
@@ -1260,6 +1281,16 @@ int vdb_upsample2x_nhwc(const void* x, int B, int H, int W, int C, void* y, void
   VDB_PREFER_MAX_SMEM(upsample2x_kernel);
   upsample2x_kernel<<<ew_blocks(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, reinterpret_cast<__nv_bfloat16*>(y));
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_interleave2x2_nhwc(const void* src, int B, int H, int W, int C, void* y, void* stream) {
+  if (!src || !y || B <= 0 || H <= 0 || W <= 0 || (C % 8)) return set_error(VDB_ERR_INVALID, "interleave2x2: null argument or C %% 8 != 0");
+  const long long total = static_cast<long long>(B) * 4 * H * W * (C / 8);
+  interleave2x2_kernel<<<ew_blocks(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), B, H, W, C, reinterpret_cast<__nv_bfloat16*>(y));
   VDB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return VDB_OK;

@@ -881,6 +881,11 @@ int vdb_gemm_bf16(const void* A, long long M, long long K, long long lda, const 
 //   mode 0: stride 1, pad 1                       (out H x W)
 //   mode 1: stride 2, pad 1                       (out H/2 x W/2)      openaimodel.py:150-152
 //   mode 2: stride 2, pad (0,1,0,1) then pad 0    (out H/2 x W/2)      autokl_modules.py:72-76
+//   mode 3 + 2*py + px: one parity sub-lattice of "nearest 2x upsample, then 3x3 conv pad 1" (openaimodel.py:107-117,
+//           autokl_modules.py:54-58) computed on the SOURCE image: output pixel (2y+py, 2x+px) of the upsampled conv only
+//           sees the 2x2 source pixels (y + ty - 1 + py, x + tx - 1 + px), ty, tx in {0,1}, so the 9 taps fold into 4 with
+//           pre-summed weights (host: fold_upsample_conv3x3).  X = source [B,H,W,C], out = [B,H,W,N] (that parity, dense),
+//           Wt = [N, 4*C] with K ordered (ty, tx, c).  2.25x fewer FLOPs than upsampling first; no skip inputs.
 // Wt is [N, 9*C + Cs1 + Cs2] bf16 with K ordered (ky, kx, c) then the 1x1-skip columns.
 // skip1/skip2: optional raw NHWC tensors at OUTPUT resolution whose 1x1 conv is accumulated too.
 int vdb_conv3x3_bf16(const void* X, int B, int H, int Wd, int C, int mode, const void* Wt, int N, long long ldw,
@@ -892,23 +897,33 @@ int vdb_conv3x3_bf16(const void* X, int B, int H, int Wd, int C, int mode, const
   if ((C % kBlockK) || (ldw % 8)) return set_error(VDB_ERR_INVALID, "conv3x3: C must be a multiple of 64, ldw of 8");
   if ((skip1 && (Cs1 % kBlockK)) || (skip2 && (Cs2 % kBlockK)))
     return set_error(VDB_ERR_INVALID, "conv3x3: skip channels must be multiples of 64");
-  if (mode < 0 || mode > 2) return set_error(VDB_ERR_INVALID, "conv3x3: bad mode");
-  if (mode != 0 && ((H & 1) || (Wd & 1))) return set_error(VDB_ERR_UNSUPPORTED, "conv3x3: stride 2 needs even H, W");
+  if (mode < 0 || mode > 6) return set_error(VDB_ERR_INVALID, "conv3x3: bad mode");
+  const bool strided = (mode == 1 || mode == 2), folded = mode >= 3;
+  if (strided && ((H & 1) || (Wd & 1))) return set_error(VDB_ERR_UNSUPPORTED, "conv3x3: stride 2 needs even H, W");
+  if (folded && (skip1 || skip2)) return set_error(VDB_ERR_INVALID, "conv3x3: the folded-upsample modes take no skip inputs");
   IgemmParams p;
   memset(&p, 0, sizeof(p));
-  const int Ho = mode ? H / 2 : H, Wo = mode ? Wd / 2 : Wd;
+  const int Ho = strided ? H / 2 : H, Wo = strided ? Wd / 2 : Wd;
   set_tile_shape(p, Wo, Ho, B);
   const uint64_t eb = 2;
   const int nkb = C / kBlockK;
   int rc;
   int nmaps = 0;
-  if (mode == 0) {
+  int ntaps = 9;
+  if (mode == 0 || folded) {
     rc = make_tmap_4d(&p.tmA[0], X, C, Wd, H, B, C * eb, (uint64_t)Wd * C * eb, (uint64_t)H * Wd * C * eb, kBlockK,
                       p.TW, p.TH, p.TB);
     if (rc) return rc;
     nmaps = 1;
-    for (int t = 0; t < 9; ++t)
-      p.seg[t] = ASeg{0, static_cast<int16_t>(t % 3 - 1), static_cast<int16_t>(t / 3 - 1), static_cast<int16_t>(nkb), 0};
+    if (mode == 0) {
+      for (int t = 0; t < 9; ++t)
+        p.seg[t] = ASeg{0, static_cast<int16_t>(t % 3 - 1), static_cast<int16_t>(t / 3 - 1), static_cast<int16_t>(nkb), 0};
+    } else {
+      const int py = (mode - 3) >> 1, px = (mode - 3) & 1;
+      ntaps = 4;
+      for (int t = 0; t < 4; ++t)      // t = ty * 2 + tx; source pixel (y + ty - 1 + py, x + tx - 1 + px)
+        p.seg[t] = ASeg{0, static_cast<int16_t>((t & 1) - 1 + px), static_cast<int16_t>((t >> 1) - 1 + py), static_cast<int16_t>(nkb), 0};
+    }
   } else {
     // four parity sub-lattices of the input: X[b, 2*yo+py, 2*xo+px, c]
     for (int py = 0; py < 2; ++py)
@@ -933,8 +948,8 @@ int vdb_conv3x3_bf16(const void* X, int B, int H, int Wd, int C, int mode, const
                       static_cast<int16_t>(nkb), 0};
     }
   }
-  p.nseg = 9;
-  p.kb_total = 9 * nkb;
+  p.nseg = ntaps;
+  p.kb_total = ntaps * nkb;
   const void* sk[2] = {skip1, skip2};
   const int sc[2] = {Cs1, Cs2};
   for (int i = 0; i < 2; ++i) {

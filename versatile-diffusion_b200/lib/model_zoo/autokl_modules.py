@@ -7,7 +7,8 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .diffusion_utils import PackedMixin, PackedModule, bf16, f32, pack_conv1x1, pack_conv3x3, require_cuda
+from .diffusion_utils import (PackedMixin, PackedModule, bf16, f32, pack_conv1x1, pack_conv3x3, require_cuda,
+                              fold_upsample_conv3x3, upsample_fold_enabled)
 
 
 def _ops():
@@ -27,10 +28,18 @@ class Upsample(PackedModule):
             self.conv = torch.nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=1, padding=1)
 
     def _pack(self):
-        return {"w": pack_conv3x3(self.conv.weight), "b": f32(self.conv.bias)} if self.with_conv else {}
+        if not self.with_conv:
+            return {}
+        d = {"w": pack_conv3x3(self.conv.weight), "b": f32(self.conv.bias)}
+        if upsample_fold_enabled(1 << 30):           # (the folded copy is only built when the switch is on)
+            d["wf"] = fold_upsample_conv3x3(self.conv.weight)
+        return d
 
     def forward(self, x):
         ops = _ops()
+        if self.with_conv and upsample_fold_enabled(x.shape[0] * x.shape[1] * x.shape[2]):
+            p = self.packed()
+            return ops.upsample2x_conv3x3_folded(x, p["wf"], bias=p["b"])     # 2.25x fewer FLOPs, no upsampled temporary
         x = ops.upsample2x(x)
         if self.with_conv:
             p = self.packed()

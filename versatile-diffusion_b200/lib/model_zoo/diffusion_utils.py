@@ -165,5 +165,39 @@ def pack_conv3x3(w):
     return bf16(w.detach().permute(0, 2, 3, 1).reshape(w.shape[0], -1))
 
 
+def fold_upsample_conv3x3(w):
+    """Weights of "nearest-2x upsample, then 3x3 conv (pad 1)" folded onto the SOURCE image.
+
+    Output pixel (2y+py, 2x+px) reads upsampled rows 2y+py+ky-1, ky in {0,1,2}, i.e. source rows y + floor((py+ky-1)/2):
+    parity 0 -> {y-1 (ky 0), y (ky 1, 2)}, parity 1 -> {y (ky 0, 1), y+1 (ky 2)}; the same along x.  Tap (ty, tx) of
+    parity (py, px) therefore reads source pixel (y + ty - 1 + py, x + tx - 1 + px) with the SUM of the 3x3 weights that land
+    on it (summed in fp32, rounded to bf16 once).  The zero padding of the upsampled image coincides with the zero padding
+    of the source, so the result is exact up to that rounding.
+    w [Cout, Cin, 3, 3] -> bf16 [4 (py*2+px), Cout, 4*Cin] with K ordered (ty, tx, ci) — conv modes 3..6 of vdb_conv3x3_bf16."""
+    w = w.detach().float()
+    groups = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}     # parity -> (3x3 taps folded into tap 0, into tap 1)
+    out = []
+    for py in (0, 1):
+        for px in (0, 1):
+            taps = []
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    acc = 0
+                    for ky in groups[py][ty]:
+                        for kx in groups[px][tx]:
+                            acc = acc + w[:, :, ky, kx]
+                    taps.append(acc)                                # [Cout, Cin]
+            out.append(torch.stack(taps, dim=1).reshape(w.shape[0], -1))   # [Cout, (ty,tx,ci)]
+    return torch.stack(out).to(torch.bfloat16).contiguous()
+
+
+def upsample_fold_enabled(n_source_pixels):
+    """VDB_UPFOLD=1 (opt-in until measured on a GPU): fold when the source grid is large enough to fill the machine without
+    split-K (the four parity convs each see only B*H*W output pixels)."""
+    import os
+    mode = os.environ.get("VDB_UPFOLD", "0")
+    return mode == "2" or (mode == "1" and n_source_pixels >= 2048)     # "2": every Upsample (tests on small models)
+
+
 def pack_conv1x1(w):
     return bf16(w.detach().reshape(w.shape[0], -1))

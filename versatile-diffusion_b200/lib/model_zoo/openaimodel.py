@@ -22,7 +22,8 @@ import torch.nn as nn
 from lib.model_zoo.common.get_model import register
 from .attention import SpatialTransformer
 from .diffusion_utils import (PackedMixin, PackedModule, bf16, f32, conv_nd, linear, normalization, pack_conv1x1, pack_conv3x3,
-                              require_cuda, timestep_embedding, zero_module)  # noqa: F401
+                              require_cuda, timestep_embedding, zero_module, fold_upsample_conv3x3,
+                              upsample_fold_enabled)  # noqa: F401
 
 
 def _ops():
@@ -65,11 +66,19 @@ class Upsample(PackedModule):
             self.conv = conv_nd(dims, self.channels, self.out_channels, 3, padding=padding)
 
     def _pack(self):
-        return {"w": pack_conv3x3(self.conv.weight), "b": f32(self.conv.bias)} if self.use_conv else {}
+        if not self.use_conv:
+            return {}
+        d = {"w": pack_conv3x3(self.conv.weight), "b": f32(self.conv.bias)}
+        if upsample_fold_enabled(1 << 30):           # (the folded copy is only built when the switch is on)
+            d["wf"] = fold_upsample_conv3x3(self.conv.weight)
+        return d
 
     def forward(self, x):
         ops = _ops()
         require_cuda(x, "Upsample")
+        if self.use_conv and upsample_fold_enabled(x.shape[0] * x.shape[1] * x.shape[2]):
+            p = self.packed()
+            return ops.upsample2x_conv3x3_folded(x, p["wf"], bias=p["b"])     # 2.25x fewer FLOPs, no upsampled temporary
         x = ops.upsample2x(x)
         if self.use_conv:
             p = self.packed()

@@ -39,6 +39,7 @@ SIGNATURES = {
     "vdb_groupnorm_nhwc": (i, [p, i, p, i, i, i, i, p, p, f, i, p, p, p]),
     "vdb_layernorm": (i, [p, ll, i, p, p, f, p, p]),
     "vdb_upsample2x_nhwc": (i, [p, i, i, i, i, p, p]),
+    "vdb_interleave2x2_nhwc": (i, [p, i, i, i, i, p, p]),
     "vdb_im2col3x3_small": (i, [p, i, i, i, i, i, f, f, p, p]),
     "vdb_permute_f32": (i, [p, i, i, ll, i, f, f, i, p, p]),
     "vdb_gaussian_sample": (i, [p, p, i, ll, f, p, p]),

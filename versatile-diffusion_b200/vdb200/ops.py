@@ -222,17 +222,18 @@ def conv3x3(x, w, bias=None, resid=None, out=None, mode=0, skip1=None, skip2=Non
     _need(resid, BF16, "resid"); _need(skip1, BF16, "skip1"); _need(skip2, BF16, "skip2")
     B, H, W, Cc = x.shape
     N = w.shape[0]
-    Ho, Wo = (H // 2, W // 2) if mode else (H, W)
+    Ho, Wo = (H // 2, W // 2) if mode in (1, 2) else (H, W)
     cs1 = skip1.shape[-1] if skip1 is not None else 0
     cs2 = skip2.shape[-1] if skip2 is not None else 0
-    assert w.shape[1] == 9 * Cc + cs1 + cs2, (w.shape, Cc, cs1, cs2)
+    ntaps = 4 if mode >= 3 else 9          # modes 3..6: folded nearest-2x upsample (one parity, 2x2 taps on the source)
+    assert w.shape[1] == ntaps * Cc + cs1 + cs2, (w.shape, Cc, cs1, cs2, mode)
     if out is None:
         out = torch.empty((B, Ho, Wo, N), dtype=out_dtype, device=x.device)
     M = B * Ho * Wo
     ws, ws_bytes = None, 0
     if ksplit != 1 and M <= 8192:
         ws, ws_bytes = workspace(x.device), WORKSPACE_BYTES
-    ktot = 9 * Cc + cs1 + cs2
+    ktot = ntaps * Cc + cs1 + cs2
     cargs = (_ptr(x), B, H, W, Cc, int(mode), _ptr(w), N, w.stride(0), _ptr(skip1), cs1,
              _ptr(skip2), cs2, _ptr(bias), int(bias_bstride), _ptr(resid),
              resid.shape[-1] if resid is not None else 0, _ptr(out), out.shape[-1],
@@ -300,6 +301,28 @@ def upsample2x(x, out=None):
         out = torch.empty((B, 2 * H, 2 * W, C), dtype=BF16, device=x.device)
     check(lib.vdb_upsample2x_nhwc(_ptr(x), B, H, W, C, _ptr(out), _stream()), "upsample2x")
     return out
+
+
+def interleave2x2(src, out=None):
+    """src bf16 [4, B, H, W, C] (parity py*2+px major) -> [B, 2H, 2W, C]."""
+    _need(src, BF16, "src")
+    _, B, H, W, C = src.shape
+    if out is None:
+        out = torch.empty((B, 2 * H, 2 * W, C), dtype=BF16, device=src.device)
+    check(lib.vdb_interleave2x2_nhwc(_ptr(src), B, H, W, C, _ptr(out), _stream()), "interleave2x2")
+    return out
+
+
+def upsample2x_conv3x3_folded(x, wf, bias=None):
+    """nearest-2x upsample + 3x3 conv (pad 1) without materialising the upsampled image: four 2x2-tap convs on the source
+    (one per output parity, weights folded by diffusion_utils.fold_upsample_conv3x3) + one interleave pass.
+    x bf16 [B,H,W,C]; wf bf16 [4, N, 4*C]; -> [B,2H,2W,N]."""
+    B, H, W, _ = x.shape
+    N = wf.shape[1]
+    parts = torch.empty((4, B, H, W, N), dtype=BF16, device=x.device)
+    for par in range(4):
+        conv3x3(x, wf[par], bias=bias, out=parts[par], mode=3 + par, ksplit=1)
+    return interleave2x2(parts)
 
 
 def im2col3x3_small(x, kpad=64, in_scale=1.0, in_shift=0.0, out=None):
