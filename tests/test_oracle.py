@@ -135,6 +135,24 @@ with torch.no_grad():
     xb = O.ddim_sample(sd, None, [cc], [uu], 8, 7.5, c_types=('image',), model_channels=64, x0=x0, x0_forward_timesteps=5,
                        x0_noise=nz)
 assert (xa - xb).abs().max() <= 5e-4 * xa.abs().max(), (xa - xb).abs().max()
+# dual-context sampler (BASELINE config 4's entry point, ddim.py:173-298): text 0.7 + image 0.3, x_T injected through randn
+ct, ut = torch.randn(1, 20, 768, generator=g) * 0.5, torch.randn(1, 20, 768, generator=g) * 0.5
+ci, ui = torch.randn(1, 33, 768, generator=g) * 0.5, torch.zeros(1, 33, 768)
+xT = torch.randn(1, 4, 16, 16, generator=g)
+orig = torch.randn
+torch.randn = lambda *a, **k: xT.clone() if (len(a) > 0 and list(a[0]) == list(xT.shape)) else orig(*a, **k)
+try:
+    with torch.no_grad():
+        xm, _ = S.sample_multicontext(steps=4, shape=[1, 4, 16, 16], x_info={'type': 'image'},
+                                      c_info_list=[{'type': 'text', 'conditioning': ct, 'unconditional_conditioning': ut,
+                                                    'unconditional_guidance_scale': 7.5, 'ratio': 0.7},
+                                                   {'type': 'image', 'conditioning': ci, 'unconditional_conditioning': ui,
+                                                    'unconditional_guidance_scale': 7.5, 'ratio': 0.3}], verbose=False, eta=0.)
+finally:
+    torch.randn = orig
+with torch.no_grad():
+    xo = O.ddim_sample(sd, xT, [ct, ci], [ut, ui], 4, 7.5, c_types=('text', 'image'), ratios=[0.7, 0.3], model_channels=64)
+assert (xm - xo).abs().max() <= 5e-4 * xm.abs().max(), (xm - xo).abs().max()
 print('LIVE-OK')
 """ % ROOT
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
