@@ -20,6 +20,7 @@ VARIANTS = [
     ({"VDB_GN_FUSED": "0"}, "groupnorm"),          # statistics + apply kernels                            (validated, round 1)
     ({"VDB_GN_CLUSTER": "5"}, "groupnorm"),        # thread-block-cluster GroupNorm, pixels kept in smem    (NOT yet run on a GPU)
     ({"VDB_GN_CLUSTER": "7"}, "groupnorm"),        # cluster GroupNorm, two-read path                       (NOT yet run on a GPU)
+    ({"VDB_LN_V2": "1"}, "layernorm"),             # persistent LayerNorm with software prefetch          (NOT yet run on a GPU)
     ({"VDB_PAIR": "1"}, "gemm or conv3x3"),        # CTA pairs (cta_group::2)                              (validated, round 1)
     ({"VDB_NFAST": "2"}, "gemm or conv3x3"),       # N-fast tile order wherever it is legal                (NOT yet run on a GPU)
     ({"VDB_IGEMM_SPEC": "0"}, "gemm or conv3x3"),  # generic epilogue only

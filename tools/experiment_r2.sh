@@ -14,7 +14,9 @@ VDB_NFAST=2 T=120 run t_nfast $PT -k "gemm or conv3x3"; NF=$?
 VDB_TEST_VARIANTS=1 T=400 run t_upfold python -m pytest -q -p no:cacheprovider tests/test_variants_gpu.py -k "folded"; UF=$?
 VDB_GN_CLUSTER=5 T=90 run t_gncl $PT -k "groupnorm"; GC=$?
 VDB_GN_CLUSTER=7 T=90 run t_gncl_nokeep $PT -k "groupnorm"
-run mb_default python tools/microbench.py attention,gemm,groupnorm $O/mb_default_$TAG.json
+VDB_LN_V2=1 T=90 run t_lnv2 $PT -k "layernorm"; LN=$?
+run mb_default python tools/microbench.py attention,gemm,groupnorm,layernorm $O/mb_default_$TAG.json
+[ "$LN" = "0" ] && VDB_LN_V2=1 run mb_lnv2 python tools/microbench.py layernorm $O/mb_lnv2_$TAG.json
 [ "$GC" = "0" ] && VDB_GN_CLUSTER=1 run mb_gncl python tools/microbench.py groupnorm $O/mb_gncl_$TAG.json
 [ "$GC" = "0" ] && VDB_GN_CLUSTER=3 run mb_gncl_nokeep python tools/microbench.py groupnorm $O/mb_gncl_nokeep_$TAG.json
 [ "$PP3" = "0" ] && VDB_ATT_PP=3 run mb_pp3 python tools/microbench.py attention $O/mb_pp3_$TAG.json
@@ -30,6 +32,7 @@ FLAGS=""
 [ "$NF" = "0" ] && FLAGS="$FLAGS VDB_NFAST=1"
 [ "$GC" = "0" ] && FLAGS="$FLAGS VDB_GN_CLUSTER=1"
 [ "$UF" = "0" ] && FLAGS="$FLAGS VDB_UPFOLD=1"
+[ "$LN" = "0" ] && FLAGS="$FLAGS VDB_LN_V2=1"
 echo "=== bench flags:$FLAGS" >> $O/exp_$TAG.log
 T=240 run bench_all env $FLAGS python bench.py --no-cpu-baseline
 if [ -f tools/bin/libvdb200_tl.so ]; then   # built HERE beforehand with tools/build_timeline_lib.sh (nvcc is on the box too, but slower)
@@ -44,5 +47,5 @@ python - "$TAG" <<'PY'
 import json, glob, sys
 for f in sorted(glob.glob("gpurun_out/mb_*_%s.json" % sys.argv[1])):
     for r in json.load(open(f))["results"]:
-        if r["name"].startswith(("attention N4096 M4096", "gemm 32768x320x1280", "groupnorm")): print(f, r["name"], r.get("graph_us"))
+        if r["name"].startswith(("attention N4096 M4096", "gemm 32768x320x1280", "groupnorm", "layernorm")): print(f, r["name"], r.get("graph_us"))
 PY

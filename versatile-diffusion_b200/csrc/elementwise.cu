@@ -731,6 +731,99 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   }
 }
 
+// Persistent LayerNorm with software prefetch (opt-in VDB_LN_V2=1, unmeasured): the kernel above runs 3.5 waves of short-lived
+// CTAs on the 32768 x 320 layers (load everything, compute, store, exit: 2.3 TB/s in-graph); here grid = resident CTAs, every
+// warp walks its rows R at a time and requests the NEXT R rows before it normalises the current ones, so loads, math and
+// stores of different iterations overlap.  C <= 512 (two 16-byte vectors per lane).
+template <int R>
+__global__ void __launch_bounds__(256) layernorm_pf_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           float eps, __nv_bfloat16* __restrict__ y) {
+  constexpr int MAXV = 2;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int V = C / 8;
+  const long long stride = static_cast<long long>(nwarps) * R;
+  // this lane's gamma / beta (fixed columns) stay in registers for the whole walk
+  float gg[MAXV][8], bb[MAXV][8];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < V) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+      gg[i][0] = g0.x; gg[i][1] = g0.y; gg[i][2] = g0.z; gg[i][3] = g0.w; gg[i][4] = g1.x; gg[i][5] = g1.y; gg[i][6] = g1.z; gg[i][7] = g1.w;
+      bb[i][0] = b0.x; bb[i][1] = b0.y; bb[i][2] = b0.z; bb[i][3] = b0.w; bb[i][4] = b1.x; bb[i][5] = b1.y; bb[i][6] = b1.z; bb[i][7] = b1.w;
+    }
+  }
+  auto load_rows = [&](long long r0, uint4 (&raw)[R][MAXV]) {
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + i * 32;
+        if (v < V && r0 + j < rows) raw[j][i] = __ldg(reinterpret_cast<const uint4*>(x + (r0 + j) * C + v * 8));
+      }
+  };
+  uint4 cur[R][MAXV], nxt[R][MAXV];
+  long long r0 = static_cast<long long>(warp) * R;
+  if (r0 < rows) load_rows(r0, cur);
+  for (; r0 < rows; r0 += stride) {
+    if (r0 + stride < rows) load_rows(r0 + stride, nxt);      // in flight while the current rows are normalised
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      if (r0 + j >= rows) break;   // warp-uniform
+      float f[MAXV][8];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        if (lane + i * 32 < V) {
+          const uint32_t w[4] = {cur[j][i].x, cur[j][i].y, cur[j][i].z, cur[j][i].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 t = unpack_bf16x2(w[k]);
+            f[i][2 * k] = t.x; f[i][2 * k + 1] = t.y;
+            s += t.x + t.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s / C;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        if (lane + i * 32 < V) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { const float d = f[i][k] - mean; q += d * d; }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q / C + eps);
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + i * 32;
+        if (v < V) {
+          uint32_t o[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            o[k] = pack_bf16x2((f[i][2 * k] - mean) * rstd * gg[i][2 * k] + bb[i][2 * k],
+                               (f[i][2 * k + 1] - mean) * rstd * gg[i][2 * k + 1] + bb[i][2 * k + 1]);
+          *reinterpret_cast<uint4*>(y + (r0 + j) * C + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) cur[j][i] = nxt[j][i];
+  }
+}
+
 // [4 parities (py, px)][B, H, W, C] bf16 -> [B, 2H, 2W, C]: out[b, 2y+py, 2x+px, :] = src[py*2+px][b, y, x, :]
 // (assembles the four parity sub-lattices produced by the folded-upsample conv modes)
 __global__ void interleave2x2_kernel(const __nv_bfloat16* __restrict__ src, int B, int H, int W, int C,
@@ -1262,6 +1355,14 @@ int vdb_layernorm(const void* x, long long rows, int C, const float* gamma, cons
   const int blocks = static_cast<int>(std::min<long long>((rows + 8 * R - 1) / (8 * R), num_sms() * 8LL));
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+  static const bool ln_v2 = [] { const char* ev = getenv("VDB_LN_V2"); return ev && ev[0] == '1'; }();
+  if (ln_v2 && V <= 64 && rows >= 4096) {
+    static const int occ = [] { int n = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, layernorm_pf_kernel<2>, 256, 0); return std::max(n, 1); }();
+    const int grid = static_cast<int>(std::min<long long>((rows + 8 * 2 - 1) / (8 * 2), static_cast<long long>(occ) * num_sms()));
+    VDB_CUDA_CHECK(launch_pdl(layernorm_pf_kernel<2>, dim3(grid), dim3(threads), 0, st, xp, rows, C, gamma, beta, eps, yp));
+    count_launch();
+    return VDB_OK;
+  }
   VDB_PREFER_MAX_SMEM((layernorm_kernel<2, 4>));
   VDB_PREFER_MAX_SMEM((layernorm_kernel<5, 2>));
   VDB_PREFER_MAX_SMEM((layernorm_kernel<8, 1>));
