@@ -26,6 +26,8 @@ if [ "$PP3" = "0" ]; then
   VDB_ATT_PP=3 T=120 run ncu_pp3 ncu --set full --clock-control none --import-source on -k regex:attention_pp_kernel --launch-skip 3 --launch-count 1 \
     -f -o $O/att_pp3_$TAG python tools/microbench.py attention $O/mb_ncu_pp3.json
 fi
+T=180 run step_breakdown python tools/step_breakdown.py 10
+cp $O/exp_$TAG.log $O/exp_$TAG.partial.log 2>/dev/null
 # one bench with every variant that passed its parity leg
 FLAGS=""
 [ "$PP3" = "0" ] && FLAGS="$FLAGS VDB_ATT_PP=3"
