@@ -114,6 +114,17 @@ int vdb_layernorm(const void* x, long long rows, int C, const float* gamma, cons
 /* ---- nearest 2x upsample NHWC — Upsample.forward openaimodel.py:114, autokl_modules.py:54 -------- */
 int vdb_upsample2x_nhwc(const void* x, int B, int H, int W, int C, void* y, void* stream);
 
+/* ---- CLIP image preprocessing on the device — replaces the host PIL round trip of CLIPImageContextEncoder._encode,
+ *      clip.py:88-94 (ToPILImage + CLIPProcessor: bicubic resize of the shortest side to 224, centre crop, rescale, normalise).
+ *      Bit-exact with torchvision.ToPILImage + Pillow's 8-bit two-pass bicubic resampling; the int32 coefficient tables
+ *      (bounds [out,2] = first tap, tap count; kk [out,ksize], 22 fractional bits) come from the host.  mean3 / std3 are HOST arrays. */
+int vdb_clip_to_u8_hwc(const float* x, int n, int H, int W, void* y /* u8 [n,H,W,3] */, void* stream);
+int vdb_resample_h_u8(const void* x /* u8 [n,H,Win,3] */, int n, int H, int Win, int Wout, const int* bounds, const int* kk,
+                      int ksize, void* y /* u8 [n,H,Wout,3] */, void* stream);
+int vdb_resample_v_crop_norm(const void* x /* u8 [n,Hin,W,3] */, int n, int Hin, int W, const int* bounds, const int* kk,
+                             int ksize /* 0: no vertical resize */, int top, int left, int S, const float* mean3,
+                             const float* std3, float* y /* fp32 [n,3,S,S] */, void* stream);
+
 /* [4 parities (py,px)][B,H,W,C] bf16 -> [B,2H,2W,C]: out[b,2y+py,2x+px,:] = src[py*2+px][b,y,x,:] (see conv mode 3..6). */
 int vdb_interleave2x2_nhwc(const void* src, int B, int H, int W, int C, void* y, void* stream);
 

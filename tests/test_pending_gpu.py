@@ -66,3 +66,15 @@ def test_p_sample_ddim_single_step_api_vs_oracle(mini):
         rx, rp, _ = O.p_sample_ddim(sd, gi["xT"], [gi["c"]], [gi["u"]], t.cpu(), index, sched, 7.5, model_channels=64)
     _cmp(x_prev, rx, 0.999, 3e-2, "p_sample_ddim x_prev")
     _cmp(pred_x0, rp, 0.997, 0.1, "p_sample_ddim pred_x0")
+
+
+def test_clip_preprocess_on_device_is_bit_exact_with_the_pil_host_path():
+    """ToPILImage + Pillow bicubic + crop + normalise on the GPU (integer arithmetic: exact)."""
+    from lib.model_zoo.clip import CLIPImageContextEncoder as E
+    g = torch.Generator().manual_seed(9)
+    for shape in ((2, 3, 256, 256), (1, 3, 300, 420), (1, 3, 512, 384), (1, 3, 224, 224), (1, 3, 100, 90)):
+        t = torch.rand(*shape, generator=g)
+        ref = E.preprocess(t)
+        out = E.preprocess_device(t.to(DEV)).cpu()
+        assert out.shape == ref.shape
+        assert (out - ref).abs().max().item() <= 1e-6, shape

@@ -824,6 +824,82 @@ __global__ void __launch_bounds__(256) layernorm_pf_kernel(const __nv_bfloat16* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// CLIP image preprocessing on the device (opt-in, not yet run on a GPU): the reference converts the
+// tensor to PIL on the HOST and lets CLIPProcessor resize it there (clip.py:88-94).  These three kernels reproduce that
+// arithmetic exactly — torchvision's ToPILImage (x * 255 truncated to uint8) and Pillow's 8-bit two-pass bicubic resampling
+// (int32 fixed-point coefficients with 22 fractional bits, horizontal pass rounded to uint8 before the vertical one), then
+// centre crop, / 255 and normalisation — so the image never leaves the GPU.  The coefficient tables are built on the
+// host exactly as Pillow's precompute_coeffs / normalize_coeffs_8bpc do (lib/model_zoo/clip.py: pil_bicubic_coeffs).
+// ---------------------------------------------------------------------------------------------
+__global__ void clip_to_u8_hwc_kernel(const float* __restrict__ x, int n, int H, int W, uint8_t* __restrict__ y) {
+  const long long total = static_cast<long long>(n) * H * W * 3;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % 3);
+    long long p = i / 3;
+    const int w = static_cast<int>(p % W); p /= W;
+    const int h = static_cast<int>(p % H);
+    const long long b = p / H;
+    const float v = fminf(fmaxf(__ldg(x + ((b * 3 + c) * H + h) * W + w), 0.f), 1.f);
+    y[i] = static_cast<uint8_t>(__fmul_rn(v, 255.f));      // .byte(): truncation toward zero
+  }
+}
+
+VDB_DEVINL uint8_t pil_clip8(int acc) {
+  const int v = acc >> 22;
+  return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// horizontal pass: x [n, H, Win, 3] u8 -> y [n, H, Wout, 3] u8
+__global__ void resample_h_u8_kernel(const uint8_t* __restrict__ x, int n, int H, int Win, int Wout,
+                                     const int* __restrict__ bounds, const int* __restrict__ kk, int ksize,
+                                     uint8_t* __restrict__ y) {
+  const long long total = static_cast<long long>(n) * H * Wout * 3;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % 3);
+    long long p = i / 3;
+    const int xx = static_cast<int>(p % Wout);
+    const long long row = p / Wout;                       // b * H + h
+    const int xmin = __ldg(bounds + 2 * xx), cnt = __ldg(bounds + 2 * xx + 1);
+    const uint8_t* src = x + (row * Win + xmin) * 3 + c;
+    const int* k = kk + static_cast<long long>(xx) * ksize;
+    int acc = 1 << 21;
+    for (int t = 0; t < cnt; ++t) acc += static_cast<int>(src[t * 3]) * __ldg(k + t);
+    y[i] = pil_clip8(acc);
+  }
+}
+
+// vertical pass (ksize == 0: no vertical resize) + centre crop + /255 + normalise: x [n, Hin, W, 3] u8 -> y [n, 3, S, S] fp32
+__global__ void resample_v_crop_norm_kernel(const uint8_t* __restrict__ x, int n, int Hin, int W,
+                                            const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, int top,
+                                            int left, int S, float m0, float m1, float m2, float s0, float s1, float s2,
+                                            float* __restrict__ y) {
+  const long long total = static_cast<long long>(n) * 3 * S * S;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(i % S);
+    long long p = i / S;
+    const int oy = static_cast<int>(p % S); p /= S;
+    const int c = static_cast<int>(p % 3);
+    const long long b = p / 3;
+    const int yy = oy + top, xs = ox + left;
+    uint8_t u;
+    if (ksize == 0) {
+      u = x[((b * Hin + yy) * W + xs) * 3 + c];
+    } else {
+      const int ymin = __ldg(bounds + 2 * yy), cnt = __ldg(bounds + 2 * yy + 1);
+      const int* k = kk + static_cast<long long>(yy) * ksize;
+      int acc = 1 << 21;
+      for (int t = 0; t < cnt; ++t) acc += static_cast<int>(x[((b * Hin + ymin + t) * W + xs) * 3 + c]) * __ldg(k + t);
+      u = pil_clip8(acc);
+    }
+    const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    y[i] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(u), 255.f), mean), sd);
+  }
+}
+
 // [4 parities (py, px)][B, H, W, C] bf16 -> [B, 2H, 2W, C]: out[b, 2y+py, 2x+px, :] = src[py*2+px][b, y, x, :]
 // (assembles the four parity sub-lattices produced by the folded-upsample conv modes)
 __global__ void interleave2x2_kernel(const __nv_bfloat16* __restrict__ src, int B, int H, int W, int C,
@@ -1382,6 +1458,39 @@ int vdb_upsample2x_nhwc(const void* x, int B, int H, int W, int C, void* y, void
   VDB_PREFER_MAX_SMEM(upsample2x_kernel);
   upsample2x_kernel<<<ew_blocks(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), B, H, W, C, reinterpret_cast<__nv_bfloat16*>(y));
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_clip_to_u8_hwc(const float* x, int n, int H, int W, void* y, void* stream) {
+  if (!x || !y || n <= 0 || H <= 0 || W <= 0) return set_error(VDB_ERR_INVALID, "clip_to_u8_hwc: bad argument");
+  clip_to_u8_hwc_kernel<<<ew_blocks(static_cast<long long>(n) * H * W * 3, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, n, H, W, reinterpret_cast<uint8_t*>(y));
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_resample_h_u8(const void* x, int n, int H, int Win, int Wout, const int* bounds, const int* kk, int ksize, void* y,
+                      void* stream) {
+  if (!x || !y || !bounds || !kk || n <= 0 || H <= 0 || Win <= 0 || Wout <= 0 || ksize <= 0)
+    return set_error(VDB_ERR_INVALID, "resample_h_u8: bad argument");
+  resample_h_u8_kernel<<<ew_blocks(static_cast<long long>(n) * H * Wout * 3, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint8_t*>(x), n, H, Win, Wout, bounds, kk, ksize, reinterpret_cast<uint8_t*>(y));
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_resample_v_crop_norm(const void* x, int n, int Hin, int W, const int* bounds, const int* kk, int ksize, int top,
+                             int left, int S, const float* mean3, const float* std3, float* y, void* stream) {
+  if (!x || !y || !mean3 || !std3 || n <= 0 || Hin <= 0 || W <= 0 || S <= 0 || top < 0 || left < 0 || left + S > W ||
+      (ksize > 0 && (!bounds || !kk)) || (ksize == 0 && top + S > Hin))
+    return set_error(VDB_ERR_INVALID, "resample_v_crop_norm: bad argument");
+  resample_v_crop_norm_kernel<<<ew_blocks(static_cast<long long>(n) * 3 * S * S, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint8_t*>(x), n, Hin, W, bounds, kk, ksize, top, left, S, mean3[0], mean3[1], mean3[2], std3[0],
+      std3[1], std3[2], y);
   VDB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return VDB_OK;

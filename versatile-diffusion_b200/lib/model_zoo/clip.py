@@ -215,6 +215,62 @@ class CLIPImageContextEncoder(AbstractEncoder):
             out.append(torch.from_numpy(a).permute(2, 0, 1))
         return torch.stack(out).contiguous()
 
+    @staticmethod
+    def pil_bicubic_coeffs(in_size, out_size):
+        """Pillow's precompute_coeffs + normalize_coeffs_8bpc for the BICUBIC filter (Resample.c): per output coordinate the
+        first tap, the tap count and the int32 weights with 22 fractional bits, computed in double precision in Pillow's
+        operation order.  -> (bounds int32 [out, 2], kk int32 [out, ksize])."""
+        import math
+        scale = filterscale = in_size / out_size
+        if filterscale < 1.0:
+            filterscale = 1.0
+        support = 2.0 * filterscale
+        ksize = int(math.ceil(support)) * 2 + 1
+        inv = 1.0 / filterscale
+        bounds = np.zeros((out_size, 2), dtype=np.int32)
+        kk = np.zeros((out_size, ksize), dtype=np.int32)
+        for xx in range(out_size):
+            center = (xx + 0.5) * scale
+            xmin = max(int(center - support + 0.5), 0)
+            cnt = min(int(center + support + 0.5), in_size) - xmin
+            ws, total = [], 0.0
+            for x in range(cnt):
+                t = abs((x + xmin - center + 0.5) * inv)
+                if t < 1.0:
+                    w = ((-0.5 + 2.0) * t - (-0.5 + 3.0)) * t * t + 1
+                elif t < 2.0:
+                    w = (((t - 5) * t + 8) * t - 4) * -0.5
+                else:
+                    w = 0.0
+                ws.append(w)
+                total += w
+            for x, w in enumerate(ws):
+                if total != 0.0:
+                    w = w / total
+                kk[xx, x] = int(-0.5 + w * (1 << 22)) if w < 0 else int(0.5 + w * (1 << 22))
+            bounds[xx] = (xmin, cnt)
+        return bounds, kk
+
+    _pre_tables = {}
+
+    @classmethod
+    def preprocess_device(cls, images, size=224):
+        """The preprocessing of `preprocess` without leaving the GPU (opt-in: VDB_CLIP_PRE_DEVICE=1 and a CUDA tensor input):
+        same integers as ToPILImage + Pillow (vdb200 kernels, coefficient tables cached per input size)."""
+        ops = _ops()
+        require_cuda(images, "CLIPImageContextEncoder.preprocess_device")
+        n, _, h, w = images.shape
+        key = (h, w, size, str(images.device))
+        tab = cls._pre_tables.get(key)
+        if tab is None:
+            nw, nh = (size, int(size * h / w)) if w <= h else (int(size * w / h), size)
+            dev = images.device
+            to = lambda pair: tuple(torch.from_numpy(a).to(dev).contiguous() for a in pair)
+            tab = {"nw": nw, "nh": nh, "h": to(cls.pil_bicubic_coeffs(w, nw)) if nw != w else None,
+                   "v": to(cls.pil_bicubic_coeffs(h, nh)) if nh != h else None}
+            cls._pre_tables[key] = tab
+        return ops.clip_preprocess_device(images.float().contiguous(), tab, size, IMAGE_MEAN, IMAGE_STD)
+
     @torch.no_grad()
     def encode_pixels(self, pixels, tok_scale=None):
         """pixels: fp32 [n,3,224,224] already preprocessed -> fp32 [n, 257, 768]. tok_scale: [n,257] (masked variant)."""
@@ -237,8 +293,14 @@ class CLIPImageContextEncoder(AbstractEncoder):
         z = ops.gemm(x, p["proj"])
         return ops.scale_by_row_norm(z.view(B, Lp, -1), L, idx=None, row_scale=ts)
 
+    def _preprocess_any(self, images):
+        import os
+        if os.environ.get("VDB_CLIP_PRE_DEVICE") == "1" and isinstance(images, torch.Tensor) and images.is_cuda:
+            return self.preprocess_device(images)
+        return self.preprocess(images)
+
     def _encode(self, images):
-        z = self.encode_pixels(self.preprocess(images))
+        z = self.encode_pixels(self._preprocess_any(images))
         return z.half() if self.fp16 else z
 
     @torch.no_grad()
@@ -255,7 +317,7 @@ class CLIPImageContextEncoder(AbstractEncoder):
         gscale = masks.mean(axis=[1, 2, 3], keepdim=True).flatten(2)
         vtoken = F.avg_pool2d(masks, patch, stride=patch).flatten(2).transpose(1, 2)          # conv with ones / P^2
         vtoken_mask = torch.cat([gscale, vtoken], dim=1).squeeze(-1)                            # [n, 257]
-        z = self.encode_pixels(self.preprocess(images), tok_scale=vtoken_mask)
+        z = self.encode_pixels(self._preprocess_any(images), tok_scale=vtoken_mask)
         return z.half() if self.fp16 else z
 
     def encode(self, images, masks=None):

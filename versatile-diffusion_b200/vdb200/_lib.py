@@ -40,6 +40,9 @@ SIGNATURES = {
     "vdb_layernorm": (i, [p, ll, i, p, p, f, p, p]),
     "vdb_upsample2x_nhwc": (i, [p, i, i, i, i, p, p]),
     "vdb_interleave2x2_nhwc": (i, [p, i, i, i, i, p, p]),
+    "vdb_clip_to_u8_hwc": (i, [p, i, i, i, p, p]),
+    "vdb_resample_h_u8": (i, [p, i, i, i, i, p, p, i, p, p]),
+    "vdb_resample_v_crop_norm": (i, [p, i, i, i, p, p, i, i, i, i, C.POINTER(f), C.POINTER(f), p, p]),
     "vdb_im2col3x3_small": (i, [p, i, i, i, i, i, f, f, p, p]),
     "vdb_permute_f32": (i, [p, i, i, ll, i, f, f, i, p, p]),
     "vdb_gaussian_sample": (i, [p, p, i, ll, f, p, p]),

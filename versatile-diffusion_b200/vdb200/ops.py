@@ -431,6 +431,31 @@ def softmax_rows(x, scale=1.0, out=None):
     return out
 
 
+def clip_preprocess_device(images, tables, size, mean, std):
+    """images fp32 CUDA [n,3,H,W] in [0,1] -> fp32 [n,3,size,size], bit-exact with ToPILImage + Pillow bicubic resize of the
+    shortest side + centre crop + rescale + normalise (reference clip.py:88-94 runs this on the host through PIL).
+    tables = {"nw","nh","h": (bounds, kk) or None, "v": (bounds, kk) or None} with int32 CUDA tensors (clip.pil_bicubic_coeffs)."""
+    import ctypes
+    _need(images, torch.float32, "images")
+    n, _, H, W = images.shape
+    nw, nh = tables["nw"], tables["nh"]
+    u8 = torch.empty((n, H, W, 3), dtype=torch.uint8, device=images.device)
+    check(lib.vdb_clip_to_u8_hwc(_ptr(images), n, H, W, _ptr(u8), _stream()), "clip_to_u8_hwc")
+    if tables["h"] is not None:
+        hb, hk = tables["h"]
+        mid = torch.empty((n, H, nw, 3), dtype=torch.uint8, device=images.device)
+        check(lib.vdb_resample_h_u8(_ptr(u8), n, H, W, nw, _ptr(hb), _ptr(hk), hk.shape[1], _ptr(mid), _stream()), "resample_h_u8")
+    else:
+        mid = u8
+    out = torch.empty((n, 3, size, size), dtype=torch.float32, device=images.device)
+    vb, vk = tables["v"] if tables["v"] is not None else (None, None)
+    m3, s3 = (ctypes.c_float * 3)(*mean), (ctypes.c_float * 3)(*std)
+    check(lib.vdb_resample_v_crop_norm(_ptr(mid), n, H, nw, _ptr(vb), _ptr(vk), 0 if vk is None else vk.shape[1],
+                                       (nh - size) // 2, (nw - size) // 2, size, m3, s3, _ptr(out), _stream()),
+          "resample_v_crop_norm")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ CLIP ends
 def clip_text_embed(tokens, tok_emb, pos_emb, Lp):
     _need(tokens, torch.int64, "tokens"); _need(tok_emb, torch.float32, "tok_emb"); _need(pos_emb, torch.float32, "pos_emb")
