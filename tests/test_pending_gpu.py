@@ -78,3 +78,12 @@ def test_clip_preprocess_on_device_is_bit_exact_with_the_pil_host_path():
         out = E.preprocess_device(t.to(DEV)).cpu()
         assert out.shape == ref.shape
         assert (out - ref).abs().max().item() <= 1e-6, shape
+
+
+def test_images_to_uint8_matches_topilimage(mini):
+    import torchvision.transforms as tvtrans
+    net, sd, gi, gold = mini
+    x = torch.rand(2, 3, 40, 56, generator=torch.Generator().manual_seed(1))
+    out = net.images_to_uint8(x.to(DEV)).cpu().numpy()
+    ref = np.stack([np.asarray(tvtrans.ToPILImage()(xi)) for xi in x])
+    assert np.array_equal(out, ref)

@@ -126,6 +126,13 @@ class VD_v2_0(nn.Module):
         return out.to(x_start.dtype)
 
     @torch.no_grad()
+    def images_to_uint8(self, x):
+        """Addition: what app.py:319 does on the host with tvtrans.ToPILImage() — decoded images
+        [n,3,H,W] in [0,1] -> uint8 [n,H,W,3] (x * 255 truncated), on the device: a quarter of the D2H bytes."""
+        require_cuda(x, "VD_v2_0.images_to_uint8")
+        return _ops().to_uint8_hwc(x.float().contiguous())
+
+    @torch.no_grad()
     def vae_encode(self, x, which, **kwargs):
         scale = self.latent_scale_factor.get(which, None) if self.latent_scale_factor is not None else None
         if kwargs.get('out_posterior', False) or scale is None:

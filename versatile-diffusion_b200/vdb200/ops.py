@@ -431,6 +431,16 @@ def softmax_rows(x, scale=1.0, out=None):
     return out
 
 
+def to_uint8_hwc(images):
+    """fp32 CUDA [n,3,H,W] in [0,1] -> uint8 [n,H,W,3] with torchvision.ToPILImage semantics (x * 255 truncated)."""
+    _need(images, torch.float32, "images")
+    n, ch, H, W = images.shape
+    assert ch == 3
+    out = torch.empty((n, H, W, 3), dtype=torch.uint8, device=images.device)
+    check(lib.vdb_clip_to_u8_hwc(_ptr(images), n, H, W, _ptr(out), _stream()), "clip_to_u8_hwc")
+    return out
+
+
 def clip_preprocess_device(images, tables, size, mean, std):
     """images fp32 CUDA [n,3,H,W] in [0,1] -> fp32 [n,3,size,size], bit-exact with ToPILImage + Pillow bicubic resize of the
     shortest side + centre crop + rescale + normalise (reference clip.py:88-94 runs this on the host through PIL).
