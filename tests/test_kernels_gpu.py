@@ -224,6 +224,12 @@ ATT_CASES = [
     (2, 12, 77, 77, 64, True),
     (2, 16, 257, 257, 64, False),
     (3, 8, 4096, 77, 40, False),
+    # shapes served by the two-tile kernel (attention_fa_kernel: d_head <= 64, >= 512 keys, Nq % 256 == 0)
+    (2, 8, 1024, 1024, 40, False),
+    (2, 4, 512, 640, 64, False),       # d 64: all four K16 steps, DVP 64
+    (1, 3, 256, 1000, 40, False),      # masked tail tile (1000 = 7 * 128 + 104)
+    (2, 2, 768, 520, 48, False),       # d 48; kv stride 520, five tiles, last one 8 keys
+    (8, 8, 4096, 4096, 40, False),     # the benchmark's own self-attention launch (B = 8, 64x64 latent)
 ]
 
 
@@ -267,7 +273,8 @@ def test_groupnorm(B, HW, C1, C2, act, eps):
     assert torch.equal(out, out2), "groupnorm must be run-to-run deterministic"
 
 
-@pytest.mark.parametrize("rows,C", [(4096, 320), (1000, 640), (512, 1280), (154, 768), (514, 1024)])
+@pytest.mark.parametrize("rows,C", [(4096, 320), (1000, 640), (512, 1280), (154, 768), (514, 1024), (32768, 320), (4099, 320),
+                                    (3, 320), (517, 64), (130, 128), (77, 256), (64, 2048), (100, 1000 // 8 * 8)])
 def test_layernorm(rows, C):
     ops = _ops()
     x = rnd(rows, C, seed=1) * 3 + 1

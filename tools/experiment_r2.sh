@@ -8,6 +8,7 @@ mkdir -p $O
 run() { name=$1; shift; echo "=== $name: $*" >> $O/exp_$TAG.log; timeout -s KILL ${T:-150} "$@" >> $O/exp_$TAG.log 2>&1; rc=$?; echo "=== $name rc=$rc" >> $O/exp_$TAG.log; return $rc; }
 PT="python -m pytest -q -p no:cacheprovider --timeout 100 tests/test_kernels_gpu.py"
 VDB_TEST_PENDING=1 T=300 run t_pending python -m pytest -q -p no:cacheprovider --timeout 200 tests/test_pending_gpu.py
+T=400 run t_benchshape python -m pytest -q -p no:cacheprovider -s --timeout 380 tests/test_parity_gpu.py -k "benchmark_shape"
 VDB_ATT_PP=3 T=90 run t_pp3 $PT -k "attention"; PP3=$?
 VDB_ATT_PP=2 T=90 run t_pp2 $PT -k "attention"; PP2=$?
 VDB_NFAST=2 T=120 run t_nfast $PT -k "gemm or conv3x3"; NF=$?

@@ -24,6 +24,9 @@ from lib.model_zoo.ddim import DDIMSampler  # noqa: E402
 from vdb200 import _lib, ops  # noqa: E402
 
 REPS = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+# torch.cuda.graph() calls torch.cuda.empty_cache() on entry: the cached blocks the recorded pointers live in would be
+# unmapped before the replay (first GPU run of this tool: "illegal memory access" on every replay).  Keep them mapped.
+torch.cuda.empty_cache = lambda: None
 dev = torch.device("cuda", 0)
 net = bench.build_net(dev)
 g = torch.Generator().manual_seed(0)

@@ -715,6 +715,340 @@ __global__ void __launch_bounds__(64 + 256 * G, 1) attention_pp_kernel(const __g
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Two-tile kernel for long, unmasked-or-tail-masked contexts at d_head <= 64 (round 2; default for self-attention at
+// the 64x64 / 32x32 ... levels where d_head = 40).  Built from the round-1 role timeline: the column-split kernel above
+// spends 0.9 us of every 2.05 us tile outside its exp2 phase (S round trip through the MMA warp, TMEM load, row-max
+// exchange), and the two CTAs of an SM run those phases in lock step, so the MUFU pipe idles ~45 % of the time.
+//   * ONE CTA per SM owns TWO 128-row query tiles (softmax warpgroups 0 / 1, 4 warps each = one warp per TMEM lane quarter).
+//   * a thread owns one query ROW and reads its whole 128-column S tile from TMEM into registers ONCE; the S buffer is
+//     released to the MMA warp right after that load (s_free), so S_{j+1} = Q K_{j+1}^T is computed underneath the exp2
+//     phase of S_j — no row-max exchange, no S round trip on the critical path, single S buffer per warpgroup.
+//   * the two warpgroups take strict turns on the MUFU pipe (named-barrier token): while one runs exp2, the other waits
+//     for its S, loads it, reduces the row max and (rarely) rescales O.
+//   * POLY of every 8 column pairs are exponentiated on the FMA pipe (packed fp32x2 Cody-Waite + cubic, rel. error
+//     7.7e-5 << bf16's 2e-3): at d_head 40 the MUFU pipe, not the tensor pipe, is the floor (1.07 G exp2 per launch).
+//   * QK^T skips the k-steps whose 16 channels are zero padding (d_head 40: 3 of the 4 K16 steps of the 64-wide atom).
+//   * K / V^T tiles are staged once per CTA and used by both warpgroups (half the L2 -> shared-memory traffic per FLOP).
+//   TMEM: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384).   warps: 0 TMA, 1 MMA, (2, 3 idle), 4-7 warpgroup 0, 8-11 warpgroup 1;
+//   the control warpgroup gives its registers away (setmaxnreg.dec 40) and the softmax warpgroups take 232 each: a row's
+//   128 scores live in registers across the whole tile.
+//   MMA issue order (steady state): PV_0(j), S_0(j+2), PV_1(j), S_1(j+2), ...
+// ---------------------------------------------------------------------------------------------------------------------
+template <int DVP, int KV_STAGES>
+constexpr size_t attention_fa_smem_bytes() {
+  return 2 * kBQ * 128 + KV_STAGES * (128 * 128 + 2 * DVP * 128) + 2 * (2 * kBQ * 128) + 32 * 8 + 1024;
+}
+
+// 2^x for a packed pair on the FMA / ALU pipes (x <= 0 expected; clamped at -126)
+VDB_DEVINL void ex2_poly2(float xa, float xb, float& ea, float& eb) {
+  xa = fmaxf(xa, -126.0f);
+  xb = fmaxf(xb, -126.0f);
+  const unsigned long long x2 = pack_f2(xa, xb);
+  const unsigned long long magic = pack_f2(12582912.0f, 12582912.0f), nmagic = pack_f2(-12582912.0f, -12582912.0f);
+  const unsigned long long one2 = pack_f2(1.0f, 1.0f), mone2 = pack_f2(-1.0f, -1.0f);
+  const unsigned long long r2 = add_f2(x2, magic);              // low mantissa bits hold rint(x)
+  const unsigned long long t2 = add_f2(r2, nmagic);             // rint(x) as a float
+  const unsigned long long f2 = fma_f2(t2, mone2, x2);          // f = x - rint(x) in [-0.5, 0.5]
+  unsigned long long p2 = fma_f2(pack_f2(0.0550886838f, 0.0550886838f), f2, pack_f2(0.242604051f, 0.242604051f));
+  p2 = fma_f2(p2, f2, pack_f2(0.693276242f, 0.693276242f));
+  p2 = fma_f2(p2, f2, pack_f2(0.99992894f, 0.99992894f));
+  (void)one2;
+  float pa, pb, ra, rb;
+  unpack_f2(p2, pa, pb);
+  unpack_f2(r2, ra, rb);
+  ea = __int_as_float(__float_as_int(pa) + (__float_as_int(ra) << 23));
+  eb = __int_as_float(__float_as_int(pb) + (__float_as_int(rb) << 23));
+}
+
+template <int DVP, int KV_STAGES, int POLY, int TOKEN>
+__global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_constant__ AttnParams p) {
+  constexpr int BKV = 128;
+  constexpr uint32_t kQBytes = kBQ * 128;          // one warpgroup's Q tile (DK = 64: one K atom)
+  constexpr uint32_t kKBytes = BKV * 128;          // one K stage (128 keys x 64 channels)
+  constexpr uint32_t kVAtom = DVP * 128;           // one 64-kv atom of V^T
+  constexpr uint32_t kVBytes = 2 * kVAtom;         // one V stage
+  constexpr uint32_t kPBytes = 2 * kBQ * 128;      // one warpgroup's P buffer (128 x 128 bf16, two 64-kv atoms)
+  static_assert(DVP % 16 == 0 && DVP <= 64, "O must fit 64 TMEM columns per warpgroup");
+  static_assert(KV_STAGES >= 2 && KV_STAGES <= kMaxKvStages, "kv stages");
+  static_assert(kVAtom % 1024 == 0, "V atom must keep 1024B alignment");
+  static_assert(POLY >= 0 && POLY <= 4, "poly pairs per 8 pairs");
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                               // [2][16 KB]
+  uint8_t* sK = sQ + 2 * kQBytes;                   // [KV_STAGES][16 KB]
+  uint8_t* sV = sK + KV_STAGES * kKBytes;           // [KV_STAGES][kVBytes]
+  uint8_t* sP = sV + KV_STAGES * kVBytes;           // [2][32 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // [kMaxKvStages]
+  uint64_t* k_empty = bars + 5;       // [kMaxKvStages]
+  uint64_t* v_full = bars + 9;        // [kMaxKvStages]
+  uint64_t* v_empty = bars + 13;      // [kMaxKvStages]
+  uint64_t* s_full = bars + 17;       // [2]
+  uint64_t* s_free = bars + 19;       // [2]  (count 4: one arrive per warp of the group once S is in registers)
+  uint64_t* p_full = bars + 21;       // [2]  (count 4)
+  uint64_t* pv_done = bars + 23;      // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 26);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * kBQ);
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int ntiles = (p.Nk + BKV - 1) / BKV;
+  const int ksteps = min(4, (p.dv + 15) >> 4);     // K16 steps of QK^T that hold non-zero channels
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KV_STAGES; ++s) {
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&s_free[g], 4);
+      mbar_init(&p_full[g], 4);
+      mbar_init(&pv_done[g], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * kQBytes);
+      for (int g = 0; g < 2; ++g)
+        tma_load_2d(sQ + g * kQBytes, &p.tmQ, q_full, p.q_col0 + head * 64, b * p.q_bs + q0 + g * kBQ);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], kKBytes);
+        tma_load_2d(sK + st * kKBytes, &p.tmK, &k_full[st], p.k_col0 + head * 64, b * p.kv_bs + j * BKV);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], kVBytes);
+        for (int a = 0; a < 2; ++a)
+          tma_load_2d(sV + st * kVBytes + a * kVAtom, &p.tmV, &v_full[st], b * p.kv_bs + j * BKV + a * 64, head * DVP);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(kBQ, BKV);
+      constexpr uint32_t idesc_o = make_idesc_bf16(kBQ, DVP);
+      // S_g(j) = Q_g K_j^T; the K stage is released after warpgroup 1's product of that tile
+      auto issue_S = [&](int g, int j) {
+        const int st = j % KV_STAGES;
+        mbar_wait(&k_full[st], (j / KV_STAGES) & 1);   // (already complete for g = 1: returns at once)
+        tc_fence_after();
+        const uint64_t qd = make_desc_sw128(smem_u32(sQ + g * kQBytes));
+        const uint64_t kd = make_desc_sw128(smem_u32(sK + st * kKBytes));
+        for (int k = 0; k < ksteps; ++k) umma_bf16_ss(tmem_base + g * 128, qd + 2 * k, kd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        if (g == 1) umma_commit(&k_empty[st]);
+        umma_commit(&s_full[g]);
+      };
+      mbar_wait(q_full, 0);
+      issue_S(0, 0);
+      issue_S(1, 0);
+      if (ntiles > 1) {
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&s_free[g], 0);                    // S_g(0) is in the group's registers
+          tc_fence_after();
+          issue_S(g, 1);
+        }
+      }
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % KV_STAGES;
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&p_full[g], j & 1);                // P_g(j) written, O_g rescaled
+          mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const uint64_t pd = make_desc_sw128(smem_u32(sP + g * kPBytes + a * kBQ * 128));
+            const uint64_t vd = make_desc_sw128(smem_u32(sV + st * kVBytes + a * kVAtom));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss(tmem_base + 256 + g * 64, pd + 2 * k, vd + 2 * k, idesc_o, (j > 0 || a > 0 || k > 0) ? 1u : 0u);
+          }
+          if (g == 1) umma_commit(&v_empty[st]);
+          umma_commit(&pv_done[g]);
+          if (j + 2 < ntiles) {
+            mbar_wait(&s_free[g], (j + 1) & 1);        // S_g(j+1) is in registers: its buffer may take S_g(j+2)
+            tc_fence_after();
+            issue_S(g, j + 2);
+          }
+        }
+      }
+    }
+  }
+  } else {
+    // ------------------------------ softmax warpgroup g: one query row per thread ------------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    const int g = (warp - 4) >> 2;
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;            // query row inside the group's tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const int q_idx = q0 + g * kBQ + r;
+    const uint32_t tmem_S = tmem_base + g * 128 + lane_off;
+    const uint32_t tmem_O = tmem_base + 256 + g * 64 + lane_off;
+    constexpr int OCH = DVP / 16;                 // 16-column O chunks
+    // exp2 token: group g owns the MUFU pipe between token_wait() and token_pass() (128 waiting + 128 arriving threads)
+    auto token_wait = [&] { if (TOKEN) asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); };
+    auto token_pass = [&] { if (TOKEN) asm volatile("bar.arrive %0, 256;" ::"r"(1 + (g ^ 1)) : "memory"); };
+    if (g == 1) token_pass();                     // prime the ring: group 0 goes first
+    float m_ref = -INFINITY;
+    float l_sum = 0.f;
+    const uint32_t prow = smem_u32(sP + g * kPBytes + r * 128);   // 32-bit shared address: STS, no generic address math
+    for (int j = 0; j < ntiles; ++j) {
+      mbar_wait(&s_full[g], j & 1);
+      tc_fence_after();
+      uint32_t keep[BKV];
+      {
+        uint32_t v0[32], v1[32], v2[32], v3[32];
+        tmem_ld32(tmem_S, v0);
+        tmem_ld32(tmem_S + 32, v1);
+        tmem_ld32(tmem_S + 64, v2);
+        tmem_ld32(tmem_S + 96, v3);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { keep[i] = v0[i]; keep[32 + i] = v1[i]; keep[64 + i] = v2[i]; keep[96 + i] = v3[i]; }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[g]);     // the MMA warp may overwrite S with the next tile's scores
+      const int kv0 = j * BKV;
+      const bool need_mask = kv0 + BKV > p.Nk;
+      float mx;
+      {
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        if (need_mask) {
+#pragma unroll
+          for (int i = 0; i < BKV; ++i)
+            if (kv0 + i >= p.Nk) keep[i] = 0xff800000u;   // -inf: contributes exp2 = 0 and never wins the max
+        }
+#pragma unroll
+        for (int i = 0; i < BKV; i += 8) {
+          m0 = fmaxf(m0, fmaxf(__uint_as_float(keep[i]), __uint_as_float(keep[i + 1])));
+          m1 = fmaxf(m1, fmaxf(__uint_as_float(keep[i + 2]), __uint_as_float(keep[i + 3])));
+          m2 = fmaxf(m2, fmaxf(__uint_as_float(keep[i + 4]), __uint_as_float(keep[i + 5])));
+          m3 = fmaxf(m3, fmaxf(__uint_as_float(keep[i + 6]), __uint_as_float(keep[i + 7])));
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      }
+      const float m_new = fmaxf(m_ref, mx);
+      bool rescale = false;
+      float factor = 1.f;
+      if (j == 0) {
+        m_ref = m_new;
+      } else {
+        const bool want = (m_new - m_ref) * p.scale_log2 > kRescaleThreshold;
+        rescale = __any_sync(0xffffffffu, want);
+        if (rescale) {
+          factor = ex2_mufu((m_ref - m_new) * p.scale_log2);
+          m_ref = m_new;
+          l_sum *= factor;
+        }
+      }
+      const float m_scaled = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;
+      // PV_g(j-1) must have retired: it reads the group's only P buffer and accumulates into O
+      if (j > 0) {
+        mbar_wait(&pv_done[g], (j - 1) & 1);
+        tc_fence_after();
+        if (rescale) {
+#pragma unroll 1
+          for (int c = 0; c < OCH; ++c) {
+            uint32_t o[16];
+            tmem_ld16(tmem_O + c * 16, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+            tmem_st16(tmem_O + c * 16, o);
+          }
+          tmem_wait_st();
+        }
+      }
+      token_wait();
+      {
+        const unsigned long long sc2 = pack_f2(p.scale_log2, p.scale_log2), nm2 = pack_f2(-m_scaled, -m_scaled);
+        unsigned long long l2 = pack_f2(0.f, 0.f), l2b = pack_f2(0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < BKV / 8; ++q) {          // 8 scores -> one 16-byte chunk of the P row
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            float xa, xb;
+            unpack_f2(fma_f2(pack_f2(__uint_as_float(keep[q * 8 + i]), __uint_as_float(keep[q * 8 + i + 1])), sc2, nm2), xa, xb);
+            // pair index inside a group of 8 pairs (two chunks): the LAST `POLY` pairs go to the FMA pipe
+            const int pair8 = (q & 1) * 4 + (i >> 1);
+            if (pair8 >= 8 - POLY) {
+              ex2_poly2(xa, xb, e[i], e[i + 1]);
+            } else {
+              e[i] = ex2_mufu(xa);
+              e[i + 1] = ex2_mufu(xb);
+            }
+            if (i & 2) l2b = add_f2(l2b, pack_f2(e[i], e[i + 1])); else l2 = add_f2(l2, pack_f2(e[i], e[i + 1]));
+          }
+          const uint4 pk = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (q >> 3) * (kBQ * 128) + (((q & 7) ^ (r & 7)) << 4)),
+                       "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+        }
+        float la, lb;
+        unpack_f2(add_f2(l2, l2b), la, lb);
+        l_sum += la + lb;
+      }
+      if (!(j == ntiles - 1 && g == 1)) token_pass();   // (the ring is primed once: skip the one surplus hand-over)
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+    }
+    mbar_wait(&pv_done[g], (ntiles - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l_sum;
+    const bool row_ok = q_idx < p.Nq;
+    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.q_bs + q_idx) * p.ldo + head * p.dv;
+#pragma unroll 1
+    for (int c = 0; c < OCH; ++c) {
+      uint32_t o[16];
+      tmem_ld16(tmem_O + c * 16, o);
+      tmem_wait_ld();
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int col = c * 16 + q * 8;
+          if (col + 8 <= p.dv) {
+            const uint4 pk = make_uint4(
+                pack_bf16x2(__uint_as_float(o[q * 8]) * inv_l, __uint_as_float(o[q * 8 + 1]) * inv_l),
+                pack_bf16x2(__uint_as_float(o[q * 8 + 2]) * inv_l, __uint_as_float(o[q * 8 + 3]) * inv_l),
+                pack_bf16x2(__uint_as_float(o[q * 8 + 4]) * inv_l, __uint_as_float(o[q * 8 + 5]) * inv_l),
+                pack_bf16x2(__uint_as_float(o[q * 8 + 6]) * inv_l, __uint_as_float(o[q * 8 + 7]) * inv_l));
+            *reinterpret_cast<uint4*>(orow + col) = pk;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
 struct AttnArgs {   // what the C ABI received; the tensor maps depend on the kernel variant's kv tile
   const void *Q, *K, *Vt;
   long long ldq, ldk, ldv;
@@ -767,6 +1101,49 @@ static int launch_attention_pp(AttnParams& p, const AttnArgs& a, cudaStream_t st
   return VDB_OK;
 }
 
+
+template <int DVP, int KV_STAGES, int POLY, int TOKEN>
+static int launch_attention_fa(AttnParams& p, const AttnArgs& a, cudaStream_t stream) {
+  constexpr size_t smem = attention_fa_smem_bytes<DVP, KV_STAGES>();
+  static_assert(smem <= 227 * 1024, "attention (two-tile) smem budget");
+  auto kernel = attention_fa_kernel<DVP, KV_STAGES, POLY, TOKEN>;
+  static bool configured = false;
+  if (!configured) {
+    VDB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    prefer_max_smem(kernel);
+    configured = true;
+  }
+  int rc = make_tmap_2d(&p.tmQ, a.Q, static_cast<uint64_t>(a.ldq), static_cast<uint64_t>(a.B) * a.q_bstride, a.ldq * 2, 64, kBQ);
+  if (rc) return rc;
+  rc = make_tmap_2d(&p.tmK, a.K, static_cast<uint64_t>(a.ldk), static_cast<uint64_t>(a.B) * a.kv_bstride, a.ldk * 2, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&p.tmV, a.Vt, static_cast<uint64_t>(a.B) * a.kv_bstride, static_cast<uint64_t>(a.H) * DVP, a.ldv * 2, 64, DVP);
+  if (rc) return rc;
+  dim3 grid((p.Nq + 2 * kBQ - 1) / (2 * kBQ), a.H, a.B);
+  VDB_CUDA_CHECK(launch_pdl(kernel, grid, dim3(384), smem, stream, p));
+  count_launch();
+  return VDB_OK;
+}
+
+template <int DVP>
+static int dispatch_attention_fa(int poly, int token, AttnParams& p, const AttnArgs& a, cudaStream_t st) {
+  if (token) {
+    switch (poly) {
+      case 0: return launch_attention_fa<DVP, 3, 0, 1>(p, a, st);
+      case 1: return launch_attention_fa<DVP, 3, 1, 1>(p, a, st);
+      case 3: return launch_attention_fa<DVP, 3, 3, 1>(p, a, st);
+      case 4: return launch_attention_fa<DVP, 3, 4, 1>(p, a, st);
+      default: return launch_attention_fa<DVP, 3, 2, 1>(p, a, st);
+    }
+  }
+  switch (poly) {
+    case 0: return launch_attention_fa<DVP, 3, 0, 0>(p, a, st);
+    case 1: return launch_attention_fa<DVP, 3, 1, 0>(p, a, st);
+    case 3: return launch_attention_fa<DVP, 3, 3, 0>(p, a, st);
+    case 4: return launch_attention_fa<DVP, 3, 4, 0>(p, a, st);
+    default: return launch_attention_fa<DVP, 3, 2, 0>(p, a, st);
+  }
+}
 }  // namespace vdb
 
 using namespace vdb;
@@ -825,6 +1202,14 @@ int vdb_attention_bf16(const void* Q, long long ldq, int q_col0, const void* K, 
   if (pp && DK == 64 && !causal && Nk >= 256 && Nq >= 256) {
     if (DVP == 48) return pp == 2 ? launch_attention_pp<48, 2, 4>(p, a, st) : launch_attention_pp<48, 3, 4>(p, a, st);
     if (DVP == 64) return pp == 2 ? launch_attention_pp<64, 2, 4>(p, a, st) : launch_attention_pp<64, 3, 4>(p, a, st);
+  }
+  // VDB_ATT_FA: the two-tile kernel (attention_fa_kernel).  0 = off; otherwise digits "PT": P = exp2 pairs of every 8 on the
+  // FMA pipe (0..4), T = 1 strict MUFU turns (token) / 0 free-running.  e.g. 21 = two of eight pairs, token.
+  static const int fa = [] { const char* e = getenv("VDB_ATT_FA"); return e ? atoi(e) : -1; }();
+  if (fa != 0 && !pp && DK == 64 && !causal && Nk >= 512 && Nq >= 256 && (Nq % 256) == 0) {
+    const int mode = fa < 0 ? 21 : fa;
+    if (DVP == 48) return dispatch_attention_fa<48>(mode / 10, mode % 10, p, a, st);
+    if (DVP == 64) return dispatch_attention_fa<64>(mode / 10, mode % 10, p, a, st);
   }
   static const int bkv = [] { const char* e = getenv("VDB_ATT_BKV"); const int v = e ? atoi(e) : 0; return (v == 64 || v == 643 || v == 128) ? v : 0; }();
   if (sw == 2) {
