@@ -256,7 +256,13 @@ def test_attention(B, H, Nq, Nk, d, causal):
                                               # large layers, the register-resident path at the small ones
                                               (8, 4096, 320, 0, 1, 1e-5), (8, 1024, 640, 640, 1, 1e-5),
                                               (8, 256, 1280, 1280, 1, 1e-5), (8, 64, 1280, 0, 1, 1e-5),
-                                              (8, 100, 320, 0, 0, 1e-6)])
+                                              (8, 100, 320, 0, 0, 1e-6),
+                                              # group-bundle kernel: cluster sizes 1..8, bundles that straddle the two concat
+                                              # sources (C1 = 1280 | 640 at 60 channels per group), odd pixel counts
+                                              (8, 4096, 320, 320, 1, 1e-5), (8, 1024, 1280, 640, 1, 1e-5), (8, 256, 1280, 640, 1, 1e-5),
+                                              (8, 1024, 640, 320, 1, 1e-5), (8, 4096, 640, 320, 1, 1e-5), (8, 64, 1280, 1280, 1, 1e-5),
+                                              (2, 577, 320, 0, 1, 1e-5), (4, 1024, 128, 0, 1, 1e-6), (4, 4096, 256, 0, 0, 1e-6),
+                                              (3, 36, 640, 640, 1, 1e-5), (1, 16384, 512, 0, 1, 1e-6)])
 def test_groupnorm(B, HW, C1, C2, act, eps):
     ops = _ops()
     x1 = rnd(B, HW, C1, seed=1) + 0.5

@@ -658,6 +658,167 @@ __global__ void __launch_bounds__(kGnThreads, 1) gn_cluster_kernel(const __nv_bf
 }
 
 // ---------------------------------------------------------------------------------------------
+// Group-bundle GroupNorm (round 2, default wherever it fits): a CTA owns a BUNDLE of G consecutive groups of ONE image
+// (G = 1, 2 or 4, the smallest that makes the bundle's channel run a multiple of 16 bytes: 40 / 40 / 120 / 40 / 120 / 80
+// channels at C = 320 / 640 / 960 / 1280 / 1920 / 2560) instead of a pixel range of all channels.  A group's statistics
+// then never leave the CTA: no grid-wide arrival counter, no global scratch, no residency requirement, and the pixels are
+// read ONCE (they stay in registers between the statistics and the normalisation).  Layers whose bundle does not fit the
+// registers of one CTA split the pixels over a thread-block cluster of S <= 8 CTAs (grid (bundles, S, B), cluster
+// (1, S, 1)); the 2 G partial sums cross the cluster through distributed shared memory behind one hardware cluster barrier.
+// The single-launch kernel above spent most of its 11-30 us per layer in serialised latency phases (publish, device-wide
+// wait, re-read), not in bandwidth: profiles/r01_variants_v8.txt.
+// Deterministic: fixed-order shuffles / rank-ordered cluster fold (every CTA of a cluster computes identical statistics).
+// Per-thread mapping: vec = t % VPB (16-byte channel octet inside the bundle), pixel lane = t / VPB; pixels pl + k * lanes.
+// ---------------------------------------------------------------------------------------------
+template <int NVMAX>
+__global__ void __launch_bounds__(512, NVMAX <= 6 ? 2 : 1) gn_bundle_kernel(const __nv_bfloat16* __restrict__ x1, int C1,
+                                                                           const __nv_bfloat16* __restrict__ x2, int C2, int HW,
+                                                                           int groups, int G, float eps, int act,
+                                                                           const float* __restrict__ gamma,
+                                                                           const float* __restrict__ beta,
+                                                                           __nv_bfloat16* __restrict__ y) {
+  const int C = C1 + C2;
+  const int cpg = C / groups;
+  const int BC = G * cpg;                 // channels per bundle (multiple of 8)
+  const int VPB = BC / 8;                 // 16-byte vectors per pixel and bundle
+  const int lanes = 512 / VPB;
+  const int S = gridDim.y;
+  const int b = blockIdx.z, bundle = blockIdx.x, part = blockIdx.y;
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float wpart[16][8];          // per-warp partials: sum | sumsq of up to 4 groups
+  __shared__ float xpart[8];              // this CTA's partials (read by the cluster peers)
+  __shared__ float gstat[8];              // mean[4] | rstd[4]
+  const int vec = threadIdx.x % VPB, pl = threadIdx.x / VPB;
+  const bool active = pl < lanes;
+  const int cb = vec * 8;                                 // first channel of this thread inside the bundle
+  const int cg = bundle * BC + cb;                        // ... and inside the (concatenated) tensor
+  const bool first = cg < C1;
+  const __nv_bfloat16* src = first ? x1 + static_cast<long long>(b) * HW * C1 + cg
+                                   : x2 + static_cast<long long>(b) * HW * C2 + (cg - C1);
+  const long long Cs = first ? C1 : C2;
+  const int pix_per = (HW + S - 1) / S;
+  const int p_begin = part * pix_per, p_end = min(HW, p_begin + pix_per);
+  uint4 keep[NVMAX];
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < NVMAX; ++k) {
+      const int p = p_begin + pl + k * lanes;
+      keep[k] = (p < p_end) ? __ldg(reinterpret_cast<const uint4*>(src + p * Cs)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < NVMAX; ++k) {     // (pixels past the range contribute zeros)
+      const uint32_t w[4] = {keep[k].x, keep[k].y, keep[k].z, keep[k].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16x2(w[i]);
+        s[2 * i] += f.x; q[2 * i] += f.x * f.x;
+        s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+      }
+    }
+  }
+  // this thread's 8 channels belong to at most two groups of the bundle (cpg >= 4): g_lo for channels < nb, g_lo + 1 after
+  const int g_lo = cb / cpg;
+  const int nb = min(8, (g_lo + 1) * cpg - cb);
+  float red[8];                            // sum[4] | sumsq[4]
+  {
+    float a0 = 0.f, c0 = 0.f, a1 = 0.f, c1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < nb) { a0 += s[i]; c0 += q[i]; } else { a1 += s[i]; c1 += q[i]; }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      red[g] = (g == g_lo) ? a0 : ((g == g_lo + 1) ? a1 : 0.f);
+      red[4 + g] = (g == g_lo) ? c0 : ((g == g_lo + 1) ? c1 : 0.f);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) red[j] += __shfl_xor_sync(0xffffffffu, red[j], o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wpart[warp][j] = red[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) a += wpart[w][threadIdx.x];
+    xpart[threadIdx.x] = a;
+  }
+  // gamma / beta of this thread's channel octet: in flight under the barriers below
+  float gam[8], bet[8];
+  if (active) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + cg)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + cg + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + cg)), b1 = __ldg(reinterpret_cast<const float4*>(beta + cg + 4));
+    gam[0] = g0.x; gam[1] = g0.y; gam[2] = g0.z; gam[3] = g0.w; gam[4] = g1.x; gam[5] = g1.y; gam[6] = g1.z; gam[7] = g1.w;
+    bet[0] = b0.x; bet[1] = b0.y; bet[2] = b0.z; bet[3] = b0.w; bet[4] = b1.x; bet[5] = b1.y; bet[6] = b1.z; bet[7] = b1.w;
+  }
+  if (S > 1) {
+    cluster_arrive();                      // (release: xpart is visible to the peers after their wait)
+    cluster_wait();
+  } else {
+    __syncthreads();
+  }
+  if (threadIdx.x < 4) {
+    float a = 0.f, c = 0.f;
+    if (S > 1) {
+      const uint32_t mine = smem_u32(xpart);
+      for (int r = 0; r < S; ++r) {        // rank order: identical in every CTA of the cluster
+        const uint32_t peer = mapa_u32(mine, static_cast<uint32_t>(r));
+        a += ld_dsmem_f32(peer + 4 * threadIdx.x);
+        c += ld_dsmem_f32(peer + 4 * (4 + threadIdx.x));
+      }
+    } else {
+      a = xpart[threadIdx.x]; c = xpart[4 + threadIdx.x];
+    }
+    const float inv_n = 1.0f / (static_cast<float>(HW) * cpg);
+    const float mean = a * inv_n;
+    const float var = fmaxf(c * inv_n - mean * mean, 0.f);
+    gstat[threadIdx.x] = mean;
+    gstat[4 + threadIdx.x] = rsqrtf(var + eps);
+  }
+  if (S > 1) cluster_arrive();             // "done reading my peers' shared memory" (waited for before exit)
+  __syncthreads();
+  if (active) {
+    float sc[8], sh[8];
+    const float m0 = gstat[g_lo], r0 = gstat[4 + g_lo], m1 = gstat[min(g_lo + 1, 3)], r1 = gstat[4 + min(g_lo + 1, 3)];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sc[i] = ((i < nb) ? r0 : r1) * gam[i];
+      sh[i] = bet[i] - ((i < nb) ? m0 : m1) * sc[i];
+    }
+    __nv_bfloat16* dst = y + static_cast<long long>(b) * HW * C + cg;
+#pragma unroll
+    for (int k = 0; k < NVMAX; ++k) {
+      const int p = p_begin + pl + k * lanes;
+      if (p < p_end) {
+        const uint32_t w[4] = {keep[k].x, keep[k].y, keep[k].z, keep[k].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack_bf16x2(w[i]);
+          float a = f.x * sc[2 * i] + sh[2 * i];
+          float c = f.y * sc[2 * i + 1] + sh[2 * i + 1];
+          if (act == 1) { a = silu_bf16_f(a); c = silu_bf16_f(c); }
+          o[i] = pack_bf16x2(a, c);
+        }
+        *reinterpret_cast<uint4*>(dst + static_cast<long long>(p) * C) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  if (S > 1) cluster_wait();               // no CTA leaves while a peer may still read its xpart
+}
+
+// ---------------------------------------------------------------------------------------------
 // LayerNorm over the last dim of [rows, C] bf16 (one warp per row, two-pass in registers).
 // ---------------------------------------------------------------------------------------------
 template <int MAXV, int R>  // MAXV: max 16-byte vectors per lane; R: rows processed concurrently per warp (memory-level parallelism)
@@ -830,7 +991,7 @@ __global__ void __launch_bounds__(256) layernorm_pf_kernel(const __nv_bfloat16* 
 // C = 320 row (40 vectors) and was measured at 2.3 TB/s in-graph on the 32768 x 320 layers.  Persistent walk with the
 // next step's rows requested before the current ones are normalised; gamma / beta live in shared memory.
 template <int VPL, int LPR>
-__global__ void __launch_bounds__(256) layernorm_rg_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C,
+__global__ void __launch_bounds__(256, 2) layernorm_rg_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            float eps, __nv_bfloat16* __restrict__ y) {
   constexpr int RPW = 32 / LPR;           // rows per warp and step
@@ -858,7 +1019,7 @@ __global__ void __launch_bounds__(256) layernorm_rg_kernel(const __nv_bfloat16* 
   load_row(r, cur);
   for (long long r0 = static_cast<long long>(warp) * RPW; r0 < rows; r0 += stride, r += stride) {
     load_row(r + stride, nxt);            // in flight while the current rows are normalised
-    float f[VPL][8];
+    // (the rows are unpacked again in every pass instead of kept as fp32: 40 fewer live registers at VPL = 5)
     float s = 0.f;
     if (r < rows) {
 #pragma unroll
@@ -867,7 +1028,6 @@ __global__ void __launch_bounds__(256) layernorm_rg_kernel(const __nv_bfloat16* 
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float2 t = unpack_bf16x2(w[i]);
-          f[k][2 * i] = t.x; f[k][2 * i + 1] = t.y;
           s += t.x + t.y;
         }
       }
@@ -878,9 +1038,15 @@ __global__ void __launch_bounds__(256) layernorm_rg_kernel(const __nv_bfloat16* 
     float q = 0.f;
     if (r < rows) {
 #pragma unroll
-      for (int k = 0; k < VPL; ++k)
+      for (int k = 0; k < VPL; ++k) {
+        const uint32_t w[4] = {cur[k].x, cur[k].y, cur[k].z, cur[k].w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { const float d = f[k][i] - mean; q += d * d; }
+        for (int i = 0; i < 4; ++i) {
+          const float2 t = unpack_bf16x2(w[i]);
+          const float d0 = t.x - mean, d1 = t.y - mean;
+          q += d0 * d0 + d1 * d1;
+        }
+      }
     }
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
@@ -894,11 +1060,13 @@ __global__ void __launch_bounds__(256) layernorm_rg_kernel(const __nv_bfloat16* 
         const float4 b0 = *reinterpret_cast<const float4*>(ln_gb + C + c0), b1 = *reinterpret_cast<const float4*>(ln_gb + C + c0 + 4);
         const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const uint32_t w[4] = {cur[k].x, cur[k].y, cur[k].z, cur[k].w};
         uint32_t o[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          o[i] = pack_bf16x2((f[k][2 * i] - mean) * rstd * gg[2 * i] + bb[2 * i],
-                             (f[k][2 * i + 1] - mean) * rstd * gg[2 * i + 1] + bb[2 * i + 1]);
+        for (int i = 0; i < 4; ++i) {
+          const float2 t = unpack_bf16x2(w[i]);
+          o[i] = pack_bf16x2((t.x - mean) * rstd * gg[2 * i] + bb[2 * i], (t.y - mean) * rstd * gg[2 * i + 1] + bb[2 * i + 1]);
+        }
         dst[k * LPR] = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
@@ -1418,6 +1586,40 @@ int vdb_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int B, in
     return set_error(VDB_ERR_UNSUPPORTED, "groupnorm: need 32 groups, C %% 32 == 0, C/8 <= 512 (C=%d)", C);
   if (!x2) C2 = 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // group-bundle kernel (default; VDB_GN_BUNDLE=0 turns it off): see gn_bundle_kernel
+  static const bool bundle_ok = [] { const char* ev = getenv("VDB_GN_BUNDLE"); return !(ev && ev[0] == '0'); }();
+  if (bundle_ok && groups == 32) {
+    const int cpg = C / groups;
+    int G = 1;
+    while (G <= 4 && ((G * cpg) % 8)) G *= 2;
+    const int BC = G * cpg, VPB = BC / 8;
+    if (G <= 4 && cpg >= 4 && VPB >= 1 && VPB <= 64) {
+      const int lanes = 512 / VPB;
+      auto nper = [&](int S) { return (((HW + S - 1) / S) + lanes - 1) / lanes; };
+      int S = 1;
+      while (S < 8 && nper(S) > 6) S *= 2;
+      // small grids: more CTAs per image while every thread still keeps >= 2 pixels
+      while (S < 8 && static_cast<long long>(groups / G) * S * B < num_sms() && nper(S * 2) >= 2) S *= 2;
+      const int n = nper(S);
+      if (n <= 12) {
+        const __nv_bfloat16* x1b = reinterpret_cast<const __nv_bfloat16*>(x1);
+        const __nv_bfloat16* x2b = reinterpret_cast<const __nv_bfloat16*>(x2);
+        __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(groups / G, S, B); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = S; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (n <= 2) VDB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gn_bundle_kernel<2>, x1b, C1, x2b, C2, HW, groups, G, eps, act, gamma, beta, yb));
+        else if (n <= 6) VDB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gn_bundle_kernel<6>, x1b, C1, x2b, C2, HW, groups, G, eps, act, gamma, beta, yb));
+        else VDB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gn_bundle_kernel<12>, x1b, C1, x2b, C2, HW, groups, G, eps, act, gamma, beta, yb));
+        count_launch();
+        return VDB_OK;
+      }
+    }
+  }
   // cluster variant (VDB_GN_CLUSTER, opt-in until measured; bit 0 = on, bit 1 = never keep the pixels in shared memory,
   // bit 2 = any batch size): UNet-sized layers only (the VAE's 512x512 layers have too few images to fill the machine with
   // <= 16 CTAs per image)
