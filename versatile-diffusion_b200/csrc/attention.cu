@@ -735,9 +735,9 @@ __global__ void __launch_bounds__(64 + 256 * G, 1) attention_pp_kernel(const __g
 //   128 scores live in registers across the whole tile.
 //   MMA issue order (steady state): PV_0(j), S_0(j+2), PV_1(j), S_1(j+2), ...
 // ---------------------------------------------------------------------------------------------------------------------
-template <int DVP, int KV_STAGES>
+template <int DVP, int KV_STAGES, int PT>
 constexpr size_t attention_fa_smem_bytes() {
-  return 2 * kBQ * 128 + KV_STAGES * (128 * 128 + 2 * DVP * 128) + 2 * (2 * kBQ * 128) + 32 * 8 + 1024;
+  return 2 * kBQ * 128 + KV_STAGES * (128 * 128 + 2 * DVP * 128) + (PT ? 0 : 2 * (2 * kBQ * 128)) + 32 * 8 + 1024;
 }
 
 // 2^x for a packed pair on the FMA / ALU pipes (x <= 0 expected; clamped at -126)
@@ -761,7 +761,7 @@ VDB_DEVINL void ex2_poly2(float xa, float xb, float& ea, float& eb) {
   eb = __int_as_float(__float_as_int(pb) + (__float_as_int(rb) << 23));
 }
 
-template <int DVP, int KV_STAGES, int POLY, int TOKEN>
+template <int DVP, int KV_STAGES, int POLY, int TOKEN, int PT>
 __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_constant__ AttnParams p) {
   constexpr int BKV = 128;
   constexpr uint32_t kQBytes = kBQ * 128;          // one warpgroup's Q tile (DK = 64: one K atom)
@@ -779,8 +779,8 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
   uint8_t* sQ = smem;                               // [2][16 KB]
   uint8_t* sK = sQ + 2 * kQBytes;                   // [KV_STAGES][16 KB]
   uint8_t* sV = sK + KV_STAGES * kKBytes;           // [KV_STAGES][kVBytes]
-  uint8_t* sP = sV + KV_STAGES * kVBytes;           // [2][32 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+  uint8_t* sP = sV + KV_STAGES * kVBytes;           // [2][32 KB]  (PT = 0 only; PT = 1 keeps P in tensor memory)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (PT ? 0 : 2 * kPBytes));
   uint64_t* q_full = bars;            // 1
   uint64_t* k_full = bars + 1;        // [kMaxKvStages]
   uint64_t* k_empty = bars + 5;       // [kMaxKvStages]
@@ -879,11 +879,19 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
           tc_fence_after();
 #pragma unroll
           for (int a = 0; a < 2; ++a) {
-            const uint64_t pd = make_desc_sw128(smem_u32(sP + g * kPBytes + a * kBQ * 128));
             const uint64_t vd = make_desc_sw128(smem_u32(sV + st * kVBytes + a * kVAtom));
+            if constexpr (PT) {
+              // P_g(j) in tensor memory: 128 lanes x 64 packed columns at [384 + 64 g, ..); a K16 step reads 8 columns
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_ss(tmem_base + 256 + g * 64, pd + 2 * k, vd + 2 * k, idesc_o, (j > 0 || a > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_ts(tmem_base + 256 + g * 64, tmem_base + 384 + g * 64 + a * 32 + k * 8, vd + 2 * k, idesc_o,
+                             (j > 0 || a > 0 || k > 0) ? 1u : 0u);
+            } else {
+              const uint64_t pd = make_desc_sw128(smem_u32(sP + g * kPBytes + a * kBQ * 128));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_ss(tmem_base + 256 + g * 64, pd + 2 * k, vd + 2 * k, idesc_o, (j > 0 || a > 0 || k > 0) ? 1u : 0u);
+            }
           }
           if (g == 1) umma_commit(&v_empty[st]);
           umma_commit(&pv_done[g]);
@@ -906,6 +914,8 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
     const int q_idx = q0 + g * kBQ + r;
     const uint32_t tmem_S = tmem_base + g * 128 + lane_off;
     const uint32_t tmem_O = tmem_base + 256 + g * 64 + lane_off;
+    const uint32_t tmem_P = tmem_base + 384 + g * 64 + lane_off;   // PT = 1: this row's 64 packed bf16x2 columns
+    (void)tmem_P;
     constexpr int OCH = DVP / 16;                 // 16-column O chunks
     // exp2 token: group g owns the MUFU pipe between token_wait() and token_pass() (128 waiting + 128 arriving threads)
     auto token_wait = [&] { if (TOKEN) asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); };
@@ -986,6 +996,8 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
       {
         const unsigned long long sc2 = pack_f2(p.scale_log2, p.scale_log2), nm2 = pack_f2(-m_scaled, -m_scaled);
         unsigned long long l2 = pack_f2(0.f, 0.f), l2b = pack_f2(0.f, 0.f);
+        uint32_t pk[PT ? 32 : 4];
+        (void)pk;
 #pragma unroll
         for (int q = 0; q < BKV / 8; ++q) {          // 8 scores -> one 16-byte chunk of the P row
           float e[8];
@@ -1003,16 +1015,23 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
             }
             if (i & 2) l2b = add_f2(l2b, pack_f2(e[i], e[i + 1])); else l2 = add_f2(l2, pack_f2(e[i], e[i + 1]));
           }
-          const uint4 pk = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (q >> 3) * (kBQ * 128) + (((q & 7) ^ (r & 7)) << 4)),
-                       "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+          if constexpr (PT) {
+            // packed bf16 pairs -> 32-bit tensor-memory columns [4 q, 4 q + 4) of this lane's P row; stored 32 columns at a time
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pk[(q & 7) * 4 + i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
+            if ((q & 7) == 7) tmem_st32(tmem_P + (q >> 3) * 32, pk);
+          } else {
+            const uint4 v4 = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (q >> 3) * (kBQ * 128) + (((q & 7) ^ (r & 7)) << 4)),
+                         "r"(v4.x), "r"(v4.y), "r"(v4.z), "r"(v4.w) : "memory");
+          }
         }
         float la, lb;
         unpack_f2(add_f2(l2, l2b), la, lb);
         l_sum += la + lb;
       }
       if (!(j == ntiles - 1 && g == 1)) token_pass();   // (the ring is primed once: skip the one surplus hand-over)
-      fence_proxy_async_smem();
+      if constexpr (PT) tmem_wait_st(); else fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[g]);
@@ -1102,11 +1121,11 @@ static int launch_attention_pp(AttnParams& p, const AttnArgs& a, cudaStream_t st
 }
 
 
-template <int DVP, int KV_STAGES, int POLY, int TOKEN>
+template <int DVP, int KV_STAGES, int POLY, int TOKEN, int PT>
 static int launch_attention_fa(AttnParams& p, const AttnArgs& a, cudaStream_t stream) {
-  constexpr size_t smem = attention_fa_smem_bytes<DVP, KV_STAGES>();
+  constexpr size_t smem = attention_fa_smem_bytes<DVP, KV_STAGES, PT>();
   static_assert(smem <= 227 * 1024, "attention (two-tile) smem budget");
-  auto kernel = attention_fa_kernel<DVP, KV_STAGES, POLY, TOKEN>;
+  auto kernel = attention_fa_kernel<DVP, KV_STAGES, POLY, TOKEN, PT>;
   static bool configured = false;
   if (!configured) {
     VDB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -1125,25 +1144,32 @@ static int launch_attention_fa(AttnParams& p, const AttnArgs& a, cudaStream_t st
   return VDB_OK;
 }
 
-template <int DVP>
-static int dispatch_attention_fa(int poly, int token, AttnParams& p, const AttnArgs& a, cudaStream_t st) {
+template <int DVP, int PT>
+static int dispatch_attention_fa2(int poly, int token, AttnParams& p, const AttnArgs& a, cudaStream_t st) {
   if (token) {
     switch (poly) {
-      case 0: return launch_attention_fa<DVP, 3, 0, 1>(p, a, st);
-      case 1: return launch_attention_fa<DVP, 3, 1, 1>(p, a, st);
-      case 3: return launch_attention_fa<DVP, 3, 3, 1>(p, a, st);
-      case 4: return launch_attention_fa<DVP, 3, 4, 1>(p, a, st);
-      default: return launch_attention_fa<DVP, 3, 2, 1>(p, a, st);
+      case 0: return launch_attention_fa<DVP, 3, 0, 1, PT>(p, a, st);
+      case 1: return launch_attention_fa<DVP, 3, 1, 1, PT>(p, a, st);
+      case 3: return launch_attention_fa<DVP, 3, 3, 1, PT>(p, a, st);
+      case 4: return launch_attention_fa<DVP, 3, 4, 1, PT>(p, a, st);
+      default: return launch_attention_fa<DVP, 3, 2, 1, PT>(p, a, st);
     }
   }
   switch (poly) {
-    case 0: return launch_attention_fa<DVP, 3, 0, 0>(p, a, st);
-    case 1: return launch_attention_fa<DVP, 3, 1, 0>(p, a, st);
-    case 3: return launch_attention_fa<DVP, 3, 3, 0>(p, a, st);
-    case 4: return launch_attention_fa<DVP, 3, 4, 0>(p, a, st);
-    default: return launch_attention_fa<DVP, 3, 2, 0>(p, a, st);
+    case 0: return launch_attention_fa<DVP, 3, 0, 0, PT>(p, a, st);
+    case 1: return launch_attention_fa<DVP, 3, 1, 0, PT>(p, a, st);
+    case 3: return launch_attention_fa<DVP, 3, 3, 0, PT>(p, a, st);
+    case 4: return launch_attention_fa<DVP, 3, 4, 0, PT>(p, a, st);
+    default: return launch_attention_fa<DVP, 3, 2, 0, PT>(p, a, st);
   }
 }
+template <int DVP>
+static int dispatch_attention_fa(int mode, AttnParams& p, const AttnArgs& a, cudaStream_t st) {
+  // mode digits "SPT": S = 1 keeps P in shared memory (SS product), else tensor memory (TS); P = FMA-pipe pairs of 8; T = token
+  const int poly = (mode / 10) % 10, token = mode % 10, smem_p = mode / 100;
+  return smem_p ? dispatch_attention_fa2<DVP, 0>(poly, token, p, a, st) : dispatch_attention_fa2<DVP, 1>(poly, token, p, a, st);
+}
+
 }  // namespace vdb
 
 using namespace vdb;
@@ -1203,13 +1229,14 @@ int vdb_attention_bf16(const void* Q, long long ldq, int q_col0, const void* K, 
     if (DVP == 48) return pp == 2 ? launch_attention_pp<48, 2, 4>(p, a, st) : launch_attention_pp<48, 3, 4>(p, a, st);
     if (DVP == 64) return pp == 2 ? launch_attention_pp<64, 2, 4>(p, a, st) : launch_attention_pp<64, 3, 4>(p, a, st);
   }
-  // VDB_ATT_FA: the two-tile kernel (attention_fa_kernel).  0 = off; otherwise digits "PT": P = exp2 pairs of every 8 on the
-  // FMA pipe (0..4), T = 1 strict MUFU turns (token) / 0 free-running.  e.g. 21 = two of eight pairs, token.
+  // VDB_ATT_FA: the two-tile kernel (attention_fa_kernel).  0 = off; otherwise digits "[S]PT": P = exp2 pairs of every 8 on
+  // the FMA pipe (0..4), T = 1 strict MUFU turns (token) / 0 free-running, leading 1 = P through shared memory (SS product)
+  // instead of tensor memory.  e.g. 21 = two of eight pairs, token, P in tensor memory; 121 = the same with P in shared memory.
   static const int fa = [] { const char* e = getenv("VDB_ATT_FA"); return e ? atoi(e) : -1; }();
   if (fa != 0 && !pp && DK == 64 && !causal && Nk >= 512 && Nq >= 256 && (Nq % 256) == 0) {
-    const int mode = fa < 0 ? 21 : fa;
-    if (DVP == 48) return dispatch_attention_fa<48>(mode / 10, mode % 10, p, a, st);
-    if (DVP == 64) return dispatch_attention_fa<64>(mode / 10, mode % 10, p, a, st);
+    const int mode = fa < 0 ? 11 : fa;
+    if (DVP == 48) return dispatch_attention_fa<48>(mode, p, a, st);
+    if (DVP == 64) return dispatch_attention_fa<64>(mode, p, a, st);
   }
   static const int bkv = [] { const char* e = getenv("VDB_ATT_BKV"); const int v = e ? atoi(e) : 0; return (v == 64 || v == 643 || v == 128) ? v : 0; }();
   if (sw == 2) {
