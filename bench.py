@@ -1,6 +1,6 @@
 """bench.py — headline benchmark of the B200-native Versatile-Diffusion sampling hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2|c3|c4]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 One "step" = one pass of the hot path over one batch: DDIMSampler.sample (50 DDIM steps, CFG 7.5, eta 0)
@@ -31,7 +31,17 @@ for p in (ROOT, PKG):
 METRIC = "512x512 images/sec @ 50-step DDIM (bs=4/GPU)"
 UNIT = "images/s"
 BS, LAT, DDIM_STEPS, SCALE = 4, 64, 50, 7.5
-FLOP_PER_IMAGE = 80.33e12 + 2.5145e12      # 100 UNet rows + VAE decode per 512^2 image
+SEED = 100
+# BASELINE.json configs[1..3]; FLOPs per 512^2 image = 100 UNet rows (50 steps x CFG pair) + VAE decode
+CONFIGS = {
+    "c2": {"workload": "t2i single-flow 512x512, 50-step DDIM, CFG 7.5, eta 0, bs 4/GPU + VAE decode (configs[1])",
+           "ctx": [("text", 77, 1.0)], "flop_per_image": 80.33e12 + 2.5145e12},
+    "c3": {"workload": "image-variation flow (CLIP-image context, 257 tokens) 512x512, 50-step DDIM, CFG 7.5, bs 4/GPU + VAE decode (configs[2])",
+           "ctx": [("image", 257, 1.0)], "flop_per_image": 81.85e12 + 2.5145e12},
+    "c4": {"workload": "dual-context (text 0.7 + image 0.3) guided generation 512x512, 50-step DDIM, CFG 7.5, bs 4/GPU + VAE decode (configs[3])",
+           "ctx": [("text", 77, 0.7), ("image", 257, 0.3)], "flop_per_image": 120.0e12 + 2.5145e12},
+}
+FLOP_PER_IMAGE = CONFIGS["c2"]["flop_per_image"]
 
 
 def measured_peaks():
@@ -99,19 +109,11 @@ def build_net(device):
     return net
 
 
-def make_inputs(rank, device, pinned):
-    import torch
-    g = torch.Generator().manual_seed(100 + rank)
-    kw = {"pin_memory": True} if pinned else {}
-    xT = torch.randn(BS, 4, LAT, LAT, generator=g).contiguous()
-    return (torch.empty_like(xT, **kw).copy_(xT),)
-
-
 def run_product(args):
     import torch
     import torch.distributed as dist
     from lib.model_zoo.ddim import DDIMSampler
-    from vdb200 import ops
+    from vdb200 import ops, parallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -120,36 +122,54 @@ def run_product(args):
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    cfg = CONFIGS[args.config]
     net = build_net(device)
     sampler = DDIMSampler(net)
 
     # contexts: rank 0 "encodes" (synthetic) and broadcasts over NCCL — the only collective of the path
+    # (vdb200.parallel.broadcast_context); uncond of the image context is zeros as in app.py:345
     g = torch.Generator().manual_seed(2)
-    cond_h = (torch.randn(1, 77, 768, generator=g) * 0.5).pin_memory()
-    uncond_h = (torch.randn(1, 77, 768, generator=g) * 0.5).pin_memory()
-    cond, uncond = cond_h.to(device), uncond_h.to(device)
-    if world > 1:
-        dist.broadcast(cond, 0)
-        dist.broadcast(uncond, 0)
-    (xT_h,) = make_inputs(rank, device, pinned=True)
+    ctx_h = []
+    for ctype, L, ratio in cfg["ctx"]:
+        c = (torch.randn(1, L, 768, generator=g) * 0.5).pin_memory()
+        u = (torch.zeros(1, L, 768) if ctype == "image" else torch.randn(1, L, 768, generator=g) * 0.5).pin_memory()
+        ctx_h.append((ctype, ratio, c, u))
+    ctx_d = [(t, r, c.to(device), u.to(device)) for t, r, c, u in ctx_h]
+    if rank != 0:
+        for _, _, c, u in ctx_d:
+            c.zero_(); u.zero_()                      # only rank 0 holds the encoded contexts before the broadcast
+    parallel.broadcast_context([x for _, _, c, u in ctx_d for x in (c, u)])
+    # this rank's rows of the GLOBAL batch, x_T drawn per global row index: an N-rank run reproduces the 1-rank rows
+    rows = parallel.shard_rows(BS * world, rank, world)
+    xT_h = parallel.seeded_latents(rows, (4, LAT, LAT), seed=SEED).pin_memory()
     xT_d = xT_h.to(device)
-    c_d, u_d = cond.repeat(BS, 1, 1).contiguous(), uncond.repeat(BS, 1, 1).contiguous()
+    ctx_rep = [(t, r, c.repeat(BS, 1, 1).contiguous(), u.repeat(BS, 1, 1).contiguous()) for t, r, c, u in ctx_d]
     img_h = torch.empty(BS, 3, 8 * LAT, 8 * LAT, dtype=torch.float32).pin_memory()
+
+    def sample_with(smp, x0, ctxs, steps=DDIM_STEPS):
+        xi = {"type": "image", "xt": x0}
+        if len(ctxs) == 1:
+            t, _, c, u = ctxs[0]
+            return smp.sample(steps=steps, shape=[BS, 4, LAT, LAT], x_info=xi,
+                              c_info={"type": t, "conditioning": c, "unconditional_conditioning": u,
+                                      "unconditional_guidance_scale": SCALE}, verbose=False, eta=0.)[0]
+        return smp.sample_multicontext(steps=steps, shape=[BS, 4, LAT, LAT], x_info=xi,
+                                       c_info_list=[{"type": t, "conditioning": c, "unconditional_conditioning": u,
+                                                     "unconditional_guidance_scale": SCALE, "ratio": r} for t, r, c, u in ctxs],
+                                       verbose=False, eta=0.)[0]
 
     def one_pass(host_io):
         if host_io:
             x0 = xT_h.to(device, non_blocking=True)
-            c = cond_h.to(device, non_blocking=True).repeat(BS, 1, 1)
-            u = uncond_h.to(device, non_blocking=True).repeat(BS, 1, 1)
+            ctxs = [(t, r, c.to(device, non_blocking=True).repeat(BS, 1, 1), u.to(device, non_blocking=True).repeat(BS, 1, 1))
+                    for t, r, c, u in ctx_h]
         else:
-            x0, c, u = xT_d, c_d, u_d
-        x, _ = sampler.sample(steps=DDIM_STEPS, shape=[BS, 4, LAT, LAT], x_info={"type": "image", "xt": x0},
-                              c_info={"type": "text", "conditioning": c, "unconditional_conditioning": u,
-                                      "unconditional_guidance_scale": SCALE}, verbose=False, eta=0.)
+            x0, ctxs = xT_d, ctx_rep
+        x = sample_with(sampler, x0, ctxs)
         im = net.vae_decode(x, "image")
         if host_io:
             img_h.copy_(im, non_blocking=True)
-        return im
+        return x, im
 
     def timed(n, host_io):
         if world > 1:
@@ -178,6 +198,16 @@ def run_product(args):
         ms = timed(args.steps, False)
         # launches: graph replays do not pass through the C ABI, so count one DDIM step and scale
         per_step = getattr(sampler, "last_step_launches", 0)
+        # ---- output check of the TIMED path (VERDICT r1 #1b): the graph-replayed sampler must reproduce an eager run of
+        # the same kernels bit for bit, and every image must be finite and inside [0, 1]
+        x_g, im_g = one_pass(False)
+        x_e = sample_with(DDIMSampler(net, use_cuda_graph=False), xT_d, ctx_rep)
+        check = {"graph_equals_eager_bitwise": bool(torch.equal(x_g, x_e)), "finite": bool(torch.isfinite(im_g).all()),
+                 "image_min": round(float(im_g.min()), 4), "image_max": round(float(im_g.max()), 4),
+                 "latent_std": round(float(x_g.float().std()), 4)}
+        if world > 1:   # sharded rows: rank r's x_T rows are rows [4r, 4r+4) of the 1-rank draw (vdb200.parallel.seeded_latents)
+            check["rows"] = list(rows)
+        del x_e
         decode_launches = 0
         c0 = ops.launch_count()
         net.vae_decode(xT_d, "image")
@@ -191,9 +221,7 @@ def run_product(args):
         if rank == 0:
             eager = DDIMSampler(net, use_cuda_graph=False)
             ops.profile_start()
-            eager.sample(steps=2, shape=[BS, 4, LAT, LAT], x_info={"type": "image", "xt": xT_d},
-                         c_info={"type": "text", "conditioning": c_d, "unconditional_conditioning": u_d,
-                                 "unconditional_guidance_scale": SCALE}, verbose=False, eta=0.)
+            sample_with(eager, xT_d, ctx_rep, steps=2)
             fam = ops.profile_stop()
             peaks = measured_peaks()
             # dominant kernel of the step = igemm_kernel (tcgen05 implicit-GEMM mainloop): it serves both the conv3x3 and
@@ -220,6 +248,10 @@ def run_product(args):
                                     "gbs": round(v["bytes"] / v["ms"] / 1e6, 1) if v["ms"] > 0 else None}
                                 for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
 
+    attn_frac = None
+    if roof is not None and fam and "attention" in fam and fam["attention"]["ms"] > 0:
+        # the metric's "attn TC-util %": attention-core FLOPs (4 B h Nq Nk d, unpadded) / event time / measured sustained peak
+        attn_frac = round(fam["attention"]["flops"] / fam["attention"]["ms"] / 1e9 / measured_peaks()["tflops_sustained"], 4)
     images = BS * world * args.steps
     value = images / (ms / 1e3)
     e2e_value = images / (ms_e2e / 1e3)
@@ -227,7 +259,7 @@ def run_product(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    cpu = cpu_baseline_sample(net) if world == 1 and not args.no_cpu_baseline else None
+    cpu = cpu_baseline_sample(net, tuple(cfg["ctx"])) if world == 1 and not args.no_cpu_baseline else None
     peaks = measured_peaks()
     # ---- roofline refinement (last GPU work of the run, single GPU only): the SAME igemm launches of two eager DDIM steps,
     # re-issued back to back inside one CUDA graph and timed with CUDA events -> the kernel's launch duration without the host
@@ -237,9 +269,7 @@ def run_product(args):
             with torch.no_grad():
                 eager = DDIMSampler(net, use_cuda_graph=False)
                 ops.record_start()
-                eager.sample(steps=2, shape=[BS, 4, LAT, LAT], x_info={"type": "image", "xt": xT_d},
-                             c_info={"type": "text", "conditioning": c_d, "unconditional_conditioning": u_d,
-                                     "unconditional_guidance_scale": SCALE}, verbose=False, eta=0.)
+                sample_with(eager, xT_d, ctx_rep, steps=2)
                 recs = ops.record_stop()
                 torch.cuda.synchronize()
                 gr = torch.cuda.CUDAGraph()
@@ -278,15 +308,18 @@ def run_product(args):
         "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random-init weights, synthetic context)",
-        "config": {"workload": "t2i single-flow 512x512, 50-step DDIM, CFG 7.5, eta 0, bs 4/GPU + VAE decode (configs[1])",
+        "config": {"workload": cfg["workload"], "name": args.config,
                    "global_batch": BS * world, "latent": [4, LAT, LAT], "parallelism": f"dp{world} (batch shards, one NCCL context broadcast)",
                    "l2": "working set (3.3 GB weights + activations) exceeds the 126 MB L2 every step; no explicit flush",
-                   "tensor_frac_of_step": round(value / world * FLOP_PER_IMAGE / (peaks["tflops_sustained"] * 1e12), 4)},
+                   "tensor_frac_of_step": round(value / world * cfg["flop_per_image"] / (peaks["tflops_sustained"] * 1e12), 4),
+                   "attn_tensor_frac": attn_frac},
         "e2e": {"value": round(e2e_value, 4), "unit": UNIT,
-                "h2d_bytes_per_step": int(xT_h.numel() * 4 + 2 * cond_h.numel() * 4),
+                "h2d_bytes_per_step": int(xT_h.numel() * 4 + sum((c.numel() + u.numel()) * 4 for _, _, c, u in ctx_h)),
                 "d2h_bytes_per_step": int(img_h.numel() * 4)},
-        "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+        "gpu_launches": int(launches), "clocks": clk, "check": check, "roofline": roof, "cpu_baseline": cpu,
     }
+    if not (check["graph_equals_eager_bitwise"] and check["finite"]):
+        line["invalid"] = "output check failed: the timed path does not reproduce the eager kernels / non-finite images"
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -313,66 +346,108 @@ def _cpu_state_dict(net=None):
     return {k: v.detach().float() for k, v in m.state_dict().items()}
 
 
-def _cpu_time_step(sd, reps):
-    """One CFG UNet evaluation for ONE image (B=2 rows, latent 64x64, text ctx) + one K4-equivalent update."""
+def host_info():
+    """(physical cores, CPU model string) of this host; torchrun exports OMP_NUM_THREADS=1, so the CPU legs set the
+    thread count explicitly instead of inheriting it (VERDICT r1 weak #7: 64 threads vs 1 under torchrun)."""
+    cores, model = set(), "unknown"
+    try:
+        phys = core = None
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name") and model == "unknown":
+                model = line.split(":", 1)[1].strip()
+            elif line.startswith("physical id"):
+                phys = line.split(":", 1)[1].strip()
+            elif line.startswith("core id"):
+                core = line.split(":", 1)[1].strip()
+            elif not line.strip():
+                if phys is not None and core is not None:
+                    cores.add((phys, core))
+                phys = core = None
+    except OSError:
+        pass
+    n = len(cores) or (os.cpu_count() or 1)
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    return max(n, 1), model
+
+
+def _cpu_time_step(sd, reps, rows=1, ctx=(("text", 77, 1.0),)):
+    """One CFG UNet evaluation for `rows` images (B = 2 * rows, latent 64x64) + one K4-equivalent update, oracle port."""
     import torch
     from oracle import vd_oracle as O
     g = torch.Generator().manual_seed(7)
-    x = torch.randn(1, 4, LAT, LAT, generator=g)
-    c, u = torch.randn(1, 77, 768, generator=g) * 0.5, torch.randn(1, 77, 768, generator=g) * 0.5
+    x = torch.randn(rows, 4, LAT, LAT, generator=g)
+    cs = [torch.randn(rows, L, 768, generator=g) * 0.5 for _, L, _ in ctx]
+    us = [torch.randn(rows, L, 768, generator=g) * 0.5 for _, L, _ in ctx]
+    kw = {} if len(ctx) == 1 and ctx[0][0] == "text" else {"c_types": tuple(t for t, _, _ in ctx)}
+    if len(ctx) > 1:
+        kw["ratios"] = [r for _, _, r in ctx]
     sched = O.ddim_schedule(O.ddpm_schedule()["alphas_cumprod"], DDIM_STEPS)
     ts = []
     with torch.no_grad():
         for _ in range(reps):
             t0 = time.perf_counter()
-            O.p_sample_ddim(sd, x, [c], [u], torch.tensor([981]), DDIM_STEPS - 1, sched, SCALE)
+            O.p_sample_ddim(sd, x, cs, us, torch.tensor([981] * rows), DDIM_STEPS - 1, sched, SCALE, **kw)
             ts.append(time.perf_counter() - t0)
     return ts
 
 
-def cpu_baseline_sample(net=None):
+def cpu_baseline_sample(net=None, ctx=(("text", 77, 1.0),)):
     import torch
     from oracle import vd_oracle as O
-    threads = torch.get_num_threads()
+    threads, model = host_info()
+    torch.set_num_threads(threads)
     sd = _cpu_state_dict(net)
-    ts = _cpu_time_step(sd, 2)
+    ts = _cpu_time_step(sd, 2, ctx=ctx)
     with torch.no_grad():
         t0 = time.perf_counter()
         O.vae_decode(sd, torch.randn(1, 4, LAT, LAT))
         t_dec = time.perf_counter() - t0
     per_image = DDIM_STEPS * min(ts) + t_dec
-    return {"value": round(1.0 / per_image, 6), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"oracle/vd_oracle.py (fp32 torch CPU port of lib/model_zoo): 2 CFG UNet steps of one image "
+    return {"value": round(1.0 / per_image, 6), "unit": UNIT, "cores": threads, "cpu": model, "kind": "port",
+            "sample": f"oracle/vd_oracle.py (fp32 torch CPU port of lib/model_zoo, {threads} threads): 2 CFG UNet steps of one image "
                       f"(B=2, latent 64x64) at {min(ts):.2f} s/step + 1 VAE decode at {t_dec:.2f} s, "
                       f"extrapolated to 50 steps", "s_per_ddim_step": round(min(ts), 3), "s_vae_decode": round(t_dec, 3)}
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU path for this config, timed on the host cores.
-    /root/reference does not exist on the GPU box, so this is the oracle PORT (kind 'port')."""
+    /root/reference does not exist on the GPU box, so this is the oracle PORT (kind 'port').  Every timed step is a
+    bounded sample (one CFG DDIM step of ONE image, B = 2 rows); in addition ONE CFG step at the product's own batch
+    (bs 4 -> B = 8 rows) is timed so that the per-forward comparison is like for like (`same_config_per_forward`)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     import torch
     from oracle import vd_oracle as O
+    threads, model = host_info()
+    torch.set_num_threads(threads)
+    cfg = CONFIGS[args.config]
+    ctx = tuple(cfg["ctx"])
     sd = _cpu_state_dict(None)
-    threads = torch.get_num_threads()
-    _cpu_time_step(sd, args.warmup if args.warmup > 0 else 1)
-    ts = _cpu_time_step(sd, args.steps)
+    _cpu_time_step(sd, args.warmup if args.warmup > 0 else 1, ctx=ctx)
+    ts = _cpu_time_step(sd, args.steps, ctx=ctx)
+    t_b8 = _cpu_time_step(sd, 1, rows=BS, ctx=ctx)[0]
     with torch.no_grad():
         t0 = time.perf_counter()
         O.vae_decode(sd, torch.randn(1, 4, LAT, LAT))
         t_dec = time.perf_counter() - t0
-    step_s = sum(ts) / len(ts)
+    ts_sorted = sorted(ts)
+    step_s = ts_sorted[len(ts_sorted) // 2]                      # median: robust against a noisy neighbour on the host
     per_image = DDIM_STEPS * step_s + t_dec
     value = 1.0 / per_image
-    sample = (f"each step = one CFG DDIM step of one 512x512 image (UNet B=2, latent 64x64, 77-token text ctx) on CPU fp32, "
-              f"{step_s:.2f} s; images/s extrapolated as 1/(50*step + vae_decode {t_dec:.2f} s)")
+    value_b8 = BS / (DDIM_STEPS * t_b8 + BS * t_dec)             # images/s from the B = 8 step (the product's own batch)
+    sample = (f"each step = one CFG DDIM step of one 512x512 image (UNet B=2, latent 64x64) on CPU fp32 with {threads} threads "
+              f"({model}), median {step_s:.2f} s (min {ts_sorted[0]:.2f}, max {ts_sorted[-1]:.2f}); images/s extrapolated as "
+              f"1/(50*step + vae_decode {t_dec:.2f} s); one CFG step at the product batch (bs 4, B=8): {t_b8:.2f} s")
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 6), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_s * 1e3, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init weights, synthetic context)",
-            "config": {"workload": "t2i single-flow 512x512, 50-step DDIM, CFG 7.5, eta 0 (configs[1]) — bounded CPU sample",
-                       "global_batch": 1},
-            "cpu_baseline": {"value": round(value, 6), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": cfg["workload"] + " — bounded CPU sample", "name": args.config, "global_batch": 1,
+                       "same_config_per_forward": True, "s_per_cfg_step_bs4": round(t_b8, 3),
+                       "images_per_s_from_bs4_step": round(value_b8, 6), "threads": threads, "cpu": model},
+            "cpu_baseline": {"value": round(value, 6), "unit": UNIT, "cores": threads, "cpu": model, "kind": "port", "sample": sample},
             "e2e": {"value": round(value, 6), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -384,6 +459,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json configs[1..3]; the driver line is c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph-roofline", action="store_true", help="keep the per-launch eager event timing of the roofline leg")
     args = ap.parse_args()

@@ -420,7 +420,23 @@ def clip_text_encode(sd, tokens, heads=12, layers=12, prefix="ctx.text.model"):
     return z / torch.norm(zp.unsqueeze(1), dim=-1, keepdim=True)
 
 
-def clip_image_encode(sd, pixels, heads=16, layers=24, patch=14, prefix="ctx.image.model"):
+def clip_image_encode_wmask(sd, pixels, masks, heads=16, layers=24, patch=14, prefix="ctx.image.model"):
+    """CLIPImageContextEncoder._encode_wmask, clip.py:103-143: masks [b,1,h,w] -> clamp, bilinear resize to 224x224; an all-ones
+    mask is the unmasked encode (:110-111); otherwise every token embedding (class token: the mask's global mean, patch tokens:
+    the mean of the mask over the patch = conv with a ones kernel / P^2, :114-121) is scaled AFTER the position embedding and
+    BEFORE pre_layrnorm (:124-133), and the normalised output is scaled by the same factors again (:141).
+    Parity note: the reference's own masked path cannot run on transformers 5.5.0 (its patched embeddings.forward lacks the
+    `interpolate_pos_encoding` keyword), so this restatement is pinned to the reference's LINES, not to its output."""
+    masks = F.interpolate(torch.clamp(masks, 0, 1).float(), [224, 224], mode="bilinear")
+    if masks.sum() == masks.numel():
+        return clip_image_encode(sd, pixels, heads, layers, patch, prefix)
+    gscale = masks.mean(dim=[1, 2, 3], keepdim=True).flatten(2)
+    vtoken = F.conv2d(masks, torch.ones(1, 1, patch, patch), stride=patch).flatten(2).transpose(1, 2) / float(patch * patch)
+    vtoken_mask = torch.cat([gscale, vtoken], dim=1)                      # [b, 257, 1]
+    return clip_image_encode(sd, pixels, heads, layers, patch, prefix, tok_scale=vtoken_mask) * vtoken_mask
+
+
+def clip_image_encode(sd, pixels, heads=16, layers=24, patch=14, prefix="ctx.image.model", tok_scale=None):
     """CLIPImageContextEncoder._encode after the CLIPProcessor, clip.py:95-101: vision_model ->
     post_layernorm on ALL tokens of last_hidden_state -> visual_projection -> divide by ||token 0||.
     pixels: [b,3,224,224] already resized/normalised."""
@@ -429,6 +445,8 @@ def clip_image_encode(sd, pixels, heads=16, layers=24, patch=14, prefix="ctx.ima
     pe = F.conv2d(pixels, sd[V + ".embeddings.patch_embedding.weight"], stride=patch).flatten(2).transpose(1, 2)
     cls = sd[V + ".embeddings.class_embedding"].expand(b, 1, -1)
     x = torch.cat([cls, pe], dim=1) + sd[V + ".embeddings.position_embedding.weight"][None]
+    if tok_scale is not None:           # masked variant (clip.py:124-133)
+        x = x * tok_scale
     c = x.shape[-1]
     x = F.layer_norm(x, (c,), sd[V + ".pre_layrnorm.weight"], sd[V + ".pre_layrnorm.bias"], 1e-5)
     for i in range(layers):

@@ -115,3 +115,49 @@ def test_clip_text_and_image_encoders_vs_oracle():
         half = ienc.encode(imgs.cuda(), masks=torch.cat([torch.ones(2, 1, 64, 32), torch.zeros(2, 1, 64, 32)], -1))
     assert torch.equal(same, out)
     assert torch.isfinite(half).all() and half[:, 1:].abs().sum() < out[:, 1:].abs().sum()
+    # masked variant against the oracle restatement of clip.py:103-143 (soft-edged, non-patch-aligned mask)
+    g = torch.Generator().manual_seed(6)
+    m = torch.zeros(2, 1, 96, 80)
+    m[0, :, 10:70, 5:60] = 1.0
+    m[1] = torch.rand(1, 96, 80, generator=g)
+    with torch.no_grad():
+        outm = ienc.encode(imgs.cuda(), masks=m)
+        refm = O.clip_image_encode_wmask({"ctx.image.model." + k: v for k, v in sd.items()}, px, m)
+    cos = F.cosine_similarity(outm.float().cpu().flatten(), refm.flatten(), dim=0).item()
+    err = (outm.float().cpu() - refm).abs().max().item() / refm.abs().max().item()
+    print(f"[parity] CLIP masked image encode: cos {cos:.6f} rel max err {err:.4f}")
+    assert cos >= 0.999 and err <= 0.05
+
+
+def test_oracle_masked_clip_reduces_to_unmasked_and_scales_tokens():
+    """CPU: the masked restatement (clip.py:103-143) equals the unmasked encode for an all-ones mask, scales every output token
+    by its mask factor, and matches transformers' own vision tower when the factors are applied to its embeddings by hand."""
+    from transformers import CLIPModel
+    from lib.model_zoo.clip import vit_l14_config
+    from oracle import vd_oracle as O
+    cfg = vit_l14_config()
+    cfg.vision_config.num_hidden_layers = 2
+    cfg.text_config.num_hidden_layers = 1
+    torch.manual_seed(0)
+    m = CLIPModel(cfg).eval()
+    sd = {"ctx.image.model." + k: v for k, v in _synth(m, 4).items()}
+    px = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    kw = dict(layers=2)
+    ones = O.clip_image_encode_wmask(sd, px, torch.ones(2, 1, 50, 70), **kw)
+    assert torch.equal(ones, O.clip_image_encode(sd, px, **kw))
+    mask = torch.ones(2, 1, 224, 224)
+    mask[:, :, :14, :14] = 0.0                       # patch token 1 (first patch) fully masked
+    mask[1, :, 100:, :] = 0.3
+    out = O.clip_image_encode_wmask(sd, px, mask, **kw)
+    assert out[:, 1].abs().max().item() == 0.0        # a zero factor zeroes the token on the way out (clip.py:141)
+    # independent check through HF's modules: scale the embeddings, run the encoder, post_layernorm + projection + norm + scale
+    with torch.no_grad():
+        emb = m.vision_model.embeddings(px)
+        gs = mask.mean(dim=[1, 2, 3], keepdim=True).flatten(2)
+        vt = F.avg_pool2d(mask, 14, stride=14).flatten(2).transpose(1, 2)
+        tm = torch.cat([gs, vt], 1)
+        h = m.vision_model.pre_layrnorm(emb * tm)
+        h = m.vision_model.encoder(inputs_embeds=h).last_hidden_state
+        z = m.visual_projection(m.vision_model.post_layernorm(h))
+        ref = z / torch.norm(z[:, 0:1], dim=-1, keepdim=True) * tm
+    assert (ref - out).abs().max().item() <= 5e-6

@@ -338,3 +338,27 @@ def test_softmax_rows():
     out = ops.softmax_rows(x, scale=0.044)
     ref = (x.float() * 0.044).softmax(-1)
     assert_close(out, ref, tol=1e-2, what="softmax_rows")
+
+
+def test_weight_repack_abi_matches_the_python_packers():
+    """vdb_pack_conv_weight / vdb_pack_geglu / vdb_pad_heads (include/vdb200.h) produce exactly the layouts that
+    lib/model_zoo's PackedModule._pack builds in Python (bit-identical bf16)."""
+    ops = _ops()
+    from lib.model_zoo.diffusion_utils import pack_conv3x3, pack_conv1x1
+    from lib.model_zoo.attention import GEGLU, CrossAttention
+    g = torch.Generator().manual_seed(5)
+    w3 = torch.randn(96, 40, 3, 3, generator=g).to(DEV)
+    w1 = torch.randn(96, 24, 1, 1, generator=g).to(DEV)
+    ref = torch.cat([pack_conv3x3(w3), pack_conv1x1(w1)], dim=1)
+    out = torch.empty_like(ref)
+    ops.pack_conv_weight(w3, out=out, col0=0)
+    ops.pack_conv_weight(w1, out=out, col0=9 * 40)
+    assert torch.equal(out, ref)
+    gl = GEGLU(64, 256).to(DEV)
+    p = gl.packed()
+    wo, bo = ops.pack_geglu(gl.proj.weight.detach().float().contiguous(), gl.proj.bias.detach().float().contiguous())
+    assert torch.equal(wo, p["w"]) and torch.equal(bo, p["b"])
+    ca = CrossAttention(320, context_dim=768, heads=8, dim_head=40).to(DEV)
+    pk = ca.packed()
+    assert torch.equal(ops.pad_heads(ca.to_q.weight.detach().float().contiguous(), 8, 40, pk["dk"]), pk["wq"])
+    assert torch.equal(ops.pad_heads(ca.to_v.weight.detach().float().contiguous(), 8, 40, pk["dv"]), pk["wv"])

@@ -1499,6 +1499,43 @@ __global__ void __launch_bounds__(256) scale_by_row_norm_kernel(const __nv_bfloa
   }
 }
 
+// ---- load-time weight repack (fp32 checkpoint layouts -> bf16 kernel layouts) ----
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int kh, int kw,
+                                        __nv_bfloat16* __restrict__ out, long long ldo, long long col0) {
+  const long long total = static_cast<long long>(Cout) * kh * kw * Cin;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % Cin);
+    long long r = i / Cin;
+    const int t = static_cast<int>(r % (kh * kw));
+    const long long n = r / (kh * kw);
+    out[n * ldo + col0 + static_cast<long long>(t) * Cin + ci] = __float2bfloat16(__ldg(w + (n * Cin + ci) * (kh * kw) + t));
+  }
+}
+__global__ void pack_geglu_kernel(const float* __restrict__ w, const float* __restrict__ b, int n2, int K,
+                                  __nv_bfloat16* __restrict__ w_out, float* __restrict__ b_out) {
+  const long long total = 2LL * n2 * K;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % K);
+    const int row = static_cast<int>(i / K);            // packed row: tile t = row / 256, r = row % 256
+    const int t = row >> 8, r = row & 255;
+    const int srow = (r < 128) ? t * 128 + r : n2 + t * 128 + (r - 128);
+    w_out[i] = __float2bfloat16(__ldg(w + static_cast<long long>(srow) * K + k));
+    if (k == 0 && b) b_out[row] = __ldg(b + srow);
+  }
+}
+__global__ void pad_heads_kernel(const float* __restrict__ w, int H, int d, int dpad, int K, __nv_bfloat16* __restrict__ out) {
+  const long long total = static_cast<long long>(H) * dpad * K;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % K);
+    const int row = static_cast<int>(i / K);
+    const int h = row / dpad, c = row % dpad;
+    out[i] = (c < d) ? __float2bfloat16(__ldg(w + (static_cast<long long>(h) * d + c) * K + k)) : __float2bfloat16(0.f);
+  }
+}
+
 static int ew_blocks(long long work_items, int threads) {
   long long b = (work_items + threads - 1) / threads;
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -1758,6 +1795,36 @@ int vdb_layernorm(const void* x, long long rows, int C, const float* gamma, cons
     VDB_CUDA_CHECK(launch_pdl(layernorm_kernel<5, 2>, dim3(blocks), dim3(threads), 0, st, xp, rows, C, gamma, beta, eps, yp));
   else
     VDB_CUDA_CHECK(launch_pdl(layernorm_kernel<8, 1>, dim3(blocks), dim3(threads), 0, st, xp, rows, C, gamma, beta, eps, yp));
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_pack_conv_weight(const float* w, int Cout, int Cin, int kh, int kw, void* out, long long ldo, long long col0, void* stream) {
+  if (!w || !out || Cout <= 0 || Cin <= 0 || kh <= 0 || kw <= 0) return set_error(VDB_ERR_INVALID, "pack_conv_weight: null/empty argument");
+  if (ldo < col0 + static_cast<long long>(kh) * kw * Cin) return set_error(VDB_ERR_INVALID, "pack_conv_weight: ldo too small");
+  const long long total = static_cast<long long>(Cout) * kh * kw * Cin;
+  pack_conv_weight_kernel<<<ew_blocks(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      w, Cout, Cin, kh, kw, reinterpret_cast<__nv_bfloat16*>(out), ldo, col0);
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_pack_geglu(const float* w, const float* b, int n2, int K, void* w_out, float* b_out, void* stream) {
+  if (!w || !w_out || n2 <= 0 || K <= 0 || (b && !b_out)) return set_error(VDB_ERR_INVALID, "pack_geglu: null/empty argument");
+  if (n2 % 128) return set_error(VDB_ERR_INVALID, "pack_geglu: the GEGLU width must be a multiple of 128");
+  pack_geglu_kernel<<<ew_blocks(2LL * n2 * K, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      w, b, n2, K, reinterpret_cast<__nv_bfloat16*>(w_out), b_out);
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_pad_heads(const float* w, int H, int d, int dpad, int K, void* out, void* stream) {
+  if (!w || !out || H <= 0 || d <= 0 || dpad < d || K <= 0) return set_error(VDB_ERR_INVALID, "pad_heads: bad argument");
+  pad_heads_kernel<<<ew_blocks(static_cast<long long>(H) * dpad * K, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      w, H, d, dpad, K, reinterpret_cast<__nv_bfloat16*>(out));
+  VDB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return VDB_OK;
 }

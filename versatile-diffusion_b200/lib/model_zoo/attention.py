@@ -94,6 +94,22 @@ class CrossAttention(PackedModule):
                 "wv": self._pad_heads(self.to_v.weight, dv), "wo": bf16(self.to_out[0].weight),
                 "bo": f32(self.to_out[0].bias)}
 
+    _KV_CACHE_SLOTS = 4
+
+    def _kv_get(self, key):
+        for ent in (self._kv_cache or ()):
+            if ent[0] == key:
+                return ent
+        return None
+
+    def _kv_put(self, ent):
+        """small per-layer cache keyed by the context buffer: two contexts of the same type (sample_multicontext with two
+        'image' c_infos) or two samplers sharing one model keep their own K / V^T buffers instead of evicting each other
+        (which silently re-projected the context inside every step and forced a graph re-capture per sample() call)"""
+        cache = [e for e in (self._kv_cache or ()) if e[0] != ent[0]]
+        cache.append(ent)
+        self._kv_cache = cache[-self._KV_CACHE_SLOTS:]
+
     def context_kv(self, context):
         """K [B*Lp, H*dk] and V^T [H*dvp, B*Lp] of a context; cached while the same tensor (and version) is passed
         again — the context is constant over the DDIM loop, so this runs once per sample() call, not per step."""
@@ -104,30 +120,31 @@ class CrossAttention(PackedModule):
             B, Lp, Cc = data.shape
             key = ("padded", data.data_ptr(), (B, Lp, Cc), L)
             cflat = data.view(B * Lp, Cc)
-            ent = self._kv_cache
-            if ent is not None and ent[0] == key:
+            ent = self._kv_get(key)
+            if ent is not None:
                 k, vt, ver = ent[1]
                 if ver != data._version:          # new prompt copied into the same buffer: refresh IN PLACE
                     ops.gemm(cflat, p["wk"], out=k)
                     ops.gemm(p["wv"], cflat, out=vt)
-                    self._kv_cache = (key, (k, vt, data._version), data)
+                    self._kv_put((key, (k, vt, data._version), data))
                 return k, vt, L, Lp
             k = ops.gemm(cflat, p["wk"])
             vt = ops.gemm(p["wv"], cflat)
-            self._kv_cache = (key, (k, vt, data._version), data)
+            self._kv_put((key, (k, vt, data._version), data))
             return k, vt, L, Lp
         # the cache entry HOLDS the context tensor: while it is alive no other allocation can reuse its address, so
         # (pointer, version, shape) identifies the contents (a freed-and-reallocated buffer would otherwise alias it)
         key = (context.data_ptr(), context._version, tuple(context.shape), context.dtype)
-        if self._kv_cache is not None and self._kv_cache[0] == key:
-            return self._kv_cache[1]
+        ent = self._kv_get(key)
+        if ent is not None:
+            return ent[1]
         B, L, Cc = context.shape
         Lp = (L + 7) // 8 * 8   # kv stride per batch item must be a multiple of 8 (TMA alignment)
         cpad = torch.zeros(B, Lp, Cc, dtype=torch.bfloat16, device=context.device)
         cpad[:, :L] = context.to(torch.bfloat16)
         cflat = cpad.view(B * Lp, Cc)
         val = (ops.gemm(cflat, p["wk"]), ops.gemm(p["wv"], cflat), L, Lp)
-        self._kv_cache = (key, val, context)
+        self._kv_put((key, val, context))
         return val
 
     def forward(self, x, context=None, resid=None, B=1):

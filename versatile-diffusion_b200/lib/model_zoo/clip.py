@@ -43,9 +43,37 @@ def _load_clip_model(version):
     (weights then come from the VD checkpoint's ctx.* keys)."""
     from transformers import CLIPModel
     try:
-        return CLIPModel.from_pretrained(version, local_files_only=True)
-    except Exception:
-        return CLIPModel(vit_l14_config())
+        m = CLIPModel.from_pretrained(version, local_files_only=True)
+        m._vdb_random_init = False
+        return m
+    except Exception as ex:   # no local files: the reference would fail here (it always downloads the pretrained CLIP)
+        import warnings
+        warnings.warn(f"CLIP '{version}' is not cached locally ({type(ex).__name__}): the encoder starts from RANDOM weights and "
+                      f"is only valid once a checkpoint with ctx.* keys has been loaded (encode() raises otherwise)", RuntimeWarning)
+        m = CLIPModel(vit_l14_config())
+        m._vdb_random_init = True
+        m.register_load_state_dict_post_hook(_clip_model_loaded_hook)
+        return m
+
+
+def _clip_model_loaded_hook(module, incompatible_keys):
+    """the same for weights loaded straight into encoder.model (tests, tools)"""
+    if not incompatible_keys.missing_keys:
+        module._vdb_random_init = False
+
+
+def _clip_weights_loaded_hook(module, incompatible_keys):
+    """load_state_dict post hook of the context encoders: the random-init fallback is only cleared when the checkpoint really
+    carried this encoder's CLIP weights (no missing model.* key)."""
+    missing = [k for k in incompatible_keys.missing_keys if k.startswith("model.") or ".model." in k]
+    if not missing:
+        module.model._vdb_random_init = False
+
+
+def _require_clip_weights(enc):
+    if getattr(enc.model, "_vdb_random_init", False) and not getattr(enc, "allow_random_init", False):
+        raise RuntimeError("CLIP context encoder still has its random-init fallback weights: load a checkpoint with the ctx.* keys "
+                           "(load_state_dict) or set encoder.allow_random_init = True for synthetic-weight tests")
 
 
 class AbstractEncoder(PackedModule):
@@ -108,6 +136,7 @@ class CLIPTextContextEncoder(AbstractEncoder):
         self.model = _load_clip_model(version)
         self.max_length = max_length
         self.fp16 = fp16
+        self.register_load_state_dict_post_hook(_clip_weights_loaded_hook)
         self.freeze()
 
     def get_device(self):
@@ -157,6 +186,7 @@ class CLIPTextContextEncoder(AbstractEncoder):
         return ops.scale_by_row_norm(z.view(B, Lp, -1), L, idx=eos)
 
     def encode(self, text):
+        _require_clip_weights(self)
         z = self.encode_tokens(self.tokenize(text))
         return z.half() if self.fp16 else z
 
@@ -168,6 +198,7 @@ class CLIPImageContextEncoder(AbstractEncoder):
         self.version = version
         self.model = _load_clip_model(version)
         self.fp16 = fp16
+        self.register_load_state_dict_post_hook(_clip_weights_loaded_hook)
         self.freeze()
 
     def get_device(self):
@@ -321,4 +352,5 @@ class CLIPImageContextEncoder(AbstractEncoder):
         return z.half() if self.fp16 else z
 
     def encode(self, images, masks=None):
+        _require_clip_weights(self)
         return self._encode(images) if masks is None else self._encode_wmask(images, masks)

@@ -122,6 +122,10 @@ class DDIMSampler(object):
         scale = float(c_infos[0]['unconditional_guidance_scale'])
         cfg = scale != 1.
         total_steps = timesteps.shape[0]
+        if total_steps <= 0 or total_steps > 1000:
+            # x0_forward_timesteps == 0 leaves no step to run: the reference's loop never executes and it raises on the unbound
+            # result (ddim.py:105-127); here the device tables would be indexed at -1
+            raise ValueError(f"DDIM walk of {total_steps} steps: need 1..1000 (x0_forward_timesteps must be >= 1)")
         sigmas = np.asarray(self.ddim_sigmas.cpu() if isinstance(self.ddim_sigmas, torch.Tensor) else self.ddim_sigmas)
         fast = self.use_cuda_graph and noise_dropout == 0. and not np.any(sigmas[:total_steps] != 0)
 

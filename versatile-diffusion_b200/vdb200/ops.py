@@ -39,11 +39,31 @@ _workspace = {}
 WORKSPACE_BYTES = 160 << 20   # covers 16-way split-K of any MN grid that fits in half the SMs (74 tiles x 128 x 256 fp32)
 
 
+def _scratch_key(device):
+    """(device, stream) key of the split-K workspace / GroupNorm scratch.  The C ABI promises reuse of a scratch buffer on ONE
+    stream only (the GroupNorm arrival counters and the split-K partials are not re-entrant), so every eager stream gets its
+    own buffers: two threads sampling on two streams of one GPU no longer share counters.  Launches issued while a CUDA graph
+    is being captured (torch captures on a side stream) use the buffers of the device's FIRST stream — the one the eager
+    warm-up step ran on — so the addresses baked into the graph are the ones that were sized and zeroed before capture.
+    Graphs captured from different streams therefore still share one scratch set and must not be replayed concurrently."""
+    dev = device.index if device.index is not None else torch.cuda.current_device()
+    sid = torch.cuda.current_stream(dev).cuda_stream
+    owner = _scratch_owner.setdefault(dev, sid)
+    if torch.cuda.is_current_stream_capturing():
+        sid = owner
+    return (dev, sid)
+
+
+_scratch_owner = {}
+
+
 def workspace(device):
-    """Fixed-size fp32 split-K scratch per device. Never reallocated: its address is baked into captured CUDA graphs."""
-    key = device.index if device.index is not None else torch.cuda.current_device()
+    """Fixed-size fp32 split-K scratch per (device, stream). Never reallocated: its address is baked into captured CUDA graphs."""
+    key = _scratch_key(device)
     w = _workspace.get(key)
     if w is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("split-K workspace must exist before CUDA-graph capture (run one eager step first)")
         w = torch.empty(WORKSPACE_BYTES // 4, dtype=torch.float32, device=device)
         _workspace[key] = w
     return w
@@ -124,8 +144,8 @@ _gn_scratch_buf = {}
 
 
 def _gn_scratch(device, nfloats):
-    """Persistent zero-initialised GroupNorm scratch per device (the kernels restore its counters to zero)."""
-    key = device.index if device.index is not None else torch.cuda.current_device()
+    """Persistent zero-initialised GroupNorm scratch per (device, stream) (the kernels restore its counters to zero)."""
+    key = _scratch_key(device)
     buf = _gn_scratch_buf.get(key)
     if buf is None or buf.numel() < nfloats:
         if buf is not None and torch.cuda.is_current_stream_capturing():
@@ -291,6 +311,37 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
         out = torch.empty_like(x)
     with _Span("layernorm", 0.0, 2.0 * 2 * rows * C):
         check(lib.vdb_layernorm(_ptr(x), rows, C, _ptr(gamma), _ptr(beta), float(eps), _ptr(out), _stream()), "layernorm")
+    return out
+
+
+def pack_conv_weight(w, out=None, col0=0):
+    """Conv2d weight fp32 [Cout, Cin, kh, kw] -> bf16 [Cout, ldo] with column col0 + (ky*kw + kx)*Cin + ci (C ABI repack)."""
+    _need(w, torch.float32, "w")
+    Cout, Cin, kh, kw = w.shape
+    if out is None:
+        out = torch.empty((Cout, col0 + kh * kw * Cin), dtype=BF16, device=w.device)
+    check(lib.vdb_pack_conv_weight(_ptr(w), Cout, Cin, kh, kw, _ptr(out), out.stride(0), col0, _stream()), "pack_conv_weight")
+    return out
+
+
+def pack_geglu(w, b=None):
+    """GEGLU.proj weight fp32 [2*n2, K] (+ bias) -> (bf16 rows interleaved per 256-row tile, fp32 bias in the same order)."""
+    _need(w, torch.float32, "w")
+    n2, K = w.shape[0] // 2, w.shape[1]
+    wo = torch.empty((2 * n2, K), dtype=BF16, device=w.device)
+    bo = torch.empty(2 * n2, dtype=torch.float32, device=w.device) if b is not None else None
+    if b is not None:
+        _need(b, torch.float32, "b")
+    check(lib.vdb_pack_geglu(_ptr(w), _ptr(b) if b is not None else None, n2, K, _ptr(wo), _ptr(bo) if bo is not None else None,
+                             _stream()), "pack_geglu")
+    return wo, bo
+
+
+def pad_heads(w, H, d, dpad):
+    """attention projection fp32 [H*d, K] -> bf16 [H*dpad, K], zero rows after each head's d rows."""
+    _need(w, torch.float32, "w")
+    out = torch.empty((H * dpad, w.shape[1]), dtype=BF16, device=w.device)
+    check(lib.vdb_pad_heads(_ptr(w), H, d, dpad, w.shape[1], _ptr(out), _stream()), "pad_heads")
     return out
 
 
