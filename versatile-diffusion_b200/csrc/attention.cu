@@ -798,7 +798,7 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
   const int head = blockIdx.y;
   const int b = blockIdx.z;
   const int ntiles = (p.Nk + BKV - 1) / BKV;
-  const int ksteps = min(4, (p.dv + 15) >> 4);     // K16 steps of QK^T that hold non-zero channels
+  constexpr int KS = (DVP + 15) / 16;              // K16 steps of QK^T that can hold non-zero channels (d_head <= DVP)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmQ);
@@ -857,50 +857,54 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
         tc_fence_after();
         const uint64_t qd = make_desc_sw128(smem_u32(sQ + g * kQBytes));
         const uint64_t kd = make_desc_sw128(smem_u32(sK + st * kKBytes));
-        for (int k = 0; k < ksteps; ++k) umma_bf16_ss(tmem_base + g * 128, qd + 2 * k, kd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < KS; ++k) umma_bf16_ss(tmem_base + g * 128, qd + 2 * k, kd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
         if (g == 1) umma_commit(&k_empty[st]);
         umma_commit(&s_full[g]);
+      };
+      // Issue order (steady state): PV_0(j), S_1(j+1), PV_1(j), S_0(j+2), ...  Every S product is queued half a cycle
+      // after the s_free arrival it depends on (the group loaded its previous scores long ago), so the only wait of this
+      // thread that can block is p_full.  (First version: PV_g(j) was followed by a wait for s_free_g(j+1), i.e. for the
+      // group to fetch its NEXT scores, ~0.25 us during which the other group's finished P tile sat unserved; ncu showed the
+      // softmax warps spending 37 % of their time waiting for pv_done: profiles/r02_ncu_attention_fa_v1.txt.)
+      auto issue_PV = [&](int g, int j) {
+        const int st = j % KV_STAGES;
+        mbar_wait(&p_full[g], j & 1);                  // P_g(j) written, O_g rescaled
+        mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const uint64_t vd = make_desc_sw128(smem_u32(sV + st * kVBytes + a * kVAtom));
+          if constexpr (PT) {
+            // P_g(j) in tensor memory: 128 lanes x 64 packed columns at [384 + 64 g, ..); a K16 step reads 8 columns
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ts(tmem_base + 256 + g * 64, tmem_base + 384 + g * 64 + a * 32 + k * 8, vd + 2 * k, idesc_o,
+                           (j > 0 || a > 0 || k > 0) ? 1u : 0u);
+          } else {
+            const uint64_t pd = make_desc_sw128(smem_u32(sP + g * kPBytes + a * kBQ * 128));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss(tmem_base + 256 + g * 64, pd + 2 * k, vd + 2 * k, idesc_o, (j > 0 || a > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        if (g == 1) umma_commit(&v_empty[st]);
+        umma_commit(&pv_done[g]);
+      };
+      auto next_S = [&](int g, int j) {                // S_g(j) once the group holds S_g(j-1) in registers
+        mbar_wait(&s_free[g], (j - 1) & 1);
+        tc_fence_after();
+        issue_S(g, j);
       };
       mbar_wait(q_full, 0);
       issue_S(0, 0);
       issue_S(1, 0);
-      if (ntiles > 1) {
-        for (int g = 0; g < 2; ++g) {
-          mbar_wait(&s_free[g], 0);                    // S_g(0) is in the group's registers
-          tc_fence_after();
-          issue_S(g, 1);
-        }
-      }
+      if (ntiles > 1) next_S(0, 1);
       for (int j = 0; j < ntiles; ++j) {
-        const int st = j % KV_STAGES;
-        for (int g = 0; g < 2; ++g) {
-          mbar_wait(&p_full[g], j & 1);                // P_g(j) written, O_g rescaled
-          mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int a = 0; a < 2; ++a) {
-            const uint64_t vd = make_desc_sw128(smem_u32(sV + st * kVBytes + a * kVAtom));
-            if constexpr (PT) {
-              // P_g(j) in tensor memory: 128 lanes x 64 packed columns at [384 + 64 g, ..); a K16 step reads 8 columns
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16_ts(tmem_base + 256 + g * 64, tmem_base + 384 + g * 64 + a * 32 + k * 8, vd + 2 * k, idesc_o,
-                             (j > 0 || a > 0 || k > 0) ? 1u : 0u);
-            } else {
-              const uint64_t pd = make_desc_sw128(smem_u32(sP + g * kPBytes + a * kBQ * 128));
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16_ss(tmem_base + 256 + g * 64, pd + 2 * k, vd + 2 * k, idesc_o, (j > 0 || a > 0 || k > 0) ? 1u : 0u);
-            }
-          }
-          if (g == 1) umma_commit(&v_empty[st]);
-          umma_commit(&pv_done[g]);
-          if (j + 2 < ntiles) {
-            mbar_wait(&s_free[g], (j + 1) & 1);        // S_g(j+1) is in registers: its buffer may take S_g(j+2)
-            tc_fence_after();
-            issue_S(g, j + 2);
-          }
-        }
+        issue_PV(0, j);
+        if (j + 1 < ntiles) next_S(1, j + 1);
+        issue_PV(1, j);
+        if (j + 2 < ntiles) next_S(0, j + 2);
       }
     }
   }
