@@ -24,6 +24,11 @@ VARIANTS = [
     ({"VDB_PAIR": "1"}, "gemm or conv3x3"),        # CTA pairs (cta_group::2)                              (validated, round 1)
     ({"VDB_NFAST": "2"}, "gemm or conv3x3"),       # N-fast tile order wherever it is legal                (NOT yet run on a GPU)
     ({"VDB_IGEMM_SPEC": "0"}, "gemm or conv3x3"),  # generic epilogue only
+    ({"VDB_EPI_TMA": "0"}, "gemm or conv3x3"),     # transposing epilogues instead of the TMA-store ones (round-1 default)
+    ({"VDB_GN_BUNDLE": "0"}, "groupnorm"),         # single-launch pixel-range GroupNorm instead of the group-bundle kernel
+    ({"VDB_LN_RG": "0"}, "layernorm"),             # warp-per-row LayerNorm instead of the row-group kernel
+    ({"VDB_ATT_FA": "0"}, "attention"),            # column-split attention kernel for every shape (round-1 default)
+    ({"VDB_ATT_FA": "111"}, "attention"),          # two-tile kernel with P through shared memory (SS product)
 ]
 
 RUN = pytest.mark.skipif(os.environ.get("VDB_TEST_VARIANTS") != "1", reason="set VDB_TEST_VARIANTS=1 to run the opt-in kernel variants")

@@ -715,6 +715,12 @@ __global__ void __launch_bounds__(64 + 256 * G, 1) attention_pp_kernel(const __g
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
+#ifdef VDB_TIMELINE   // two-tile kernel: 24 slots per kv tile (tools/attention_fa_timeline.py)
+#define VDB_FTL(slot, j, who) do { if (p.timeline && (who) && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (j) < 16) p.timeline[(j) * 24 + (slot)] = gtime(); } while (0)
+#else
+#define VDB_FTL(slot, j, who) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Two-tile kernel for long, unmasked-or-tail-masked contexts at d_head <= 64 (round 2; default for self-attention at
 // the 64x64 / 32x32 ... levels where d_head = 40).  Built from the round-1 role timeline: the column-split kernel above
@@ -870,6 +876,7 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
       auto issue_PV = [&](int g, int j) {
         const int st = j % KV_STAGES;
         mbar_wait(&p_full[g], j & 1);                  // P_g(j) written, O_g rescaled
+        VDB_FTL(16 + 3 * g, j, true);
         mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
         tc_fence_after();
 #pragma unroll
@@ -890,11 +897,13 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
         }
         if (g == 1) umma_commit(&v_empty[st]);
         umma_commit(&pv_done[g]);
+        VDB_FTL(17 + 3 * g, j, true);
       };
       auto next_S = [&](int g, int j) {                // S_g(j) once the group holds S_g(j-1) in registers
         mbar_wait(&s_free[g], (j - 1) & 1);
         tc_fence_after();
         issue_S(g, j);
+        VDB_FTL(18 + 3 * g, j - 1, true);              // (slot of the tile during which it was issued)
       };
       mbar_wait(q_full, 0);
       issue_S(0, 0);
@@ -928,9 +937,13 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
     float m_ref = -INFINITY;
     float l_sum = 0.f;
     const uint32_t prow = smem_u32(sP + g * kPBytes + r * 128);   // 32-bit shared address: STS, no generic address math
+    const bool tlw = (quarter == 0) && (lane == 0);   // (debug timeline: first warp of each group)
+    (void)tlw;
     for (int j = 0; j < ntiles; ++j) {
+      VDB_FTL(8 * g + 7, j, tlw);
       mbar_wait(&s_full[g], j & 1);
       tc_fence_after();
+      VDB_FTL(8 * g + 0, j, tlw);
       uint32_t keep[BKV];
       {
         uint32_t v0[32], v1[32], v2[32], v3[32];
@@ -945,6 +958,7 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[g]);     // the MMA warp may overwrite S with the next tile's scores
+      VDB_FTL(8 * g + 1, j, tlw);
       const int kv0 = j * BKV;
       const bool need_mask = kv0 + BKV > p.Nk;
       float mx;
@@ -980,9 +994,11 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
       }
       const float m_scaled = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;
       // PV_g(j-1) must have retired: it reads the group's only P buffer and accumulates into O
+      VDB_FTL(8 * g + 2, j, tlw);
       if (j > 0) {
         mbar_wait(&pv_done[g], (j - 1) & 1);
         tc_fence_after();
+        VDB_FTL(8 * g + 3, j, tlw);
         if (rescale) {
 #pragma unroll 1
           for (int c = 0; c < OCH; ++c) {
@@ -997,6 +1013,7 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
         }
       }
       token_wait();
+      VDB_FTL(8 * g + 4, j, tlw);
       {
         const unsigned long long sc2 = pack_f2(p.scale_log2, p.scale_log2), nm2 = pack_f2(-m_scaled, -m_scaled);
         unsigned long long l2 = pack_f2(0.f, 0.f), l2b = pack_f2(0.f, 0.f);
@@ -1019,6 +1036,11 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
             }
             if (i & 2) l2b = add_f2(l2b, pack_f2(e[i], e[i + 1])); else l2 = add_f2(l2, pack_f2(e[i], e[i + 1]));
           }
+          // TOKEN 2 / 3: hand the MUFU token over after 3/4 / 1/2 of the tile's exponentials have been issued: the next
+          // group's ramp-up (barrier latency, first scale FFMAs) then overlaps this group's tail instead of idling the pipe
+          if constexpr (TOKEN >= 2) {
+            if (q == (TOKEN == 2 ? 11 : 7) && !(j == ntiles - 1 && g == 1)) token_pass();
+          }
           if constexpr (PT) {
             // packed bf16 pairs -> 32-bit tensor-memory columns [4 q, 4 q + 4) of this lane's P row; stored 32 columns at a time
 #pragma unroll
@@ -1034,11 +1056,15 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
         unpack_f2(add_f2(l2, l2b), la, lb);
         l_sum += la + lb;
       }
-      if (!(j == ntiles - 1 && g == 1)) token_pass();   // (the ring is primed once: skip the one surplus hand-over)
+      VDB_FTL(8 * g + 5, j, tlw);
+      if constexpr (TOKEN == 1) {
+        if (!(j == ntiles - 1 && g == 1)) token_pass();   // (the ring is primed once: skip the one surplus hand-over)
+      }
       if constexpr (PT) tmem_wait_st(); else fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[g]);
+      VDB_FTL(8 * g + 6, j, tlw);
     }
     mbar_wait(&pv_done[g], (ntiles - 1) & 1);
     tc_fence_after();
@@ -1148,23 +1174,22 @@ static int launch_attention_fa(AttnParams& p, const AttnArgs& a, cudaStream_t st
   return VDB_OK;
 }
 
+template <int DVP, int PT, int TOKEN>
+static int dispatch_attention_fa3(int poly, AttnParams& p, const AttnArgs& a, cudaStream_t st) {
+  switch (poly) {
+    case 0: return launch_attention_fa<DVP, 3, 0, TOKEN, PT>(p, a, st);
+    case 2: return launch_attention_fa<DVP, 3, 2, TOKEN, PT>(p, a, st);
+    case 3: return launch_attention_fa<DVP, 3, 3, TOKEN, PT>(p, a, st);
+    default: return launch_attention_fa<DVP, 3, 1, TOKEN, PT>(p, a, st);
+  }
+}
 template <int DVP, int PT>
 static int dispatch_attention_fa2(int poly, int token, AttnParams& p, const AttnArgs& a, cudaStream_t st) {
-  if (token) {
-    switch (poly) {
-      case 0: return launch_attention_fa<DVP, 3, 0, 1, PT>(p, a, st);
-      case 1: return launch_attention_fa<DVP, 3, 1, 1, PT>(p, a, st);
-      case 3: return launch_attention_fa<DVP, 3, 3, 1, PT>(p, a, st);
-      case 4: return launch_attention_fa<DVP, 3, 4, 1, PT>(p, a, st);
-      default: return launch_attention_fa<DVP, 3, 2, 1, PT>(p, a, st);
-    }
-  }
-  switch (poly) {
-    case 0: return launch_attention_fa<DVP, 3, 0, 0, PT>(p, a, st);
-    case 1: return launch_attention_fa<DVP, 3, 1, 0, PT>(p, a, st);
-    case 3: return launch_attention_fa<DVP, 3, 3, 0, PT>(p, a, st);
-    case 4: return launch_attention_fa<DVP, 3, 4, 0, PT>(p, a, st);
-    default: return launch_attention_fa<DVP, 3, 2, 0, PT>(p, a, st);
+  switch (token) {
+    case 0: return dispatch_attention_fa3<DVP, PT, 0>(poly, p, a, st);
+    case 2: return dispatch_attention_fa3<DVP, PT, 2>(poly, p, a, st);
+    case 3: return dispatch_attention_fa3<DVP, PT, 3>(poly, p, a, st);
+    default: return dispatch_attention_fa3<DVP, PT, 1>(poly, p, a, st);
   }
 }
 template <int DVP>
@@ -1234,7 +1259,7 @@ int vdb_attention_bf16(const void* Q, long long ldq, int q_col0, const void* K, 
     if (DVP == 64) return pp == 2 ? launch_attention_pp<64, 2, 4>(p, a, st) : launch_attention_pp<64, 3, 4>(p, a, st);
   }
   // VDB_ATT_FA: the two-tile kernel (attention_fa_kernel).  0 = off; otherwise digits "[S]PT": P = exp2 pairs of every 8 on
-  // the FMA pipe (0..4), T = 1 strict MUFU turns (token) / 0 free-running, leading 1 = P through shared memory (SS product)
+  // the FMA pipe (0..4), T = MUFU token: 0 free-running, 1 passed at the end of a tile's exp2 phase, 2 / 3 after 3/4 / 1/2 of it, leading 1 = P through shared memory (SS product)
   // instead of tensor memory.  e.g. 21 = two of eight pairs, token, P in tensor memory; 121 = the same with P in shared memory.
   static const int fa = [] { const char* e = getenv("VDB_ATT_FA"); return e ? atoi(e) : -1; }();
   if (fa != 0 && !pp && DK == 64 && !causal && Nk >= 512 && Nq >= 256 && (Nq % 256) == 0) {

@@ -51,7 +51,7 @@ static EncodeTiledFn get_encode() {
 }
 
 static int encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                  const cuuint32_t* box) {
+                  const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode();
   if (!fn) return set_error(2, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   if (reinterpret_cast<uintptr_t>(ptr) & 15) return set_error(1, "tensor map: base pointer must be 16-byte aligned");
@@ -59,7 +59,7 @@ static int encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* d
   for (int i = 0; i < rank - 1; ++i)
     if (strides[i] % 16) return set_error(1, "tensor map: stride %d (%llu B) not a multiple of 16", i, (unsigned long long)strides[i]);
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(2, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)", (int)r, rank,
@@ -82,6 +82,16 @@ int make_tmap_4d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint
   cuuint64_t strides[3] = {stride1, stride2, stride3};
   cuuint32_t box[4] = {box0, box1, box2, box3};
   return encode(m, ptr, 4, dims, strides, box);
+}
+
+// store-side map of an epilogue staging tile: 32 bf16 columns (64 B) x 32 rows, SWIZZLE_64B
+int make_tmap_4d_sw64(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
+                      uint64_t stride1, uint64_t stride2, uint64_t stride3, uint32_t box0, uint32_t box1, uint32_t box2,
+                      uint32_t box3) {
+  cuuint64_t dims[4] = {d0, d1, d2, d3};
+  cuuint64_t strides[3] = {stride1, stride2, stride3};
+  cuuint32_t box[4] = {box0, box1, box2, box3};
+  return encode(m, ptr, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 }  // namespace vdb

@@ -30,6 +30,10 @@ int make_tmap_4d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint
                  uint64_t stride1, uint64_t stride2, uint64_t stride3, uint32_t box0, uint32_t box1,
                  uint32_t box2, uint32_t box3);
 
+int make_tmap_4d_sw64(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
+                      uint64_t stride1, uint64_t stride2, uint64_t stride3, uint32_t box0, uint32_t box1,
+                      uint32_t box2, uint32_t box3);   // SWIZZLE_64B (epilogue store tiles: 64-byte rows)
+
 // Ask for the maximum shared-memory carveout for a kernel (once).  The tcgen05 kernels need ~230 KB of shared memory;
 // if the small kernels between them ran with a different L1/shared split the SMs would have to be reconfigured (which
 // needs them idle) at every transition of the ~470-kernel step.  Measured: no effect on the step time, so this is

@@ -39,6 +39,7 @@ struct ASeg {
 struct alignas(64) IgemmParams {
   CUtensorMap tmA[kMaxA];  // 4D (C, W, H, B) bf16, box (64, TW, TH, TB), SWIZZLE_128B
   CUtensorMap tmB;         // 2D (Ktot, N) bf16, box (64, BN), SWIZZLE_128B (CTA-pair launches: box (64, BN/2))
+  CUtensorMap tmO;         // TMA-store epilogues: 4D (N, Wo, Ho, Bo) bf16 output, box (32, bw, bh, bb) = one warp's 32 x 32 chunk, SWIZZLE_64B
   ASeg seg[kMaxSeg];
   int nseg;
   int kb_total;      // total k-blocks over all segments
@@ -128,13 +129,14 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + STAGES * kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  float* sstage = reinterpret_cast<float*>(smem + STAGES * kStageBytes);   // kNumEpiWarps x 4 KB, 1024-byte aligned: [32][32] fp32
+                                                                           // transposition tiles, or 2 x 2 KB bf16 TMA-store tiles
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes + EW * 4096);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* sbias = reinterpret_cast<float*>(tmem_holder + 4);   // [BN] bias of the current output tile
-  float* sstage = sbias + BN;                                  // kNumEpiWarps x [32][32] fp32 swizzled transposition tiles
   auto epi_bar_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory"); };   // the epilogue warps only
 
   const int warp = threadIdx.x >> 5;
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kMaxA; ++i) tma_prefetch_desc(&p.tmA[i]);
     tma_prefetch_desc(&p.tmB);
+    if constexpr (MODE >= 3) tma_prefetch_desc(&p.tmO);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -292,6 +295,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
       o[0] = x0.x; o[1] = x0.y; o[2] = x0.z; o[3] = x0.w; o[4] = x1.x; o[5] = x1.y; o[6] = x1.z; o[7] = x1.w;
     };
     int it = 0;
+    int st_buf = 0;                     // TMA-store epilogues: which of this warp's two staging tiles is written next
+    (void)st_buf;
     const float* sbias_src = nullptr;   // which bias row/offset currently sits in sbias
     const uint32_t leader_tmem_empty[2] = {(CTAS == 2) ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u,
                                            (CTAS == 2) ? mapa_u32(smem_u32(&tmem_empty[1]), 0) : 0u};
@@ -422,7 +427,98 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
           __syncwarp();
         }
       };
-      if constexpr (MODE == 1) {
+      if constexpr (MODE == 3 || MODE == 4) {
+        // ---- TMA-store epilogues (round 2).  Everything stays in the tcgen05.ld layout (one ROW of 32 columns per thread):
+        // bias from shared memory (broadcast reads), residual as this row's own 64 contiguous bytes, bf16 pack, four 16-byte
+        // shared-memory stores into this warp's 32 x 32 staging tile (64-byte rows, SWIZZLE_64B pattern: conflict-free),
+        // then ONE thread hands the tile to the TMA unit (cp.async.bulk.tensor store; out-of-range rows / columns are clipped by
+        // the tensor map).  Against the fp32 transposition above this halves the shared-memory traffic of the epilogue
+        // (2 x 64 B instead of 2 x 128 B per row and chunk) and removes the 8 global-store instructions per thread and chunk —
+        // the K <= 640 GEMMs were bound by exactly that (profiles/r01_ncu_hot_lines_v7.txt).  Two staging tiles per warp:
+        // the store of chunk i is read out while chunk i+1 is built.
+        uint8_t* stg = reinterpret_cast<uint8_t*>(sstage) + (warp - 2) * 4096;
+        const int qrow = quarter * 32;                                   // first tile row of this warp's TMEM lane quarter
+        const int ow = wt * p.TW + (qrow % p.TW), oh = ht * p.TH + ((qrow / p.TW) % p.TH), ob = bt * p.TB + qrow / (p.TW * p.TH);
+        constexpr int OUTC = (MODE == 4) ? BN / 2 : BN;                  // output columns per tile
+        const int ochunks = (MODE == 4) ? OUTC / 32 : f_nchunks;
+        const int ocol0 = n_idx * OUTC;
+        const int o_first = (((OUTC / 32) % kWPQ) != 0) ? ((half + it) % kWPQ) : half;
+        auto load_resid_row = [&](int c, uint4 (&rr)[4]) {
+          const uint4* src = reinterpret_cast<const uint4*>(p.resid + static_cast<long long>(gp) * p.ldr + ocol0 + c * 32);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) rr[k] = __ldg(src + k);
+        };
+        uint4 rr[4];
+        const bool do_resid = (MODE == 3) && has_resid && row_ok;
+        if (do_resid && o_first < ochunks) load_resid_row(o_first, rr);
+#pragma unroll 1
+        for (int c = o_first; c < ochunks; c += kWPQ) {
+          float o[32];
+          if constexpr (MODE == 4) {
+            uint32_t va[32], vg[32];
+            tmem_ld32(trow + c * 32, va);
+            tmem_ld32(trow + OUTC + c * 32, vg);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 ba = p.bias ? *reinterpret_cast<const float4*>(sbias + c * 32 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4 bg = p.bias ? *reinterpret_cast<const float4*>(sbias + OUTC + c * 32 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              o[j] = (__uint_as_float(va[j]) + ba.x) * gelu_fast_f(__uint_as_float(vg[j]) + bg.x);
+              o[j + 1] = (__uint_as_float(va[j + 1]) + ba.y) * gelu_fast_f(__uint_as_float(vg[j + 1]) + bg.y);
+              o[j + 2] = (__uint_as_float(va[j + 2]) + ba.z) * gelu_fast_f(__uint_as_float(vg[j + 2]) + bg.z);
+              o[j + 3] = (__uint_as_float(va[j + 3]) + ba.w) * gelu_fast_f(__uint_as_float(vg[j + 3]) + bg.w);
+            }
+          } else {
+            uint32_t v[32];
+            tmem_ld32(trow + c * 32, v);
+            uint4 rn[4];
+            const bool more = c + kWPQ < ochunks;
+            if (do_resid && more) load_resid_row(c + kWPQ, rn);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = p.bias ? *reinterpret_cast<const float4*>(sbias + c * 32 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              o[j] = __uint_as_float(v[j]) + bb.x; o[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
+              o[j + 2] = __uint_as_float(v[j + 2]) + bb.z; o[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
+            }
+            if (do_resid) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t w4[4] = {rr[k].x, rr[k].y, rr[k].z, rr[k].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 x = unpack_bf16x2(w4[q]);
+                  o[k * 8 + 2 * q] += x.x;
+                  o[k * 8 + 2 * q + 1] += x.y;
+                }
+              }
+              if (more) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) rr[k] = rn[k];
+              }
+            }
+          }
+          // the staging tile about to be rewritten was handed to the TMA unit two chunks ago: wait until it has been read
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          uint8_t* tile = stg + st_buf * 2048;
+          const uint32_t trow_s = smem_u32(tile) + lane * 64;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(trow_s + ((q ^ ((lane >> 1) & 3)) << 4)),
+                         "r"(pack_bf16x2(o[q * 8], o[q * 8 + 1])), "r"(pack_bf16x2(o[q * 8 + 2], o[q * 8 + 3])),
+                         "r"(pack_bf16x2(o[q * 8 + 4], o[q * 8 + 5])), "r"(pack_bf16x2(o[q * 8 + 6], o[q * 8 + 7]))
+                         : "memory");
+          }
+          fence_proxy_async_smem();      // every writer: generic-proxy stores -> visible to the TMA (async proxy) read
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&p.tmO, tile, ocol0 + c * 32, ow, oh, ob);
+            bulk_commit();
+          }
+          st_buf ^= 1;
+        }
+      } else if constexpr (MODE == 1) {
         // lean fast path: every chunk is a full 32-column bf16 chunk with one bias row; the residual rows of the
         // next chunk are requested before this chunk is processed (their first use otherwise exposes ~1 us)
         uint4 rr[4];
@@ -593,6 +689,9 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
         if constexpr (CTAS == 2) mbar_arrive_cluster(leader_tmem_empty[as]);   // the MMA issuer lives in rank 0
         else mbar_arrive(&tmem_empty[as]);
       }
+    }
+    if constexpr (MODE >= 3) {
+      if (lane == 0) bulk_wait<0>();     // every TMA store of this thread has completed before the CTA may exit
     }
   }
 
@@ -773,12 +872,34 @@ static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot
     if (e.act == ACT_GEGLU && BN == 256) mode = 2;
     else if (e.act == ACT_NONE && e.alpha == 1.f && (N % 32) == 0) mode = 1;
   }
+  // TMA-store epilogues (modes 3 / 4 = modes 1 / 2 with the output tile leaving through shared memory + cp.async.bulk.tensor;
+  // VDB_EPI_TMA=0 keeps the transposing epilogues): the warp's 32 rows x 32 columns must be one box of the output tensor map
+  static const int epi_tma = [] { const char* ev = getenv("VDB_EPI_TMA"); return (ev && ev[0] == '0') ? 0 : 1; }();
+  if (epi_tma && (mode == 1 || mode == 2) && (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 &&
+      (!e.resid || (reinterpret_cast<uintptr_t>(e.resid) & 15) == 0)) {
+    const int bw = std::min(p.TW, 32), bh = std::min(p.TH, 32 / bw), bb = 32 / (bw * bh);
+    const long long ncols = (mode == 2) ? N / 2 : N;
+    if (bb <= p.TB &&
+        make_tmap_4d_sw64(&p.tmO, e.out, static_cast<uint64_t>(ncols), static_cast<uint64_t>(p.Wo), static_cast<uint64_t>(p.Ho),
+                          static_cast<uint64_t>(p.Bo), static_cast<uint64_t>(e.ldo) * 2, static_cast<uint64_t>(p.Wo) * e.ldo * 2,
+                          static_cast<uint64_t>(p.Ho) * p.Wo * e.ldo * 2, 32, bw, bh, bb) == 0)
+      mode += 2;
+  }
   if (pair) {
     ++g_pair_launches;
     switch (BN) {
       case 128: rc = launch_igemm<128, 7, 2, 8, 0>(p, num_tiles / 2, stream); break;
       case 160: rc = launch_igemm<160, 7, 2, 8, 0>(p, num_tiles / 2, stream); break;
       default: rc = launch_igemm<256, 6, 2, 8, 0>(p, num_tiles / 2, stream); break;
+    }
+  } else if (mode == 4) {
+    rc = launch_igemm<256, 4, 1, 8, 4>(p, num_tiles, stream);
+  } else if (mode == 3) {
+    switch (BN) {
+      case 64: rc = launch_igemm<64, 8, 1, 8, 3>(p, num_tiles, stream); break;
+      case 128: rc = launch_igemm<128, 6, 1, 8, 3>(p, num_tiles, stream); break;
+      case 160: rc = launch_igemm<160, 5, 1, 8, 3>(p, num_tiles, stream); break;
+      default: rc = launch_igemm<256, 4, 1, 8, 3>(p, num_tiles, stream); break;
     }
   } else if (mode == 2) {
     rc = launch_igemm<256, 4, 1, 8, 2>(p, num_tiles, stream);
