@@ -172,7 +172,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, one elected lane per tcgen05 instruction (see umma_bf16_ss_w)
       constexpr uint32_t idesc_s = make_idesc_bf16(kBQ, kBKV);
       constexpr uint32_t idesc_o = make_idesc_bf16(kBQ, DVP);
       auto issue_S = [&](int j) {
@@ -185,21 +185,21 @@ attention_kernel(const __grid_constant__ AttnParams p) {
           const uint64_t qd = make_desc_sw128(smem_u32(sQ + a * kBQ * 128));
           const uint64_t kd = make_desc_sw128(smem_u32(sK + st * kKBytes + a * kBKV * 128));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss(d, qd + 2 * k, kd + 2 * k, idesc_s, (a > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss_w(d, qd + 2 * k, kd + 2 * k, idesc_s, (a > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(&k_empty[st]);
-        umma_commit(&s_full[j % SB]);
+        umma_commit_w(&k_empty[st]);
+        umma_commit_w(&s_full[j % SB]);
       };
       mbar_wait(q_full, 0);
       issue_S(0);
       if (SB == 2 && ntiles > 1) issue_S(1);
       for (int j = 0; j < ntiles; ++j) {
         const int st = j % KV_STAGES;
-        VDB_ATL(8, j, true);
+        VDB_ATL(8, j, lane == 0);
         mbar_wait(&p_full[j % PF], (j / PF) & 1);   // P_j written, O rescaled, S_j consumed
-        VDB_ATL(9, j, true);
+        VDB_ATL(9, j, lane == 0);
         if (SB == 1 && j + 1 < ntiles) issue_S(j + 1);   // single S buffer: free now; queue it ahead of PV_j
-        VDB_ATL(10, j, true);
+        VDB_ATL(10, j, lane == 0);
         mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
         tc_fence_after();
         const uint8_t* pb = sP + (j % PB) * kPBytes;
@@ -209,11 +209,11 @@ attention_kernel(const __grid_constant__ AttnParams p) {
           const uint64_t vd = make_desc_sw128(smem_u32(sV + st * kVBytes + a * kVAtom));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(tmem_O, pd + 2 * k, vd + 2 * k, idesc_o, (j > 0 || a > 0 || k > 0) ? 1u : 0u);
+            umma_bf16_ss_w(tmem_O, pd + 2 * k, vd + 2 * k, idesc_o, (j > 0 || a > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(&v_empty[st]);
-        umma_commit(pv_done);
-        VDB_ATL(11, j, true);
+        umma_commit_w(&v_empty[st]);
+        umma_commit_w(pv_done);
+        VDB_ATL(11, j, lane == 0);
         if (SB == 2 && j + 2 < ntiles) issue_S(j + 2);
       }
     }
@@ -853,7 +853,7 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // the whole warp runs the issue loop (convergent control flow); one elected lane issues each tcgen05 instruction
       constexpr uint32_t idesc_s = make_idesc_bf16(kBQ, BKV);
       constexpr uint32_t idesc_o = make_idesc_bf16(kBQ, DVP);
       // S_g(j) = Q_g K_j^T; the K stage is released after warpgroup 1's product of that tile
@@ -864,9 +864,9 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
         const uint64_t qd = make_desc_sw128(smem_u32(sQ + g * kQBytes));
         const uint64_t kd = make_desc_sw128(smem_u32(sK + st * kKBytes));
 #pragma unroll
-        for (int k = 0; k < KS; ++k) umma_bf16_ss(tmem_base + g * 128, qd + 2 * k, kd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-        if (g == 1) umma_commit(&k_empty[st]);
-        umma_commit(&s_full[g]);
+        for (int k = 0; k < KS; ++k) umma_bf16_ss_w(tmem_base + g * 128, qd + 2 * k, kd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        if (g == 1) umma_commit_w(&k_empty[st]);
+        umma_commit_w(&s_full[g]);
       };
       // Issue order (steady state): PV_0(j), S_1(j+1), PV_1(j), S_0(j+2), ...  Every S product is queued half a cycle
       // after the s_free arrival it depends on (the group loaded its previous scores long ago), so the only wait of this
@@ -876,7 +876,7 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
       auto issue_PV = [&](int g, int j) {
         const int st = j % KV_STAGES;
         mbar_wait(&p_full[g], j & 1);                  // P_g(j) written, O_g rescaled
-        VDB_FTL(16 + 3 * g, j, true);
+        VDB_FTL(16 + 3 * g, j, lane == 0);
         mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
         tc_fence_after();
 #pragma unroll
@@ -886,24 +886,24 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
             // P_g(j) in tensor memory: 128 lanes x 64 packed columns at [384 + 64 g, ..); a K16 step reads 8 columns
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16_ts(tmem_base + 256 + g * 64, tmem_base + 384 + g * 64 + a * 32 + k * 8, vd + 2 * k, idesc_o,
+              umma_bf16_ts_w(tmem_base + 256 + g * 64, tmem_base + 384 + g * 64 + a * 32 + k * 8, vd + 2 * k, idesc_o,
                            (j > 0 || a > 0 || k > 0) ? 1u : 0u);
           } else {
             const uint64_t pd = make_desc_sw128(smem_u32(sP + g * kPBytes + a * kBQ * 128));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16_ss(tmem_base + 256 + g * 64, pd + 2 * k, vd + 2 * k, idesc_o, (j > 0 || a > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_ss_w(tmem_base + 256 + g * 64, pd + 2 * k, vd + 2 * k, idesc_o, (j > 0 || a > 0 || k > 0) ? 1u : 0u);
           }
         }
-        if (g == 1) umma_commit(&v_empty[st]);
-        umma_commit(&pv_done[g]);
-        VDB_FTL(17 + 3 * g, j, true);
+        if (g == 1) umma_commit_w(&v_empty[st]);
+        umma_commit_w(&pv_done[g]);
+        VDB_FTL(17 + 3 * g, j, lane == 0);
       };
       auto next_S = [&](int g, int j) {                // S_g(j) once the group holds S_g(j-1) in registers
         mbar_wait(&s_free[g], (j - 1) & 1);
         tc_fence_after();
         issue_S(g, j);
-        VDB_FTL(18 + 3 * g, j - 1, true);              // (slot of the tile during which it was issued)
+        VDB_FTL(18 + 3 * g, j - 1, lane == 0);              // (slot of the tile during which it was issued)
       };
       mbar_wait(q_full, 0);
       issue_S(0, 0);

@@ -670,8 +670,8 @@ __global__ void __launch_bounds__(kGnThreads, 1) gn_cluster_kernel(const __nv_bf
 // Deterministic: fixed-order shuffles / rank-ordered cluster fold (every CTA of a cluster computes identical statistics).
 // Per-thread mapping: vec = t % VPB (16-byte channel octet inside the bundle), pixel lane = t / VPB; pixels pl + k * lanes.
 // ---------------------------------------------------------------------------------------------
-template <int NVMAX>
-__global__ void __launch_bounds__(512, NVMAX <= 6 ? 2 : 1) gn_bundle_kernel(const __nv_bfloat16* __restrict__ x1, int C1,
+template <int NVMAX, int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS == 512 && NVMAX <= 6) ? 2 : 1) gn_bundle_kernel(const __nv_bfloat16* __restrict__ x1, int C1,
                                                                            const __nv_bfloat16* __restrict__ x2, int C2, int HW,
                                                                            int groups, int G, float eps, int act,
                                                                            const float* __restrict__ gamma,
@@ -681,12 +681,12 @@ __global__ void __launch_bounds__(512, NVMAX <= 6 ? 2 : 1) gn_bundle_kernel(cons
   const int cpg = C / groups;
   const int BC = G * cpg;                 // channels per bundle (multiple of 8)
   const int VPB = BC / 8;                 // 16-byte vectors per pixel and bundle
-  const int lanes = 512 / VPB;
+  const int lanes = THREADS / VPB;
   const int S = gridDim.y;
   const int b = blockIdx.z, bundle = blockIdx.x, part = blockIdx.y;
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float wpart[16][8];          // per-warp partials: sum | sumsq of up to 4 groups
+  __shared__ float wpart[THREADS / 32][8];          // per-warp partials: sum | sumsq of up to 4 groups
   __shared__ float xpart[8];              // this CTA's partials (read by the cluster peers)
   __shared__ float gstat[8];              // mean[4] | rstd[4]
   const int vec = threadIdx.x % VPB, pl = threadIdx.x / VPB;
@@ -699,7 +699,11 @@ __global__ void __launch_bounds__(512, NVMAX <= 6 ? 2 : 1) gn_bundle_kernel(cons
   const long long Cs = first ? C1 : C2;
   const int pix_per = (HW + S - 1) / S;
   const int p_begin = part * pix_per, p_end = min(HW, p_begin + pix_per);
-  uint4 keep[NVMAX];
+  // THREADS == 1024 (one CTA per SM, 64 registers per thread): the pixels wait in shared memory (cp.async, 16 bytes per
+  // request, slot [k][thread]: every thread reads back only what it requested itself) instead of in registers
+  constexpr bool kSmem = THREADS > 512;
+  extern __shared__ uint4 gn_keep_smem[];
+  uint4 keep[kSmem ? 1 : NVMAX];
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
@@ -707,13 +711,24 @@ __global__ void __launch_bounds__(512, NVMAX <= 6 ? 2 : 1) gn_bundle_kernel(cons
 #pragma unroll
     for (int k = 0; k < NVMAX; ++k) {
       const int p = p_begin + pl + k * lanes;
-      keep[k] = (p < p_end) ? __ldg(reinterpret_cast<const uint4*>(src + p * Cs)) : make_uint4(0u, 0u, 0u, 0u);
+      if constexpr (kSmem) {
+        uint4* slot = gn_keep_smem + k * THREADS + threadIdx.x;
+        if (p < p_end) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(slot)), "l"(src + p * Cs) : "memory");
+        else *slot = make_uint4(0u, 0u, 0u, 0u);
+      } else {
+        keep[k] = (p < p_end) ? __ldg(reinterpret_cast<const uint4*>(src + p * Cs)) : make_uint4(0u, 0u, 0u, 0u);
+      }
     }
+    if constexpr (kSmem) asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   }
+  auto kept = [&](int k) -> uint4 {
+    if constexpr (kSmem) return gn_keep_smem[k * THREADS + threadIdx.x]; else return keep[k];
+  };
   if (active) {
 #pragma unroll
     for (int k = 0; k < NVMAX; ++k) {     // (pixels past the range contribute zeros)
-      const uint32_t w[4] = {keep[k].x, keep[k].y, keep[k].z, keep[k].w};
+      const uint4 kv = kept(k);
+      const uint32_t w[4] = {kv.x, kv.y, kv.z, kv.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 f = unpack_bf16x2(w[i]);
@@ -751,7 +766,7 @@ __global__ void __launch_bounds__(512, NVMAX <= 6 ? 2 : 1) gn_bundle_kernel(cons
   if (threadIdx.x < 8) {
     float a = 0.f;
 #pragma unroll
-    for (int w = 0; w < 16; ++w) a += wpart[w][threadIdx.x];
+    for (int w = 0; w < THREADS / 32; ++w) a += wpart[w][threadIdx.x];
     xpart[threadIdx.x] = a;
   }
   // gamma / beta of this thread's channel octet: in flight under the barriers below
@@ -801,7 +816,8 @@ __global__ void __launch_bounds__(512, NVMAX <= 6 ? 2 : 1) gn_bundle_kernel(cons
     for (int k = 0; k < NVMAX; ++k) {
       const int p = p_begin + pl + k * lanes;
       if (p < p_end) {
-        const uint32_t w[4] = {keep[k].x, keep[k].y, keep[k].z, keep[k].w};
+        const uint4 kv = kept(k);
+        const uint32_t w[4] = {kv.x, kv.y, kv.z, kv.w};
         uint32_t o[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -1631,6 +1647,42 @@ int vdb_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int B, in
     while (G <= 4 && ((G * cpg) % 8)) G *= 2;
     const int BC = G * cpg, VPB = BC / 8;
     if (G <= 4 && cpg >= 4 && VPB >= 1 && VPB <= 64) {
+      const __nv_bfloat16* x1b = reinterpret_cast<const __nv_bfloat16*>(x1);
+      const __nv_bfloat16* x2b = reinterpret_cast<const __nv_bfloat16*>(x2);
+      __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y);
+      auto launch = [&](auto kernel, int threads, int S, size_t smem = 0) -> int {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(groups / G, S, B); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = S; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        VDB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, x1b, C1, x2b, C2, HW, groups, G, eps, act, gamma, beta, yb));
+        count_launch();
+        return VDB_OK;
+      };
+      auto nper_t = [&](int threads, int S) { const int ln = threads / VPB; return (((HW + S - 1) / S) + ln - 1) / ln; };
+      // big layers (the 64x64 level at B = 8): 1024-thread CTAs, one per SM, the pixels staged in up to 176 KB of shared memory:
+      // a 4096-pixel C = 320 layer is ONE wave of 128 CTAs (2-CTA clusters) — with 512-thread register-resident CTAs it needs
+      // 8-CTA clusters = 512 CTAs = 1.7 waves of the 296 resident slots (18 us measured) — and the C = 960 / 1920 concat
+      // layers that fit neither variant before no longer fall back to the pixel-range kernel
+      // (VDB_GN_BIG=0 turns this off)
+      static const bool big_ok = [] { const char* ev = getenv("VDB_GN_BIG"); return !(ev && ev[0] == '0'); }();
+      if (big_ok && static_cast<long long>(HW) * B >= 16384) {
+        for (int S = 1; S <= 8; S *= 2) {
+          if (static_cast<long long>(groups / G) * S * B > 4LL * num_sms()) break;   // (at most ~4 waves of one CTA per SM)
+          if (nper_t(1024, S) <= 11) {
+            constexpr size_t smem = 11 * 1024 * sizeof(uint4);
+            static bool configured = false;
+            if (!configured) {
+              VDB_CUDA_CHECK(cudaFuncSetAttribute(gn_bundle_kernel<11, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+              configured = true;
+            }
+            return launch(gn_bundle_kernel<11, 1024>, 1024, S, smem);
+          }
+        }
+      }
       const int lanes = 512 / VPB;
       auto nper = [&](int S) { return (((HW + S - 1) / S) + lanes - 1) / lanes; };
       int S = 1;
@@ -1638,23 +1690,9 @@ int vdb_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int B, in
       // small grids: more CTAs per image while every thread still keeps >= 2 pixels
       while (S < 8 && static_cast<long long>(groups / G) * S * B < num_sms() && nper(S * 2) >= 2) S *= 2;
       const int n = nper(S);
-      if (n <= 12) {
-        const __nv_bfloat16* x1b = reinterpret_cast<const __nv_bfloat16*>(x1);
-        const __nv_bfloat16* x2b = reinterpret_cast<const __nv_bfloat16*>(x2);
-        __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y);
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(groups / G, S, B); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = S; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        if (n <= 2) VDB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gn_bundle_kernel<2>, x1b, C1, x2b, C2, HW, groups, G, eps, act, gamma, beta, yb));
-        else if (n <= 6) VDB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gn_bundle_kernel<6>, x1b, C1, x2b, C2, HW, groups, G, eps, act, gamma, beta, yb));
-        else VDB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gn_bundle_kernel<12>, x1b, C1, x2b, C2, HW, groups, G, eps, act, gamma, beta, yb));
-        count_launch();
-        return VDB_OK;
-      }
+      if (n <= 2) return launch(gn_bundle_kernel<2, 512>, 512, S);
+      if (n <= 6) return launch(gn_bundle_kernel<6, 512>, 512, S);
+      if (n <= 12) return launch(gn_bundle_kernel<12, 512>, 512, S);
     }
   }
   // cluster variant (VDB_GN_CLUSTER, opt-in until measured; bit 0 = on, bit 1 = never keep the pixels in shared memory,

@@ -235,7 +235,10 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0 && cta_rank == 0) {
+    // single CTAs: the WHOLE warp runs the issue loop and one elected lane issues each tcgen05 instruction (convergent control
+    // flow keeps the descriptors in uniform registers; under `if (lane == 0)` every MMA sat in an ELECT / R2UR / BRA.U.ANY
+    // loop of ~90 cycles, more than the 32-80 tensor cycles of a BN <= 160 MMA).  CTA pairs keep the single-thread form.
+    if ((CTAS == 1) || (lane == 0 && cta_rank == 0)) {
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM * CTAS, BN);
       uint32_t stage = 0, phase = 0;
       int it = 0;
@@ -259,12 +262,12 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
             if constexpr (CTAS == 2) umma_bf16_ss_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
-            else umma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            else umma_bf16_ss_w(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
-          if constexpr (CTAS == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+          if constexpr (CTAS == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit_w(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if constexpr (CTAS == 2) umma_commit_pair(&tmem_full[as]); else umma_commit(&tmem_full[as]);
+        if constexpr (CTAS == 2) umma_commit_pair(&tmem_full[as]); else umma_commit_w(&tmem_full[as]);
         VDB_TL(3, it);                             // MMA: all MMAs of the tile issued
       }
     }
