@@ -767,7 +767,7 @@ VDB_DEVINL void ex2_poly2(float xa, float xb, float& ea, float& eb) {
   eb = __int_as_float(__float_as_int(pb) + (__float_as_int(rb) << 23));
 }
 
-template <int DVP, int KV_STAGES, int POLY, int TOKEN, int PT>
+template <int DVP, int KV_STAGES, int POLY, int TOKEN, int PT, int PH>
 __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_constant__ AttnParams p) {
   constexpr int BKV = 128;
   constexpr uint32_t kQBytes = kBQ * 128;          // one warpgroup's Q tile (DK = 64: one K atom)
@@ -1012,53 +1012,110 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
           tmem_wait_st();
         }
       }
-      token_wait();
-      VDB_FTL(8 * g + 4, j, tlw);
-      {
+      if constexpr (PH) {
+        // ---- phase-split tile (round 2, default).  Measured (profiles/r02_attention_fa_timeline_v2.txt): a softmax warp alone on
+        // its SM sub-partition issues MUFU.EX2 at only ~62 % of the pipe rate when the scale FFMAs, row sums, bf16 packs and P
+        // stores are interleaved with it (fixed issue stalls after every MUFU; nothing of the SAME warp fills them), so the two
+        // groups' exp2 phases — serialised by the token — set the kernel's pace at 2 x 800 ns per tile pair.  Here the token
+        // covers ONLY a dense run of MUFU.EX2 (in place on the row's 128 registers); everything else of the tile — scaling and the
+        // FMA-pipe exponentials before it (A), row sum / pack / P store after it (C) — runs while the OTHER group owns the pipe.
         const unsigned long long sc2 = pack_f2(p.scale_log2, p.scale_log2), nm2 = pack_f2(-m_scaled, -m_scaled);
-        unsigned long long l2 = pack_f2(0.f, 0.f), l2b = pack_f2(0.f, 0.f);
-        uint32_t pk[PT ? 32 : 4];
-        (void)pk;
 #pragma unroll
-        for (int q = 0; q < BKV / 8; ++q) {          // 8 scores -> one 16-byte chunk of the P row
-          float e[8];
+        for (int i = 0; i < BKV; i += 2) {            // A: x = s * scale - m  (and 2^x on the FMA pipe for the POLY pairs of every 8)
+          float xa, xb;
+          unpack_f2(fma_f2(pack_f2(__uint_as_float(keep[i]), __uint_as_float(keep[i + 1])), sc2, nm2), xa, xb);
+          if (((i >> 1) & 7) >= 8 - POLY) ex2_poly2(xa, xb, xa, xb);
+          keep[i] = __float_as_uint(xa);
+          keep[i + 1] = __float_as_uint(xb);
+        }
+        token_wait();
+        VDB_FTL(8 * g + 4, j, tlw);
 #pragma unroll
-          for (int i = 0; i < 8; i += 2) {
-            float xa, xb;
-            unpack_f2(fma_f2(pack_f2(__uint_as_float(keep[q * 8 + i]), __uint_as_float(keep[q * 8 + i + 1])), sc2, nm2), xa, xb);
-            // pair index inside a group of 8 pairs (two chunks): the LAST `POLY` pairs go to the FMA pipe
-            const int pair8 = (q & 1) * 4 + (i >> 1);
-            if (pair8 >= 8 - POLY) {
-              ex2_poly2(xa, xb, e[i], e[i + 1]);
-            } else {
-              e[i] = ex2_mufu(xa);
-              e[i + 1] = ex2_mufu(xb);
-            }
-            if (i & 2) l2b = add_f2(l2b, pack_f2(e[i], e[i + 1])); else l2 = add_f2(l2, pack_f2(e[i], e[i + 1]));
-          }
-          // TOKEN 2 / 3: hand the MUFU token over after 3/4 / 1/2 of the tile's exponentials have been issued: the next
-          // group's ramp-up (barrier latency, first scale FFMAs) then overlaps this group's tail instead of idling the pipe
-          if constexpr (TOKEN >= 2) {
-            if (q == (TOKEN == 2 ? 11 : 7) && !(j == ntiles - 1 && g == 1)) token_pass();
-          }
-          if constexpr (PT) {
-            // packed bf16 pairs -> 32-bit tensor-memory columns [4 q, 4 q + 4) of this lane's P row; stored 32 columns at a time
-#pragma unroll
-            for (int i = 0; i < 4; ++i) pk[(q & 7) * 4 + i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
-            if ((q & 7) == 7) tmem_st32(tmem_P + (q >> 3) * 32, pk);
-          } else {
-            const uint4 v4 = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (q >> 3) * (kBQ * 128) + (((q & 7) ^ (r & 7)) << 4)),
-                         "r"(v4.x), "r"(v4.y), "r"(v4.z), "r"(v4.w) : "memory");
+        for (int i = 0; i < BKV; i += 2) {            // M: the MUFU run (volatile: stays between the two barrier instructions)
+          if (((i >> 1) & 7) < 8 - POLY) {
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(keep[i]));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(keep[i + 1]));
           }
         }
-        float la, lb;
-        unpack_f2(add_f2(l2, l2b), la, lb);
-        l_sum += la + lb;
-      }
-      VDB_FTL(8 * g + 5, j, tlw);
-      if constexpr (TOKEN == 1) {
+        VDB_FTL(8 * g + 5, j, tlw);
         if (!(j == ntiles - 1 && g == 1)) token_pass();   // (the ring is primed once: skip the one surplus hand-over)
+        {                                                 // C: row sum, bf16 pack, P store
+          unsigned long long l2 = pack_f2(0.f, 0.f), l2b = pack_f2(0.f, 0.f);
+          uint32_t pk[PT ? 32 : 4];
+          (void)pk;
+#pragma unroll
+          for (int q = 0; q < BKV / 8; ++q) {
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              const unsigned long long e2 = pack_f2(__uint_as_float(keep[q * 8 + i]), __uint_as_float(keep[q * 8 + i + 1]));
+              if (i & 2) l2b = add_f2(l2b, e2); else l2 = add_f2(l2, e2);
+            }
+            if constexpr (PT) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                pk[(q & 7) * 4 + i] = pack_bf16x2(__uint_as_float(keep[q * 8 + 2 * i]), __uint_as_float(keep[q * 8 + 2 * i + 1]));
+              if ((q & 7) == 7) tmem_st32(tmem_P + (q >> 3) * 32, pk);
+            } else {
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (q >> 3) * (kBQ * 128) + (((q & 7) ^ (r & 7)) << 4)),
+                           "r"(pack_bf16x2(__uint_as_float(keep[q * 8]), __uint_as_float(keep[q * 8 + 1]))),
+                           "r"(pack_bf16x2(__uint_as_float(keep[q * 8 + 2]), __uint_as_float(keep[q * 8 + 3]))),
+                           "r"(pack_bf16x2(__uint_as_float(keep[q * 8 + 4]), __uint_as_float(keep[q * 8 + 5]))),
+                           "r"(pack_bf16x2(__uint_as_float(keep[q * 8 + 6]), __uint_as_float(keep[q * 8 + 7]))) : "memory");
+            }
+          }
+          float la, lb;
+          unpack_f2(add_f2(l2, l2b), la, lb);
+          l_sum += la + lb;
+        }
+      } else {
+      token_wait();
+        VDB_FTL(8 * g + 4, j, tlw);
+        {
+          const unsigned long long sc2 = pack_f2(p.scale_log2, p.scale_log2), nm2 = pack_f2(-m_scaled, -m_scaled);
+          unsigned long long l2 = pack_f2(0.f, 0.f), l2b = pack_f2(0.f, 0.f);
+          uint32_t pk[PT ? 32 : 4];
+          (void)pk;
+  #pragma unroll
+          for (int q = 0; q < BKV / 8; ++q) {          // 8 scores -> one 16-byte chunk of the P row
+            float e[8];
+  #pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              float xa, xb;
+              unpack_f2(fma_f2(pack_f2(__uint_as_float(keep[q * 8 + i]), __uint_as_float(keep[q * 8 + i + 1])), sc2, nm2), xa, xb);
+              // pair index inside a group of 8 pairs (two chunks): the LAST `POLY` pairs go to the FMA pipe
+              const int pair8 = (q & 1) * 4 + (i >> 1);
+              if (pair8 >= 8 - POLY) {
+                ex2_poly2(xa, xb, e[i], e[i + 1]);
+              } else {
+                e[i] = ex2_mufu(xa);
+                e[i + 1] = ex2_mufu(xb);
+              }
+              if (i & 2) l2b = add_f2(l2b, pack_f2(e[i], e[i + 1])); else l2 = add_f2(l2, pack_f2(e[i], e[i + 1]));
+            }
+            // TOKEN 2 / 3: hand the MUFU token over after 3/4 / 1/2 of the tile's exponentials have been issued: the next
+            // group's ramp-up (barrier latency, first scale FFMAs) then overlaps this group's tail instead of idling the pipe
+            if constexpr (TOKEN >= 2) {
+              if (q == (TOKEN == 2 ? 11 : 7) && !(j == ntiles - 1 && g == 1)) token_pass();
+            }
+            if constexpr (PT) {
+              // packed bf16 pairs -> 32-bit tensor-memory columns [4 q, 4 q + 4) of this lane's P row; stored 32 columns at a time
+  #pragma unroll
+              for (int i = 0; i < 4; ++i) pk[(q & 7) * 4 + i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
+              if ((q & 7) == 7) tmem_st32(tmem_P + (q >> 3) * 32, pk);
+            } else {
+              const uint4 v4 = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (q >> 3) * (kBQ * 128) + (((q & 7) ^ (r & 7)) << 4)),
+                           "r"(v4.x), "r"(v4.y), "r"(v4.z), "r"(v4.w) : "memory");
+            }
+          }
+          float la, lb;
+          unpack_f2(add_f2(l2, l2b), la, lb);
+          l_sum += la + lb;
+        }
+        VDB_FTL(8 * g + 5, j, tlw);
+        if constexpr (TOKEN == 1) {
+          if (!(j == ntiles - 1 && g == 1)) token_pass();   // (the ring is primed once: skip the one surplus hand-over)
+        }
       }
       if constexpr (PT) tmem_wait_st(); else fence_proxy_async_smem();
       tc_fence_before();
@@ -1151,11 +1208,11 @@ static int launch_attention_pp(AttnParams& p, const AttnArgs& a, cudaStream_t st
 }
 
 
-template <int DVP, int KV_STAGES, int POLY, int TOKEN, int PT>
+template <int DVP, int KV_STAGES, int POLY, int TOKEN, int PT, int PH>
 static int launch_attention_fa(AttnParams& p, const AttnArgs& a, cudaStream_t stream) {
   constexpr size_t smem = attention_fa_smem_bytes<DVP, KV_STAGES, PT>();
   static_assert(smem <= 227 * 1024, "attention (two-tile) smem budget");
-  auto kernel = attention_fa_kernel<DVP, KV_STAGES, POLY, TOKEN, PT>;
+  auto kernel = attention_fa_kernel<DVP, KV_STAGES, POLY, TOKEN, PT, PH>;
   static bool configured = false;
   if (!configured) {
     VDB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -1174,29 +1231,24 @@ static int launch_attention_fa(AttnParams& p, const AttnArgs& a, cudaStream_t st
   return VDB_OK;
 }
 
-template <int DVP, int PT, int TOKEN>
+template <int DVP, int PT, int TOKEN, int PH>
 static int dispatch_attention_fa3(int poly, AttnParams& p, const AttnArgs& a, cudaStream_t st) {
   switch (poly) {
-    case 0: return launch_attention_fa<DVP, 3, 0, TOKEN, PT>(p, a, st);
-    case 2: return launch_attention_fa<DVP, 3, 2, TOKEN, PT>(p, a, st);
-    case 3: return launch_attention_fa<DVP, 3, 3, TOKEN, PT>(p, a, st);
-    default: return launch_attention_fa<DVP, 3, 1, TOKEN, PT>(p, a, st);
-  }
-}
-template <int DVP, int PT>
-static int dispatch_attention_fa2(int poly, int token, AttnParams& p, const AttnArgs& a, cudaStream_t st) {
-  switch (token) {
-    case 0: return dispatch_attention_fa3<DVP, PT, 0>(poly, p, a, st);
-    case 2: return dispatch_attention_fa3<DVP, PT, 2>(poly, p, a, st);
-    case 3: return dispatch_attention_fa3<DVP, PT, 3>(poly, p, a, st);
-    default: return dispatch_attention_fa3<DVP, PT, 1>(poly, p, a, st);
+    case 0: return launch_attention_fa<DVP, 3, 0, TOKEN, PT, PH>(p, a, st);
+    case 1: return launch_attention_fa<DVP, 3, 1, TOKEN, PT, PH>(p, a, st);
+    case 3: return launch_attention_fa<DVP, 3, 3, TOKEN, PT, PH>(p, a, st);
+    default: return launch_attention_fa<DVP, 3, 2, TOKEN, PT, PH>(p, a, st);
   }
 }
 template <int DVP>
 static int dispatch_attention_fa(int mode, AttnParams& p, const AttnArgs& a, cudaStream_t st) {
-  // mode digits "SPT": S = 1 keeps P in shared memory (SS product), else tensor memory (TS); P = FMA-pipe pairs of 8; T = token
-  const int poly = (mode / 10) % 10, token = mode % 10, smem_p = mode / 100;
-  return smem_p ? dispatch_attention_fa2<DVP, 0>(poly, token, p, a, st) : dispatch_attention_fa2<DVP, 1>(poly, token, p, a, st);
+  // mode digits "[H][S]PT": P = exp2 pairs of every 8 on the FMA pipe (0..3); T = 1 MUFU token / 0 free-running; S = 1 keeps P in
+  // shared memory (SS product) instead of tensor memory (TS); H = 1 the round-2a tile body (exp2 interleaved with its pack / store
+  // work) instead of the phase-split one.  Kept variants: the default and the ones the profiles under profiles/ compare against.
+  const int poly = (mode / 10) % 10, token = mode % 10 ? 1 : 0, smem_p = (mode / 100) % 10, legacy = (mode / 1000) % 10;
+  if (legacy) return token ? dispatch_attention_fa3<DVP, 1, 1, 0>(poly, p, a, st) : dispatch_attention_fa3<DVP, 1, 0, 0>(poly, p, a, st);
+  if (smem_p) return dispatch_attention_fa3<DVP, 0, 1, 1>(poly, p, a, st);
+  return token ? dispatch_attention_fa3<DVP, 1, 1, 1>(poly, p, a, st) : dispatch_attention_fa3<DVP, 1, 0, 1>(poly, p, a, st);
 }
 
 }  // namespace vdb
@@ -1263,7 +1315,7 @@ int vdb_attention_bf16(const void* Q, long long ldq, int q_col0, const void* K, 
   // instead of tensor memory.  e.g. 21 = two of eight pairs, token, P in tensor memory; 121 = the same with P in shared memory.
   static const int fa = [] { const char* e = getenv("VDB_ATT_FA"); return e ? atoi(e) : -1; }();
   if (fa != 0 && !pp && DK == 64 && !causal && Nk >= 512 && Nq >= 256 && (Nq % 256) == 0) {
-    const int mode = fa < 0 ? 11 : fa;
+    const int mode = fa < 0 ? 21 : fa;
     if (DVP == 48) return dispatch_attention_fa<48>(mode, p, a, st);
     if (DVP == 64) return dispatch_attention_fa<64>(mode, p, a, st);
   }
