@@ -806,7 +806,25 @@ static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot
                      const IgemmEpilogue& e, int bn_forced, int ksplit_forced, void* workspace,
                      size_t ws_bytes, cudaStream_t stream) {
   int BN = pick_bn(static_cast<int>(N), e.act, bn_forced);
-  if (!bn_forced && e.act != ACT_GEGLU && p.kb_total < 32) {
+  // Tile-width model (round 2; VDB_BN_MODEL=0 restores the divisibility rule above): the persistent grid runs
+  // waves = ceil(tiles / #SMs) rounds of one tile per CTA, a tile costs kb * c(BN) cycles of mainloop (operand fill at ~90 B/clk
+  // per SM or the MMA itself, whichever is longer) plus ~1500 cycles of pipeline fill / epilogue tail.  The divisibility rule sent
+  // e.g. M 2048 x N 1280 x K 1280 (15 launches per step) to BN 256 = 80 tiles on 148 SMs; BN 160 gives 128 shorter tiles.
+  static const int bn_model = [] { const char* ev = getenv("VDB_BN_MODEL"); return (ev && ev[0] == '0') ? 0 : 1; }();
+  if (bn_model && !bn_forced && e.act != ACT_GEGLU && p.kb_total >= 8) {
+    const long long tm = static_cast<long long>(p.tilesW) * p.tilesH * p.tilesB;
+    const int cand[4] = {256, 160, 128, 64};
+    double best = 1e30;
+    for (int c : cand) {
+      const long long tiles = tm * ((N + c - 1) / c);
+      const long long waves = (tiles + num_sms() - 1) / num_sms();
+      const double per_kb = std::max(2.0 * c, (16384.0 + 128.0 * c) / 90.0);
+      // columns of a partial last N tile are computed in full: charge them
+      const double cost = static_cast<double>(waves) * (p.kb_total * per_kb + 1500.0);
+      if (cost < best * 0.97) { best = cost; BN = c; }     // (prefer the wider tile unless the gain is clear)
+    }
+  }
+  if (!bn_forced && !bn_model && e.act != ACT_GEGLU && p.kb_total < 32) {
     // short K and a small MN grid (the 8x8 level): narrower tiles fill more SMs and need no split-K reduction pass
     // (M 512, N 1280, K 1280: 10.7 us with BN 64 vs 18.1 us with BN 256 + split-K 2, tools/bn_sweep.py)
     const int tm = p.tilesW * p.tilesH * p.tilesB;
