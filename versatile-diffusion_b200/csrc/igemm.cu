@@ -816,11 +816,16 @@ static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot
     const int cand[4] = {256, 160, 128, 64};
     double best = 1e30;
     for (int c : cand) {
-      const long long tiles = tm * ((N + c - 1) / c);
-      const long long waves = (tiles + num_sms() - 1) / num_sms();
+      const long long tiles = tm * ((N + c - 1) / c);      // (a partial last N tile is computed in full)
+      // split-K exactly as decided below: small MN grids with a deep K run kb / ks blocks per unit plus a reduction pass
+      long long ks = 1;
+      if (ksplit_forced > 0) ks = ksplit_forced;
+      else if (tiles * 2 <= num_sms() && p.kb_total >= 16 && (N % 4) == 0 && workspace)
+        ks = std::max<long long>(1, std::min<long long>(std::min<long long>(num_sms() / tiles, p.kb_total / 8), 16));
+      const long long waves = (tiles * ks + num_sms() - 1) / num_sms();
       const double per_kb = std::max(2.0 * c, (16384.0 + 128.0 * c) / 90.0);
-      // columns of a partial last N tile are computed in full: charge them
-      const double cost = static_cast<double>(waves) * (p.kb_total * per_kb + 1500.0);
+      const double kb_unit = static_cast<double>((p.kb_total + ks - 1) / ks);
+      const double cost = static_cast<double>(waves) * (kb_unit * per_kb + 1500.0) + (ks > 1 ? 12000.0 : 0.0);
       if (cost < best * 0.97) { best = cost; BN = c; }     // (prefer the wider tile unless the gain is clear)
     }
   }
