@@ -50,9 +50,11 @@ def test_folded_weights_reproduce_upsample_then_conv(B, C, N, H, W):
     assert (wf.float() - wf_exact).abs().max() <= 8e-3 * wf_exact.abs().max() + 1e-6
 
 
-def test_fold_switch_is_off_by_default(monkeypatch):
+def test_fold_switch(monkeypatch):
     from lib.model_zoo.diffusion_utils import upsample_fold_enabled
-    monkeypatch.delenv("VDB_UPFOLD", raising=False)
+    monkeypatch.setenv("VDB_UPFOLD", "0")
     assert not upsample_fold_enabled(1 << 20)
+    monkeypatch.delenv("VDB_UPFOLD", raising=False)          # default since round 2: on for grids that fill the machine
+    assert upsample_fold_enabled(4096) and not upsample_fold_enabled(512)
     monkeypatch.setenv("VDB_UPFOLD", "1")
     assert upsample_fold_enabled(4096) and not upsample_fold_enabled(512)

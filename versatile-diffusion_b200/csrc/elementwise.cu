@@ -664,7 +664,7 @@ __global__ void __launch_bounds__(kGnThreads, 1) gn_cluster_kernel(const __nv_bf
 // then never leave the CTA: no grid-wide arrival counter, no global scratch, no residency requirement, and the pixels are
 // read ONCE (they stay in registers between the statistics and the normalisation).  Layers whose bundle does not fit the
 // registers of one CTA split the pixels over a thread-block cluster of S <= 8 CTAs (grid (bundles, S, B), cluster
-// (1, S, 1)); the 2 G partial sums cross the cluster through distributed shared memory behind one hardware cluster barrier.
+// (1, S, 1)); the 2 G partial sums are pushed into every peer's shared memory (st.shared::cluster + a remote mbarrier arrival).
 // The single-launch kernel above spent most of its 11-30 us per layer in serialised latency phases (publish, device-wide
 // wait, re-read), not in bandwidth: profiles/r01_variants_v8.txt.
 // Deterministic: fixed-order shuffles / rank-ordered cluster fold (every CTA of a cluster computes identical statistics).
@@ -687,8 +687,23 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512 && NVMAX <= 6) ? 2 : 
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float wpart[THREADS / 32][8];          // per-warp partials: sum | sumsq of up to 4 groups
-  __shared__ float xpart[8];              // this CTA's partials (read by the cluster peers)
+  __shared__ float xpart[8];              // this CTA's partials
+  __shared__ float xall[8][8];            // S > 1: every rank's partials, WRITTEN BY THE PEERS (st.shared::cluster)
+  __shared__ uint64_t xbar;               // S > 1: counts the 8 S remote-write arrivals
   __shared__ float gstat[8];              // mean[4] | rstd[4]
+  if (S > 1) {
+    // one-way exchange instead of two cluster barriers (ncu: barrier.cluster.arrive.release + wait were ~30 % of this kernel's
+    // stall samples on the 64x64 layers): every CTA pushes its 8 partial sums into each peer's xall[rank] and arrives on the
+    // peer's mbarrier; a CTA leaves only after all 8 S arrivals, i.e. after every write into its memory has landed, and its own
+    // pushes target CTAs that cannot leave before receiving them.  The only cluster barrier left is split-phase: arrive here,
+    // right after the mbarrier is initialised, wait just before the first push (long complete by then).
+    if (threadIdx.x == 0) {
+      mbar_init(&xbar, 8 * S);
+      fence_barrier_init();
+    }
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  }
   const int vec = threadIdx.x % VPB, pl = threadIdx.x / VPB;
   const bool active = pl < lanes;
   const int cb = vec * 8;                                 // first channel of this thread inside the bundle
@@ -778,19 +793,33 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512 && NVMAX <= 6) ? 2 : 
     bet[0] = b0.x; bet[1] = b0.y; bet[2] = b0.z; bet[3] = b0.w; bet[4] = b1.x; bet[5] = b1.y; bet[6] = b1.z; bet[7] = b1.w;
   }
   if (S > 1) {
-    cluster_arrive();                      // (release: xpart is visible to the peers after their wait)
-    cluster_wait();
+    __syncthreads();                       // xpart complete
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");   // every peer's mbarrier is initialised
+    if (threadIdx.x < 8) {
+      const float v = xpart[threadIdx.x];
+      const uint32_t slot = smem_u32(&xall[part][threadIdx.x]), bar = smem_u32(&xbar);
+      for (int r = 0; r < S; ++r) {
+        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(mapa_u32(slot, static_cast<uint32_t>(r))), "f"(v) : "memory");
+        mbar_arrive_cluster(mapa_u32(bar, static_cast<uint32_t>(r)));     // release.cluster: orders this thread's store before it
+      }
+    }
+    if (threadIdx.x < 4) {                 // (the threads that fold the partials wait; the rest meet them at the barrier below)
+      uint32_t ok = 0;
+      while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
+            : "=r"(ok) : "r"(smem_u32(&xbar)), "r"(0u) : "memory");
+      }
+    }
   } else {
     __syncthreads();
   }
   if (threadIdx.x < 4) {
     float a = 0.f, c = 0.f;
     if (S > 1) {
-      const uint32_t mine = smem_u32(xpart);
       for (int r = 0; r < S; ++r) {        // rank order: identical in every CTA of the cluster
-        const uint32_t peer = mapa_u32(mine, static_cast<uint32_t>(r));
-        a += ld_dsmem_f32(peer + 4 * threadIdx.x);
-        c += ld_dsmem_f32(peer + 4 * (4 + threadIdx.x));
+        a += xall[r][threadIdx.x];
+        c += xall[r][4 + threadIdx.x];
       }
     } else {
       a = xpart[threadIdx.x]; c = xpart[4 + threadIdx.x];
@@ -801,7 +830,6 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512 && NVMAX <= 6) ? 2 : 
     gstat[threadIdx.x] = mean;
     gstat[4 + threadIdx.x] = rsqrtf(var + eps);
   }
-  if (S > 1) cluster_arrive();             // "done reading my peers' shared memory" (waited for before exit)
   __syncthreads();
   if (active) {
     float sc[8], sh[8];
@@ -831,7 +859,6 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 512 && NVMAX <= 6) ? 2 : 
       }
     }
   }
-  if (S > 1) cluster_wait();               // no CTA leaves while a peer may still read its xpart
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -192,10 +192,11 @@ def fold_upsample_conv3x3(w):
 
 
 def upsample_fold_enabled(n_source_pixels):
-    """VDB_UPFOLD=1 (opt-in until measured on a GPU): fold when the source grid is large enough to fill the machine without
-    split-K (the four parity convs each see only B*H*W output pixels)."""
+    """Nearest-2x upsample folded into the following 3x3 conv (default ON since round 2: parity-tested on a B200,
+    gpurun_out/exp_r2a.log, and +1.1 % on the C2 bench): fold when the source grid is large enough to fill the machine without
+    split-K (the four parity convs each see only B*H*W output pixels).  VDB_UPFOLD=0 turns it off, =2 folds every Upsample."""
     import os
-    mode = os.environ.get("VDB_UPFOLD", "0")
+    mode = os.environ.get("VDB_UPFOLD", "1")
     return mode == "2" or (mode == "1" and n_source_pixels >= 2048)     # "2": every Upsample (tests on small models)
 
 

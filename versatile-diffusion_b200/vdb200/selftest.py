@@ -54,7 +54,9 @@ def smoke():
     n = ops.launch_count()
     print(f"[smoke] 2-step DDIM latent cosine vs oracle {cos:.6f}; decoded image max|err| {err:.4f}; "
           f"{n} vdb200 kernel launches")
-    if not (cos >= 0.995 and err <= 0.1 and n > 0):   # bf16 vs fp32, 2 DDIM steps from pure noise
+    # bf16 vs fp32, 2 CFG DDIM steps from pure noise (CFG 7.5 amplifies the per-forward bf16 error ~7.5x): latent cosine >= 0.999
+    # (observed 0.99905), decoded [0,1] image within 0.1 (observed 0.088)
+    if not (cos >= 0.999 and err <= 0.1 and n > 0):
         raise AssertionError("smoke: CUDA path deviates from the CPU oracle")
 
 
