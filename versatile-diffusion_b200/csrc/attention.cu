@@ -440,280 +440,10 @@ attention_kernel(const __grid_constant__ AttnParams p) {
   if (warp == 2) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Ping-pong variant (opt-in, VDB_ATT_PP=2|3; written from the role timeline of the kernel above and NOT yet measured).
-// The timeline (profiles/r01_attention_timeline_v8.txt) shows the softmax warps that share an SM sub-partition running
-// their exp2 phases at the same time: the MUFU pipe is saturated for ~55 % of a tile and idle while all of them wait for
-// S, load it from TMEM, reduce the row max and exchange it.  Here ONE CTA per SM owns G query tiles ("groups" of 8 softmax
-// warps each) and the groups take turns on the MUFU pipe: a group enters its exp2 phase only when the previous group hands
-// it a token (named barrier, bar.sync / bar.arrive), so the other G-1 groups' S wait / TMEM load / max / exchange / O
-// rescale run underneath it.  K and V tiles are staged once per CTA and shared by the groups (1/G of the L2 traffic).
-//   TMEM: group g owns columns [128 g, 128 g + 128): S (64 columns, single buffer) | O (<= 64 columns).
-//   kv tile = 64 columns, d_head <= 64 (DK = 64), no causal mask.
-//   warps: 0 TMA, 1 MMA, 2 + 8 g .. 9 + 8 g softmax group g (TMEM lane quarter = warp % 4, column half = (warp - 2 - 8 g) / 4).
-//   named barriers: 1 + 4 g + quarter = max exchange of a quarter's two warps; 13 + g = exp2 token of group g.
-// ---------------------------------------------------------------------------------------------------------------------
-template <int DVP, int G, int KV_STAGES>
-constexpr size_t attention_pp_smem_bytes() {
-  return G * kBQ * 128 + KV_STAGES * (64 * 128 + DVP * 128) + G * kBQ * 128 + 32 * 8 + G * (512 + 256) * 4 + 1024;
-}
-
-template <int DVP, int G, int KV_STAGES>
-__global__ void __launch_bounds__(64 + 256 * G, 1) attention_pp_kernel(const __grid_constant__ AttnParams p) {
-  constexpr int BKV = 64;
-  constexpr uint32_t kQBytes = kBQ * 128;          // one group's Q tile (DK = 64: one K atom)
-  constexpr uint32_t kKBytes = BKV * 128;          // one K stage
-  constexpr uint32_t kVBytes = DVP * 128;          // one V stage (one 64-kv atom of V^T)
-  constexpr uint32_t kPBytes = kBQ * 128;          // one group's P buffer (128 x 64 bf16)
-  constexpr uint32_t kGroupCols = 128;             // TMEM columns per group: S [0, 64) | O [64, 64 + DVP)
-  static_assert(G == 2 || G == 3, "two or three softmax groups");
-  static_assert(DVP % 16 == 0 && DVP <= 64, "O must fit the group's 64 spare TMEM columns");
-  static_assert(KV_STAGES >= 2 && KV_STAGES <= kMaxKvStages, "kv stages");
-  static_assert(kVBytes % 1024 == 0, "V stage must keep 1024B alignment");
-
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                               // [G][16 KB]
-  uint8_t* sK = sQ + G * kQBytes;                   // [KV_STAGES][8 KB]
-  uint8_t* sV = sK + KV_STAGES * kKBytes;           // [KV_STAGES][kVBytes]
-  uint8_t* sP = sV + KV_STAGES * kVBytes;           // [G][16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + G * kPBytes);
-  uint64_t* q_full = bars;            // 1
-  uint64_t* k_full = bars + 1;        // [kMaxKvStages]
-  uint64_t* k_empty = bars + 5;       // [kMaxKvStages]
-  uint64_t* v_full = bars + 9;        // [kMaxKvStages]
-  uint64_t* v_empty = bars + 13;      // [kMaxKvStages]
-  uint64_t* s_full = bars + 17;       // [G]
-  uint64_t* p_full = bars + 20;       // [G]  (count 8: one arrive per softmax warp of the group)
-  uint64_t* pv_done = bars + 23;      // [G]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 30);
-  float* sx = reinterpret_cast<float*>(bars + 32);   // per group: [2 parity][2 halves][128] row max | [2 halves][128] row sums
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * (G * kBQ);
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
-  const int ntiles = (p.Nk + BKV - 1) / BKV;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmQ);
-    tma_prefetch_desc(&p.tmK);
-    tma_prefetch_desc(&p.tmV);
-  }
-  if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
-    for (int s = 0; s < KV_STAGES; ++s) {
-      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
-      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
-    }
-    for (int g = 0; g < G; ++g) {
-      mbar_init(&s_full[g], 1);
-      mbar_init(&p_full[g], 8);
-      mbar_init(&pv_done[g], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc<512>(tmem_holder);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_holder;
-  pdl_launch_dependents();
-  pdl_wait();
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, G * kQBytes);
-      for (int g = 0; g < G; ++g)
-        tma_load_2d(sQ + g * kQBytes, &p.tmQ, q_full, p.q_col0 + head * 64, b * p.q_bs + q0 + g * kBQ);
-      for (int j = 0; j < ntiles; ++j) {
-        const int st = j % KV_STAGES;
-        const uint32_t ph = (j / KV_STAGES) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], kKBytes);
-        tma_load_2d(sK + st * kKBytes, &p.tmK, &k_full[st], p.k_col0 + head * 64, b * p.kv_bs + j * BKV);
-        mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], kVBytes);
-        tma_load_2d(sV + st * kVBytes, &p.tmV, &v_full[st], b * p.kv_bs + j * BKV, head * DVP);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(kBQ, BKV);
-      constexpr uint32_t idesc_o = make_idesc_bf16(kBQ, DVP);
-      // S_g(j) = Q_g K_j^T; the K stage is released after the LAST group's product of that tile
-      auto issue_S = [&](int g, int j) {
-        const int st = j % KV_STAGES;
-        mbar_wait(&k_full[st], (j / KV_STAGES) & 1);   // (already complete for g > 0: returns at once)
-        tc_fence_after();
-        const uint64_t qd = make_desc_sw128(smem_u32(sQ + g * kQBytes));
-        const uint64_t kd = make_desc_sw128(smem_u32(sK + st * kKBytes));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + g * kGroupCols, qd + 2 * k, kd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-        if (g == G - 1) umma_commit(&k_empty[st]);
-        umma_commit(&s_full[g]);
-      };
-      mbar_wait(q_full, 0);
-      for (int g = 0; g < G; ++g) issue_S(g, 0);
-      for (int j = 0; j < ntiles; ++j) {
-        const int st = j % KV_STAGES;
-        for (int g = 0; g < G; ++g) {                  // the groups arrive in token order: 0, 1, .., G-1
-          mbar_wait(&p_full[g], j & 1);                // P_g(j) written, O_g rescaled, S_g(j) consumed
-          if (j + 1 < ntiles) issue_S(g, j + 1);       // the group's single S buffer is free: queue it ahead of PV_g(j)
-          mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
-          tc_fence_after();
-          const uint64_t pd = make_desc_sw128(smem_u32(sP + g * kPBytes));
-          const uint64_t vd = make_desc_sw128(smem_u32(sV + st * kVBytes));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(tmem_base + g * kGroupCols + 64, pd + 2 * k, vd + 2 * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-          if (g == G - 1) umma_commit(&v_empty[st]);
-          umma_commit(&pv_done[g]);
-        }
-      }
-    }
-  } else {
-    // ------------------------------ softmax group g ------------------------------
-    const int g = (warp - 2) >> 3;
-    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int hw = ((warp - 2) & 7) >> 2;         // which half of the 64 S columns / of the O columns
-    const int r = quarter * 32 + lane;            // query row inside the group's tile == TMEM lane
-    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const int q_idx = q0 + g * kBQ + r;
-    const uint32_t tmem_S = tmem_base + g * kGroupCols + lane_off;
-    const uint32_t tmem_O = tmem_S + 64;
-    constexpr int WC = 32;                        // S columns per warp and tile
-    constexpr int OCH = DVP / 16;                 // 16-column O chunks
-    const int oc_begin = hw == 0 ? 0 : (OCH + 1) / 2;
-    const int oc_end = hw == 0 ? (OCH + 1) / 2 : OCH;
-    float* sxm = sx + g * 768;                    // [2 parity][2 halves][128 rows]
-    float* sxl = sxm + 512;                       // [2 halves][128 rows]
-    auto pair_sync = [&] { asm volatile("bar.sync %0, 64;" ::"r"(1 + g * 4 + quarter) : "memory"); };
-    // exp2 token: group g may use the MUFU pipe between token_wait() and token_pass(); 256 waiting + 256 arriving threads
-    auto token_wait = [&] { asm volatile("bar.sync %0, 512;" ::"r"(13 + g) : "memory"); };
-    auto token_pass = [&] { asm volatile("bar.arrive %0, 512;" ::"r"(13 + (g + 1) % G) : "memory"); };
-    if (g == G - 1) token_pass();                 // prime the ring: group 0 goes first
-    float m_ref = -INFINITY;
-    float l_sum = 0.f;
-    uint8_t* prow = sP + g * kPBytes + r * 128;
-    const int chunk0 = hw * 4;                    // first 16-byte chunk of this warp's 32 columns inside the 128-byte row
-    for (int j = 0; j < ntiles; ++j) {
-      mbar_wait(&s_full[g], j & 1);
-      tc_fence_after();
-      const int kv0 = j * BKV;
-      const bool need_mask = kv0 + BKV > p.Nk;
-      uint32_t keep[WC];
-      tmem_ld32(tmem_S + hw * WC, keep);
-      tmem_wait_ld();
-      float mx = -INFINITY;
-      if (need_mask) {
-#pragma unroll
-        for (int i = 0; i < WC; ++i)
-          if (kv0 + hw * WC + i < p.Nk) mx = fmaxf(mx, __uint_as_float(keep[i]));
-      } else {
-#pragma unroll
-        for (int i = 0; i < WC; ++i) mx = fmaxf(mx, __uint_as_float(keep[i]));
-      }
-      sxm[((j & 1) * 2 + hw) * 128 + r] = mx;
-      pair_sync();
-      mx = fmaxf(mx, sxm[((j & 1) * 2 + (hw ^ 1)) * 128 + r]);
-      const float m_new = fmaxf(m_ref, mx);
-      bool rescale = false;
-      float factor = 1.f;
-      if (j == 0) {
-        m_ref = m_new;
-      } else {
-        const bool want = (m_new - m_ref) * p.scale_log2 > kRescaleThreshold;
-        rescale = __any_sync(0xffffffffu, want);
-        if (rescale) {
-          factor = ex2_mufu((m_ref - m_new) * p.scale_log2);
-          m_ref = m_new;
-          l_sum *= factor;
-        }
-      }
-      const float m_scaled = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;
-      // PV_g(j-1) must have retired: it reads the group's only P buffer and accumulates into O
-      if (j > 0) {
-        mbar_wait(&pv_done[g], (j - 1) & 1);
-        tc_fence_after();
-      }
-      token_wait();
-      {
-        const unsigned long long sc2 = pack_f2(p.scale_log2, p.scale_log2), nm2 = pack_f2(-m_scaled, -m_scaled);
-        unsigned long long l2 = pack_f2(0.f, 0.f);
-#pragma unroll
-        for (int q = 0; q < WC / 8; ++q) {
-          float e[8];
-#pragma unroll
-          for (int i = 0; i < 8; i += 2) {
-            float xa, xb;
-            unpack_f2(fma_f2(pack_f2(__uint_as_float(keep[q * 8 + i]), __uint_as_float(keep[q * 8 + i + 1])), sc2, nm2), xa, xb);
-            e[i] = ex2_mufu(xa);
-            e[i + 1] = ex2_mufu(xb);
-            if (need_mask && !(kv0 + hw * WC + q * 8 + i < p.Nk)) e[i] = 0.f;
-            if (need_mask && !(kv0 + hw * WC + q * 8 + i + 1 < p.Nk)) e[i + 1] = 0.f;
-            l2 = add_f2(l2, pack_f2(e[i], e[i + 1]));
-          }
-          const uint4 pk = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
-          *reinterpret_cast<uint4*>(prow + (((chunk0 + q) ^ (r & 7)) << 4)) = pk;
-        }
-        float la, lb;
-        unpack_f2(l2, la, lb);
-        l_sum += la + lb;
-      }
-      if (!(j == ntiles - 1 && g == G - 1)) token_pass();   // (the ring is primed once: skip the one surplus hand-over)
-      if (rescale) {      // j > 0: O is settled (pv_done waited above); not MUFU work, so after the hand-over
-#pragma unroll 1
-        for (int c = oc_begin; c < oc_end; ++c) {
-          uint32_t o[16];
-          tmem_ld16(tmem_O + c * 16, o);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-          tmem_st16(tmem_O + c * 16, o);
-        }
-        tmem_wait_st();
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[g]);
-    }
-    sxl[hw * 128 + r] = l_sum;
-    pair_sync();
-    l_sum += sxl[(hw ^ 1) * 128 + r];
-    mbar_wait(&pv_done[g], (ntiles - 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.f / l_sum;
-    const bool row_ok = q_idx < p.Nq;
-    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.q_bs + q_idx) * p.ldo + head * p.dv;
-#pragma unroll 1
-    for (int c = oc_begin; c < oc_end; ++c) {
-      uint32_t o[16];
-      tmem_ld16(tmem_O + c * 16, o);
-      tmem_wait_ld();
-      if (row_ok) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int col = c * 16 + q * 8;
-          if (col + 8 <= p.dv) {
-            const uint4 pk = make_uint4(
-                pack_bf16x2(__uint_as_float(o[q * 8]) * inv_l, __uint_as_float(o[q * 8 + 1]) * inv_l),
-                pack_bf16x2(__uint_as_float(o[q * 8 + 2]) * inv_l, __uint_as_float(o[q * 8 + 3]) * inv_l),
-                pack_bf16x2(__uint_as_float(o[q * 8 + 4]) * inv_l, __uint_as_float(o[q * 8 + 5]) * inv_l),
-                pack_bf16x2(__uint_as_float(o[q * 8 + 6]) * inv_l, __uint_as_float(o[q * 8 + 7]) * inv_l));
-            *reinterpret_cast<uint4*>(orow + col) = pk;
-          }
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
-}
+// (Round 1 left a "ping-pong" variant here — 2-3 query tiles per CTA taking turns on the MUFU pipe through named barriers, with
+// the single S buffer released only after P was written.  First GPU run, round 2: 566 us (G = 2) / 596 us (G = 3) against
+// 459 us for the kernel above on the B = 8, N = 4096, d = 40 launch (profiles/r02_visit_a_pending_variants.log): the S round
+// trip through the MMA warp stayed on every group's critical path.  Removed; the two-tile kernels below release S early.)
 
 #ifdef VDB_TIMELINE   // two-tile kernel: 24 slots per kv tile (tools/attention_fa_timeline.py)
 #define VDB_FTL(slot, j, who) do { if (p.timeline && (who) && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (j) < 16) p.timeline[(j) * 24 + (slot)] = gtime(); } while (0)
@@ -1166,7 +896,9 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
 // (tools/mufu_mix_bench.cu) shows two warps per sub-partition feed the pipe at 97 % with this instruction mix.
 //   warps: 0 TMA, 1 MMA, 2-3 idle, 4 + 8 g + 4 h + quarter = softmax group g (query tile), column half h.
 //   named barriers: 1 / 2 = MUFU token of group 0 / 1 (256 waiting + 256 arriving), 3 + 4 g + quarter = row-max exchange.
-//   registers: control warpgroup 80, softmax warpgroups 104 (1 + 4 warps per sub-partition: 80 + 4 x 104 = 496 <= 512).
+//   registers: 96 per thread for all 20 warps (640 x 96 = the CTA's whole allocation).  No setmaxnreg here: the pool it
+//   redistributes is the CTA's launch allocation (20 warps x 96), and an increase beyond it blocks forever — the first version
+//   of this kernel hung on exactly that (control 80 + softmax 104 > pool).
 // ---------------------------------------------------------------------------------------------------------------------
 template <int DVP, int KV_STAGES>
 constexpr size_t attention_fa2_smem_bytes() {
@@ -1240,7 +972,6 @@ __global__ void __launch_bounds__(640, 1) attention_fa2_kernel(const __grid_cons
   pdl_wait();
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     if (warp == 0) {
       if (lane == 0) {
         mbar_arrive_expect_tx(q_full, 2 * kQBytes);
@@ -1308,7 +1039,6 @@ __global__ void __launch_bounds__(640, 1) attention_fa2_kernel(const __grid_cons
     }
   } else {
     // ------------------------------ softmax group g, column half hw ------------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int g = (warp - 4) >> 3;
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int hw = ((warp - 4) & 7) >> 2;         // which 64 score columns / which half of the O columns
@@ -1404,7 +1134,7 @@ __global__ void __launch_bounds__(640, 1) attention_fa2_kernel(const __grid_cons
       {
         const unsigned long long sc2 = pack_f2(p.scale_log2, p.scale_log2), nm2 = pack_f2(-m_scaled, -m_scaled);
         unsigned long long l2 = pack_f2(0.f, 0.f), l2b = pack_f2(0.f, 0.f);
-        uint32_t pk[32];
+        uint32_t pk[16];
 #pragma unroll
         for (int q = 0; q < WC / 8; ++q) {
           float e[8];
@@ -1423,9 +1153,9 @@ __global__ void __launch_bounds__(640, 1) attention_fa2_kernel(const __grid_cons
             if (i & 2) l2b = add_f2(l2b, pack_f2(e[i], e[i + 1])); else l2 = add_f2(l2, pack_f2(e[i], e[i + 1]));
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) pk[q * 4 + i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
+          for (int i = 0; i < 4; ++i) pk[(q & 3) * 4 + i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
+          if ((q & 3) == 3) tmem_st16(tmem_P + (q >> 2) * 16, pk);   // 32 probabilities = 16 packed columns per store
         }
-        tmem_st32(tmem_P, pk);                    // this half row's 64 probabilities as 32 packed columns
         float la, lb;
         unpack_f2(add_f2(l2, l2b), la, lb);
         l_sum += la + lb;
@@ -1499,30 +1229,6 @@ static int launch_attention(AttnParams& p, const AttnArgs& a, cudaStream_t strea
   count_launch();
   return VDB_OK;
 }
-
-template <int DVP, int G, int KV_STAGES>
-static int launch_attention_pp(AttnParams& p, const AttnArgs& a, cudaStream_t stream) {
-  constexpr size_t smem = attention_pp_smem_bytes<DVP, G, KV_STAGES>();
-  static_assert(smem <= 227 * 1024, "attention (ping-pong) smem budget");
-  auto kernel = attention_pp_kernel<DVP, G, KV_STAGES>;
-  static bool configured = false;
-  if (!configured) {
-    VDB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    prefer_max_smem(kernel);
-    configured = true;
-  }
-  int rc = make_tmap_2d(&p.tmQ, a.Q, static_cast<uint64_t>(a.ldq), static_cast<uint64_t>(a.B) * a.q_bstride, a.ldq * 2, 64, kBQ);
-  if (rc) return rc;
-  rc = make_tmap_2d(&p.tmK, a.K, static_cast<uint64_t>(a.ldk), static_cast<uint64_t>(a.B) * a.kv_bstride, a.ldk * 2, 64, 64);
-  if (rc) return rc;
-  rc = make_tmap_2d(&p.tmV, a.Vt, static_cast<uint64_t>(a.B) * a.kv_bstride, static_cast<uint64_t>(a.H) * DVP, a.ldv * 2, 64, DVP);
-  if (rc) return rc;
-  dim3 grid((p.Nq + G * kBQ - 1) / (G * kBQ), a.H, a.B);
-  VDB_CUDA_CHECK(launch_pdl(kernel, grid, dim3(64 + 256 * G), smem, stream, p));
-  count_launch();
-  return VDB_OK;
-}
-
 
 template <int DVP, int KV_STAGES, int POLY, int TOKEN, int PT, int PH>
 static int launch_attention_fa(AttnParams& p, const AttnArgs& a, cudaStream_t stream) {
@@ -1661,24 +1367,15 @@ int vdb_attention_bf16(const void* Q, long long ldq, int q_col0, const void* K, 
   //                    of a 128-column tile are masked padding)
   //   VDB_ATT_BKV=128  the 128-column kernel everywhere
   // default: the three-CTA kernel for short contexts (65..512 keys), the 128-column kernel otherwise
-  // VDB_ATT_PP=2|3: the ping-pong kernel (2 or 3 query tiles per CTA taking turns on the MUFU pipe) for long, unmasked contexts
-  static const int pp = [] { const char* e = getenv("VDB_ATT_PP"); const int v = e ? atoi(e) : 0; return (v == 2 || v == 3) ? v : 0; }();
-  if (pp && DK == 64 && !causal && Nk >= 256 && Nq >= 256) {
-    if (DVP == 48) return pp == 2 ? launch_attention_pp<48, 2, 4>(p, a, st) : launch_attention_pp<48, 3, 4>(p, a, st);
-    if (DVP == 64) return pp == 2 ? launch_attention_pp<64, 2, 4>(p, a, st) : launch_attention_pp<64, 3, 4>(p, a, st);
-  }
-  // VDB_ATT_FA: the two-tile kernel (attention_fa_kernel).  0 = off; otherwise digits "[S]PT": P = exp2 pairs of every 8 on
-  // the FMA pipe (0..4), T = MUFU token: 0 free-running, 1 passed at the end of a tile's exp2 phase, 2 / 3 after 3/4 / 1/2 of it, leading 1 = P through shared memory (SS product)
-  // instead of tensor memory.  e.g. 21 = two of eight pairs, token, P in tensor memory; 121 = the same with P in shared memory.
   // VDB_ATT_FA2: the column-split two-tile kernel (attention_fa2_kernel, default): digits "PT" as below; 0 = off (falls to VDB_ATT_FA)
   static const int fa2 = [] { const char* e = getenv("VDB_ATT_FA2"); return e ? atoi(e) : -1; }();
-  if (fa2 != 0 && !pp && DK == 64 && !causal && Nk >= 512 && Nq >= 256 && (Nq % 256) == 0 && !getenv("VDB_ATT_FA")) {
+  if (fa2 != 0 && DK == 64 && !causal && Nk >= 512 && Nq >= 256 && (Nq % 256) == 0 && !getenv("VDB_ATT_FA")) {
     const int mode = fa2 < 0 ? 21 : fa2;
     if (DVP == 48) return dispatch_attention_fa2<48>(mode, p, a, st);
     if (DVP == 64) return dispatch_attention_fa2<64>(mode, p, a, st);
   }
   static const int fa = [] { const char* e = getenv("VDB_ATT_FA"); return e ? atoi(e) : -1; }();
-  if (fa != 0 && !pp && DK == 64 && !causal && Nk >= 512 && Nq >= 256 && (Nq % 256) == 0) {
+  if (fa != 0 && DK == 64 && !causal && Nk >= 512 && Nq >= 256 && (Nq % 256) == 0) {
     const int mode = fa < 0 ? 21 : fa;
     if (DVP == 48) return dispatch_attention_fa<48>(mode, p, a, st);
     if (DVP == 64) return dispatch_attention_fa<64>(mode, p, a, st);
