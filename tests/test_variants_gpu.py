@@ -14,15 +14,10 @@ VARIANTS = [
     ({"VDB_ATT_BKV": "64"}, "attention"),          # 64-column kv tiles, double-buffered S / P           (validated, round 1)
     ({"VDB_ATT_BKV": "643"}, "attention"),         # three CTAs per SM                                     (validated, round 1)
     ({"VDB_ATT_BKV": "128"}, "attention"),         # the 128-column kernel for every context length        (validated, round 1)
-    ({"VDB_ATT_PP": "2"}, "attention"),            # ping-pong, two query tiles per CTA                    (NOT yet run on a GPU)
-    ({"VDB_ATT_PP": "3"}, "attention"),            # ping-pong, three query tiles per CTA                  (NOT yet run on a GPU)
     ({"VDB_GN_REG": "0"}, "groupnorm"),            # generic two-read single-launch GroupNorm              (validated, round 1)
     ({"VDB_GN_FUSED": "0"}, "groupnorm"),          # statistics + apply kernels                            (validated, round 1)
-    ({"VDB_GN_CLUSTER": "5"}, "groupnorm"),        # thread-block-cluster GroupNorm, pixels kept in smem    (NOT yet run on a GPU)
-    ({"VDB_GN_CLUSTER": "7"}, "groupnorm"),        # cluster GroupNorm, two-read path                       (NOT yet run on a GPU)
-    ({"VDB_LN_V2": "1"}, "layernorm"),             # persistent LayerNorm with software prefetch          (NOT yet run on a GPU)
     ({"VDB_PAIR": "1"}, "gemm or conv3x3"),        # CTA pairs (cta_group::2)                              (validated, round 1)
-    ({"VDB_NFAST": "2"}, "gemm or conv3x3"),       # N-fast tile order wherever it is legal                (NOT yet run on a GPU)
+    ({"VDB_NFAST": "2"}, "gemm or conv3x3"),       # N-fast tile order wherever it is legal                (validated, round 2: no gain)
     ({"VDB_IGEMM_SPEC": "0"}, "gemm or conv3x3"),  # generic epilogue only
     ({"VDB_EPI_TMA": "0"}, "gemm or conv3x3"),     # transposing epilogues instead of the TMA-store ones (round-1 default)
     ({"VDB_GN_BUNDLE": "0"}, "groupnorm"),         # single-launch pixel-range GroupNorm instead of the group-bundle kernel
@@ -46,7 +41,7 @@ def test_variant(env, select):
 
 @RUN
 def test_folded_upsample_conv_kernel():
-    """conv modes 3..6 + interleave2x2 (NOT yet run on a GPU) against torch's upsample + conv2d on the bf16-rounded operands."""
+    """conv modes 3..6 + interleave2x2 against torch's upsample + conv2d on the bf16-rounded operands."""
     import torch
     import torch.nn.functional as F
     sys.path.insert(0, os.path.join(ROOT, "versatile-diffusion_b200"))

@@ -491,14 +491,9 @@ __global__ void __launch_bounds__(kGnThreads, 2) gn_fused_kernel(const __nv_bflo
 }
 
 // ---------------------------------------------------------------------------------------------
-// Cluster GroupNorm (opt-in, VDB_GN_CLUSTER=1; written at the end of round 1 and NOT yet measured).  The single-launch kernel
-// above pays a device-wide round trip per GroupNorm (global partial rows, an atomic arrival counter polled by every CTA)
-// and reads its pixels twice; it reaches 1.6-2.1 TB/s on the 64x64 layers.  Here the CL CTAs of one image form a
-// thread-block cluster: partial statistics are exchanged through distributed shared memory and the only synchronisation
-// is the hardware cluster barrier, so there is no residency requirement and no global scratch.  KEEP = true: the CTA's
-// pixel range (<= 160 KB) stays in shared memory between the statistics and the normalisation (x is read once).
-// grid (CL, B), cluster (CL, 1, 1), block 512; CTA r of the cluster owns pixels [r * ceil(HW / CL), ...).
-// Deterministic: fixed-order reductions, every CTA folds the CL partial rows in rank order.
+// (Round 1 left a thread-block-cluster GroupNorm here — the CTAs of one image as a 16-CTA cluster, pixel ranges kept in 160 KB
+// of shared memory.  First GPU run, round 2: 45 us against 26 us for the single-launch kernel above on the 64x64 C = 320 layer,
+// slower on every UNet shape (profiles/r02_visit_a_pending_variants.log).  Removed; the group-bundle kernel below replaces it.)
 // ---------------------------------------------------------------------------------------------
 VDB_DEVINL float ld_dsmem_f32(uint32_t cluster_addr) {
   float v;
@@ -507,155 +502,6 @@ VDB_DEVINL float ld_dsmem_f32(uint32_t cluster_addr) {
 }
 VDB_DEVINL void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 VDB_DEVINL void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-
-template <bool KEEP>
-__global__ void __launch_bounds__(kGnThreads, 1) gn_cluster_kernel(const __nv_bfloat16* __restrict__ x1, int C1,
-                                                                   const __nv_bfloat16* __restrict__ x2, int C2, int HW,
-                                                                   int groups, float eps, int act,
-                                                                   const float* __restrict__ gamma,
-                                                                   const float* __restrict__ beta,
-                                                                   __nv_bfloat16* __restrict__ y) {
-  constexpr int UNR = 8;
-  constexpr int kMaxCPT = 6;
-  const int C = C1 + C2;
-  const int V = C / 8;
-  const int cpg = C / groups;
-  const int b = blockIdx.y, rank = blockIdx.x, CL = gridDim.x;
-  pdl_launch_dependents();
-  pdl_wait();
-  const int pix_per = (HW + CL - 1) / CL;
-  const int p_begin = rank * pix_per;
-  const int p_end = min(HW, p_begin + pix_per);
-  __shared__ float part[kGnThreads * 16];   // phase 1: reduction scratch; phase 2: per-channel scale | shift
-  __shared__ float cpart[64];               // this CTA's {sum, sumsq} per group: read by the whole cluster through DSMEM
-  __shared__ float gmean[32], grstd[32];
-  extern __shared__ __align__(16) uint8_t gn_tile_raw[];
-  uint4* tile = reinterpret_cast<uint4*>(gn_tile_raw);   // KEEP: [pix_per][V] raw vectors of this CTA's pixels
-  const int lanes = kGnThreads / V;
-  const int v = threadIdx.x % V;
-  const int pl = threadIdx.x / V;
-  const bool active = pl < lanes;
-  const bool first = v * 8 < C1;
-  const __nv_bfloat16* src = first ? x1 + static_cast<long long>(b) * HW * C1 + v * 8
-                                   : x2 + static_cast<long long>(b) * HW * C2 + (v * 8 - C1);
-  const long long Cs = first ? C1 : C2;
-  // ---- phase 1 ----
-  if (active) {
-    float s[8], q[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
-    for (int p = p_begin + pl; p < p_end; p += UNR * lanes) {
-      uint4 u[UNR];
-#pragma unroll
-      for (int k = 0; k < UNR; ++k)
-        u[k] = (p + k * lanes < p_end) ? __ldg(reinterpret_cast<const uint4*>(src + (p + k * lanes) * Cs)) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-      for (int k = 0; k < UNR; ++k) {
-        if (KEEP && p + k * lanes < p_end) tile[static_cast<size_t>(p + k * lanes - p_begin) * V + v] = u[k];
-        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = unpack_bf16x2(w[i]);
-          s[2 * i] += f.x; q[2 * i] += f.x * f.x;
-          s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
-        }
-      }
-    }
-    float* dst = part + (static_cast<size_t>(pl) * V + v) * 16;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { dst[i] = s[i]; dst[8 + i] = q[i]; }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += kGnThreads) {
-    float s = 0.f, q = 0.f;
-    for (int l = 0; l < lanes; ++l) {
-      const float* ps = part + (static_cast<size_t>(l) * V + c / 8) * 16 + (c & 7);
-      s += ps[0]; q += ps[8];
-    }
-    float* own = part + (static_cast<size_t>(c / 8)) * 16 + (c & 7);
-    own[0] = s; own[8] = q;
-  }
-  __syncthreads();
-  if (threadIdx.x < groups) {
-    float s = 0.f, q = 0.f;
-    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
-      const float* ps = part + (static_cast<size_t>(c / 8)) * 16 + (c & 7);
-      s += ps[0]; q += ps[8];
-    }
-    cpart[2 * threadIdx.x] = s;
-    cpart[2 * threadIdx.x + 1] = q;
-  }
-  float gam[kMaxCPT], bet[kMaxCPT];      // in flight across the cluster barrier
-#pragma unroll
-  for (int k = 0; k < kMaxCPT; ++k) {
-    const int c = threadIdx.x + k * kGnThreads;
-    gam[k] = (c < C) ? __ldg(gamma + c) : 0.f;
-    bet[k] = (c < C) ? __ldg(beta + c) : 0.f;
-  }
-  // ---- every CTA of the image has published its partials ----
-  cluster_arrive();
-  cluster_wait();
-  if (threadIdx.x < 2 * groups) {          // thread t folds column t of the CL partial rows, in rank order
-    const uint32_t mine = smem_u32(&cpart[threadIdx.x]);
-    float acc = 0.f;
-    for (int r = 0; r < CL; ++r) acc += ld_dsmem_f32(mapa_u32(mine, static_cast<uint32_t>(r)));
-    part[6144 + threadIdx.x] = acc;
-  }
-  __syncthreads();
-  cluster_arrive();                        // "I am done reading my peers' shared memory" (waited for before exit)
-  if (threadIdx.x < groups) {
-    const float s = part[6144 + 2 * threadIdx.x], q = part[6144 + 2 * threadIdx.x + 1];
-    const float inv_n = 1.0f / (static_cast<float>(HW) * cpg);
-    const float mean = s * inv_n;
-    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
-    gmean[threadIdx.x] = mean;
-    grstd[threadIdx.x] = rsqrtf(var + eps);
-  }
-  __syncthreads();
-  float* scale = part;
-  float* shift = part + C;
-#pragma unroll
-  for (int k = 0; k < kMaxCPT; ++k) {
-    const int c = threadIdx.x + k * kGnThreads;
-    if (c < C) {
-      const int g = c / cpg;
-      const float sc = grstd[g] * gam[k];
-      scale[c] = sc;
-      shift[c] = bet[k] - gmean[g] * sc;
-    }
-  }
-  __syncthreads();
-  // ---- phase 2 ----
-  if (active) {
-    __nv_bfloat16* dstb = y + static_cast<long long>(b) * HW * C + v * 8;
-    const int c0 = v * 8;
-    for (int p = p_begin + pl; p < p_end; p += UNR * lanes) {
-      uint4 u[UNR];
-#pragma unroll
-      for (int k = 0; k < UNR; ++k)
-        if (p + k * lanes < p_end)
-          u[k] = KEEP ? tile[static_cast<size_t>(p + k * lanes - p_begin) * V + v]
-                      : __ldg(reinterpret_cast<const uint4*>(src + (p + k * lanes) * Cs));
-#pragma unroll
-      for (int k = 0; k < UNR; ++k) {
-        if (p + k * lanes < p_end) {
-          const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-          uint32_t o[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = unpack_bf16x2(w[i]);
-            float a = f.x * scale[c0 + 2 * i] + shift[c0 + 2 * i];
-            float bb = f.y * scale[c0 + 2 * i + 1] + shift[c0 + 2 * i + 1];
-            if (act == 1) { a = silu_bf16_f(a); bb = silu_bf16_f(bb); }
-            o[i] = pack_bf16x2(a, bb);
-          }
-          *reinterpret_cast<uint4*>(dstb + static_cast<long long>(p + k * lanes) * C) = make_uint4(o[0], o[1], o[2], o[3]);
-        }
-      }
-    }
-  }
-  cluster_wait();                          // no CTA leaves while a peer may still read its cpart
-}
 
 // ---------------------------------------------------------------------------------------------
 // Group-bundle GroupNorm (round 2, default wherever it fits): a CTA owns a BUNDLE of G consecutive groups of ONE image
@@ -935,99 +781,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   }
 }
 
-// Persistent LayerNorm with software prefetch (opt-in VDB_LN_V2=1, unmeasured): the kernel above runs 3.5 waves of short-lived
-// CTAs on the 32768 x 320 layers (load everything, compute, store, exit: 2.3 TB/s in-graph); here grid = resident CTAs, every
-// warp walks its rows R at a time and requests the NEXT R rows before it normalises the current ones, so loads, math and
-// stores of different iterations overlap.  C <= 512 (two 16-byte vectors per lane).
-template <int R>
-__global__ void __launch_bounds__(256) layernorm_pf_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C,
-                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           float eps, __nv_bfloat16* __restrict__ y) {
-  constexpr int MAXV = 2;
-  pdl_launch_dependents();
-  pdl_wait();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int V = C / 8;
-  const long long stride = static_cast<long long>(nwarps) * R;
-  // this lane's gamma / beta (fixed columns) stay in registers for the whole walk
-  float gg[MAXV][8], bb[MAXV][8];
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int v = lane + i * 32;
-    if (v < V) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
-      gg[i][0] = g0.x; gg[i][1] = g0.y; gg[i][2] = g0.z; gg[i][3] = g0.w; gg[i][4] = g1.x; gg[i][5] = g1.y; gg[i][6] = g1.z; gg[i][7] = g1.w;
-      bb[i][0] = b0.x; bb[i][1] = b0.y; bb[i][2] = b0.z; bb[i][3] = b0.w; bb[i][4] = b1.x; bb[i][5] = b1.y; bb[i][6] = b1.z; bb[i][7] = b1.w;
-    }
-  }
-  auto load_rows = [&](long long r0, uint4 (&raw)[R][MAXV]) {
-#pragma unroll
-    for (int j = 0; j < R; ++j)
-#pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        const int v = lane + i * 32;
-        if (v < V && r0 + j < rows) raw[j][i] = __ldg(reinterpret_cast<const uint4*>(x + (r0 + j) * C + v * 8));
-      }
-  };
-  uint4 cur[R][MAXV], nxt[R][MAXV];
-  long long r0 = static_cast<long long>(warp) * R;
-  if (r0 < rows) load_rows(r0, cur);
-  for (; r0 < rows; r0 += stride) {
-    if (r0 + stride < rows) load_rows(r0 + stride, nxt);      // in flight while the current rows are normalised
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-      if (r0 + j >= rows) break;   // warp-uniform
-      float f[MAXV][8];
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        if (lane + i * 32 < V) {
-          const uint32_t w[4] = {cur[j][i].x, cur[j][i].y, cur[j][i].z, cur[j][i].w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 t = unpack_bf16x2(w[k]);
-            f[i][2 * k] = t.x; f[i][2 * k + 1] = t.y;
-            s += t.x + t.y;
-          }
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      const float mean = s / C;
-      float q = 0.f;
-#pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        if (lane + i * 32 < V) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) { const float d = f[i][k] - mean; q += d * d; }
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-      const float rstd = rsqrtf(q / C + eps);
-#pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        const int v = lane + i * 32;
-        if (v < V) {
-          uint32_t o[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            o[k] = pack_bf16x2((f[i][2 * k] - mean) * rstd * gg[i][2 * k] + bb[i][2 * k],
-                               (f[i][2 * k + 1] - mean) * rstd * gg[i][2 * k + 1] + bb[i][2 * k + 1]);
-          *reinterpret_cast<uint4*>(y + (r0 + j) * C + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < R; ++j)
-#pragma unroll
-      for (int i = 0; i < MAXV; ++i) cur[j][i] = nxt[j][i];
-  }
-}
-
+// (Round 1's persistent prefetching variant of this kernel measured 12.8 us against 17.8 us on the 32768 x 320 layers; the
+// row-group kernel below reaches 10.1 us and replaced both as the default: profiles/r02_visit_b_summary.log.)
 // Row-group LayerNorm (round 2, default when C = 8 * VPL * LPR fits): LPR lanes share a row, each lane owns VPL 16-byte
 // vectors (vector l + k * LPR: consecutive lanes read consecutive 16-byte pieces), so a warp covers 32 / LPR rows per
 // step with EVERY lane busy — the warp-per-row kernel above leaves 24 of 32 lanes idle on the second vector of a
@@ -1722,48 +1477,6 @@ int vdb_groupnorm_nhwc(const void* x1, int C1, const void* x2, int C2, int B, in
       if (n <= 12) return launch(gn_bundle_kernel<12, 512>, 512, S);
     }
   }
-  // cluster variant (VDB_GN_CLUSTER, opt-in until measured; bit 0 = on, bit 1 = never keep the pixels in shared memory,
-  // bit 2 = any batch size): UNet-sized layers only (the VAE's 512x512 layers have too few images to fill the machine with
-  // <= 16 CTAs per image)
-  static const int cluster_mode = [] { const char* ev = getenv("VDB_GN_CLUSTER"); return ev ? atoi(ev) : 0; }();
-  if ((cluster_mode & 1) && C <= 3072 && HW >= 16 && HW <= 16384 && ((cluster_mode & 4) || B * 8 >= num_sms() / 4)) {
-    static int max_cl = 16;                       // drops to 8 if the device refuses 16-CTA (non-portable) clusters
-    int CL = 1;
-    while (CL * 2 <= max_cl && CL * 2 * 8 <= HW) CL *= 2;
-    const int pix_per = (HW + CL - 1) / CL;
-    const size_t tile_bytes = static_cast<size_t>(pix_per) * C * 2;
-    const bool keep = !(cluster_mode & 2) && tile_bytes <= 160 * 1024;
-    const __nv_bfloat16* x1b = reinterpret_cast<const __nv_bfloat16*>(x1);
-    const __nv_bfloat16* x2b = reinterpret_cast<const __nv_bfloat16*>(x2);
-    __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y);
-    static bool configured = false;
-    if (!configured) {
-      VDB_CUDA_CHECK(cudaFuncSetAttribute(gn_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      VDB_CUDA_CHECK(cudaFuncSetAttribute(gn_cluster_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-      VDB_CUDA_CHECK(cudaFuncSetAttribute(gn_cluster_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-      configured = true;
-    }
-    for (;;) {
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(CL, B); cfg.blockDim = dim3(kGnThreads); cfg.stream = st;
-      cfg.dynamicSmemBytes = keep ? tile_bytes : 0;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr; cfg.numAttrs = 1;
-      cudaError_t err = keep ? cudaLaunchKernelEx(&cfg, gn_cluster_kernel<true>, x1b, C1, x2b, C2, HW, groups, eps, act, gamma, beta, yb)
-                             : cudaLaunchKernelEx(&cfg, gn_cluster_kernel<false>, x1b, C1, x2b, C2, HW, groups, eps, act, gamma, beta, yb);
-      if (err == cudaSuccess) break;
-      if (CL == 16 && max_cl == 16) {            // 16-CTA clusters not schedulable here: retry once with 8 (needs a new tile size)
-        cudaGetLastError();
-        max_cl = 8;
-        return vdb_groupnorm_nhwc(x1, C1, x2, C2, B, HW, groups, gamma, beta, eps, act, scratch, y, stream);
-      }
-      return set_error(VDB_ERR_CUDA, "groupnorm (cluster): launch failed: %s", cudaGetErrorString(err));
-    }
-    count_launch(1);
-    return VDB_OK;
-  }
   static const bool fused_ok = [] { const char* ev = getenv("VDB_GN_FUSED"); return !(ev && ev[0] == '0'); }();
   // register-resident variant for the small layers (VDB_GN_REG=0 turns it off)
   static const bool reg_ok = [] { const char* ev = getenv("VDB_GN_REG"); return !(ev && ev[0] == '0'); }();
@@ -1842,14 +1555,6 @@ int vdb_layernorm(const void* x, long long rows, int C, const float* gamma, cons
       case 32: return launch_rg(layernorm_rg_kernel<4, 8>, 4);      // C 256
       default: break;
     }
-  }
-  static const bool ln_v2 = [] { const char* ev = getenv("VDB_LN_V2"); return ev && ev[0] == '1'; }();
-  if (ln_v2 && V <= 64 && rows >= 4096) {
-    static const int occ = [] { int n = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, layernorm_pf_kernel<2>, 256, 0); return std::max(n, 1); }();
-    const int grid = static_cast<int>(std::min<long long>((rows + 8 * 2 - 1) / (8 * 2), static_cast<long long>(occ) * num_sms()));
-    VDB_CUDA_CHECK(launch_pdl(layernorm_pf_kernel<2>, dim3(grid), dim3(threads), 0, st, xp, rows, C, gamma, beta, eps, yp));
-    count_launch();
-    return VDB_OK;
   }
   VDB_PREFER_MAX_SMEM((layernorm_kernel<2, 4>));
   VDB_PREFER_MAX_SMEM((layernorm_kernel<5, 2>));
