@@ -471,7 +471,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
 //   128 scores live in registers across the whole tile.
 //   MMA issue order (steady state): PV_0(j), S_0(j+2), PV_1(j), S_1(j+2), ...
 // ---------------------------------------------------------------------------------------------------------------------
-template <int DVP, int KV_STAGES, int PT>
+template <int DVP, int KV_STAGES, int PT = 1>
 constexpr size_t attention_fa_smem_bytes() {
   return 2 * kBQ * 128 + KV_STAGES * (128 * 128 + 2 * DVP * 128) + (PT ? 0 : 2 * (2 * kBQ * 128)) + 32 * 8 + 1024;
 }
@@ -497,8 +497,9 @@ VDB_DEVINL void ex2_poly2(float xa, float xb, float& ea, float& eb) {
   eb = __int_as_float(__float_as_int(pb) + (__float_as_int(rb) << 23));
 }
 
-template <int DVP, int KV_STAGES, int POLY, int TOKEN, int PT, int PH>
+template <int DVP, int KV_STAGES, int POLY, int TOKEN>
 __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_constant__ AttnParams p) {
+  constexpr int PT = 1;   // P in tensor memory (TS product).  PT = 0 (P through shared memory, SS product) measured the same: 350 vs 347 us
   constexpr int BKV = 128;
   constexpr uint32_t kQBytes = kBQ * 128;          // one warpgroup's Q tile (DK = 64: one K atom)
   constexpr uint32_t kKBytes = BKV * 128;          // one K stage (128 keys x 64 channels)
@@ -742,63 +743,8 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
           tmem_wait_st();
         }
       }
-      if constexpr (PH) {
-        // ---- phase-split tile (round 2, default).  Measured (profiles/r02_attention_fa_timeline_v2.txt): a softmax warp alone on
-        // its SM sub-partition issues MUFU.EX2 at only ~62 % of the pipe rate when the scale FFMAs, row sums, bf16 packs and P
-        // stores are interleaved with it (fixed issue stalls after every MUFU; nothing of the SAME warp fills them), so the two
-        // groups' exp2 phases — serialised by the token — set the kernel's pace at 2 x 800 ns per tile pair.  Here the token
-        // covers ONLY a dense run of MUFU.EX2 (in place on the row's 128 registers); everything else of the tile — scaling and the
-        // FMA-pipe exponentials before it (A), row sum / pack / P store after it (C) — runs while the OTHER group owns the pipe.
-        const unsigned long long sc2 = pack_f2(p.scale_log2, p.scale_log2), nm2 = pack_f2(-m_scaled, -m_scaled);
-#pragma unroll
-        for (int i = 0; i < BKV; i += 2) {            // A: x = s * scale - m  (and 2^x on the FMA pipe for the POLY pairs of every 8)
-          float xa, xb;
-          unpack_f2(fma_f2(pack_f2(__uint_as_float(keep[i]), __uint_as_float(keep[i + 1])), sc2, nm2), xa, xb);
-          if (((i >> 1) & 7) >= 8 - POLY) ex2_poly2(xa, xb, xa, xb);
-          keep[i] = __float_as_uint(xa);
-          keep[i + 1] = __float_as_uint(xb);
-        }
+      {
         token_wait();
-        VDB_FTL(8 * g + 4, j, tlw);
-#pragma unroll
-        for (int i = 0; i < BKV; i += 2) {            // M: the MUFU run (volatile: stays between the two barrier instructions)
-          if (((i >> 1) & 7) < 8 - POLY) {
-            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(keep[i]));
-            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(keep[i + 1]));
-          }
-        }
-        VDB_FTL(8 * g + 5, j, tlw);
-        if (!(j == ntiles - 1 && g == 1)) token_pass();   // (the ring is primed once: skip the one surplus hand-over)
-        {                                                 // C: row sum, bf16 pack, P store
-          unsigned long long l2 = pack_f2(0.f, 0.f), l2b = pack_f2(0.f, 0.f);
-          uint32_t pk[PT ? 32 : 4];
-          (void)pk;
-#pragma unroll
-          for (int q = 0; q < BKV / 8; ++q) {
-#pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-              const unsigned long long e2 = pack_f2(__uint_as_float(keep[q * 8 + i]), __uint_as_float(keep[q * 8 + i + 1]));
-              if (i & 2) l2b = add_f2(l2b, e2); else l2 = add_f2(l2, e2);
-            }
-            if constexpr (PT) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                pk[(q & 7) * 4 + i] = pack_bf16x2(__uint_as_float(keep[q * 8 + 2 * i]), __uint_as_float(keep[q * 8 + 2 * i + 1]));
-              if ((q & 7) == 7) tmem_st32(tmem_P + (q >> 3) * 32, pk);
-            } else {
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (q >> 3) * (kBQ * 128) + (((q & 7) ^ (r & 7)) << 4)),
-                           "r"(pack_bf16x2(__uint_as_float(keep[q * 8]), __uint_as_float(keep[q * 8 + 1]))),
-                           "r"(pack_bf16x2(__uint_as_float(keep[q * 8 + 2]), __uint_as_float(keep[q * 8 + 3]))),
-                           "r"(pack_bf16x2(__uint_as_float(keep[q * 8 + 4]), __uint_as_float(keep[q * 8 + 5]))),
-                           "r"(pack_bf16x2(__uint_as_float(keep[q * 8 + 6]), __uint_as_float(keep[q * 8 + 7]))) : "memory");
-            }
-          }
-          float la, lb;
-          unpack_f2(add_f2(l2, l2b), la, lb);
-          l_sum += la + lb;
-        }
-      } else {
-      token_wait();
         VDB_FTL(8 * g + 4, j, tlw);
         {
           const unsigned long long sc2 = pack_f2(p.scale_log2, p.scale_log2), nm2 = pack_f2(-m_scaled, -m_scaled);
@@ -822,11 +768,6 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
               }
               if (i & 2) l2b = add_f2(l2b, pack_f2(e[i], e[i + 1])); else l2 = add_f2(l2, pack_f2(e[i], e[i + 1]));
             }
-            // TOKEN 2 / 3: hand the MUFU token over after 3/4 / 1/2 of the tile's exponentials have been issued: the next
-            // group's ramp-up (barrier latency, first scale FFMAs) then overlaps this group's tail instead of idling the pipe
-            if constexpr (TOKEN >= 2) {
-              if (q == (TOKEN == 2 ? 11 : 7) && !(j == ntiles - 1 && g == 1)) token_pass();
-            }
             if constexpr (PT) {
               // packed bf16 pairs -> 32-bit tensor-memory columns [4 q, 4 q + 4) of this lane's P row; stored 32 columns at a time
   #pragma unroll
@@ -843,9 +784,7 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
           l_sum += la + lb;
         }
         VDB_FTL(8 * g + 5, j, tlw);
-        if constexpr (TOKEN == 1) {
-          if (!(j == ntiles - 1 && g == 1)) token_pass();   // (the ring is primed once: skip the one surplus hand-over)
-        }
+        if (!(j == ntiles - 1 && g == 1)) token_pass();   // (the ring is primed once: skip the one surplus hand-over)
       }
       if constexpr (PT) tmem_wait_st(); else fence_proxy_async_smem();
       tc_fence_before();
@@ -885,321 +824,11 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Two-tile kernel, column-split softmax (round 2b; default).  Same structure as attention_fa_kernel above — one CTA per SM, two
-// 128-row query tiles, single S buffer per tile released as soon as the scores sit in registers, P in tensor memory (TS
-// product), warp-uniform MMA issue, MUFU token between the two tiles' softmax groups — but every query tile is served by EIGHT
-// softmax warps: the two warps of a TMEM lane quarter split the 128 score columns (64 each) and exchange the row max once
-// per tile through shared memory.  Why: with one warp per sub-partition and tile, each warp walked its ~600 instructions per
-// tile at ~0.2 IPC (dependent-issue latency, nothing else to issue on the sub-partition but the other tile's warp):
-// 1.7 us per tile pair against 0.85 us of MUFU work (profiles/r02_attention_fa_timeline_v3.txt); the MUFU probe
-// (tools/mufu_mix_bench.cu) shows two warps per sub-partition feed the pipe at 97 % with this instruction mix.
-//   warps: 0 TMA, 1 MMA, 2-3 idle, 4 + 8 g + 4 h + quarter = softmax group g (query tile), column half h.
-//   named barriers: 1 / 2 = MUFU token of group 0 / 1 (256 waiting + 256 arriving), 3 + 4 g + quarter = row-max exchange.
-//   registers: 96 per thread for all 20 warps (640 x 96 = the CTA's whole allocation).  No setmaxnreg here: the pool it
-//   redistributes is the CTA's launch allocation (20 warps x 96), and an increase beyond it blocks forever — the first version
-//   of this kernel hung on exactly that (control 80 + softmax 104 > pool).
-// ---------------------------------------------------------------------------------------------------------------------
-template <int DVP, int KV_STAGES>
-constexpr size_t attention_fa2_smem_bytes() {
-  return 2 * kBQ * 128 + KV_STAGES * (128 * 128 + 2 * DVP * 128) + 32 * 8 + 2 * (512 + 256) * 4 + 1024;
-}
-
-template <int DVP, int KV_STAGES, int POLY, int TOKEN>
-__global__ void __launch_bounds__(640, 1) attention_fa2_kernel(const __grid_constant__ AttnParams p) {
-  constexpr int BKV = 128;
-  constexpr int WC = 64;                           // score columns per softmax warp and tile
-  constexpr uint32_t kQBytes = kBQ * 128;
-  constexpr uint32_t kKBytes = BKV * 128;
-  constexpr uint32_t kVAtom = DVP * 128;
-  constexpr uint32_t kVBytes = 2 * kVAtom;
-  static_assert(DVP % 16 == 0 && DVP <= 64, "O must fit 64 TMEM columns per query tile");
-  static_assert(KV_STAGES >= 2 && KV_STAGES <= kMaxKvStages, "kv stages");
-  static_assert(kVAtom % 1024 == 0, "V atom must keep 1024B alignment");
-  static_assert(POLY >= 0 && POLY <= 4, "poly pairs per 8 pairs");
-
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                               // [2][16 KB]
-  uint8_t* sK = sQ + 2 * kQBytes;                   // [KV_STAGES][16 KB]
-  uint8_t* sV = sK + KV_STAGES * kKBytes;           // [KV_STAGES][kVBytes]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KV_STAGES * kVBytes);
-  uint64_t* q_full = bars;            // 1
-  uint64_t* k_full = bars + 1;        // [kMaxKvStages]
-  uint64_t* k_empty = bars + 5;       // [kMaxKvStages]
-  uint64_t* v_full = bars + 9;        // [kMaxKvStages]
-  uint64_t* v_empty = bars + 13;      // [kMaxKvStages]
-  uint64_t* s_full = bars + 17;       // [2]
-  uint64_t* s_free = bars + 19;       // [2]  (count 8: one arrive per warp of the group once its scores are in registers)
-  uint64_t* p_full = bars + 21;       // [2]  (count 8)
-  uint64_t* pv_done = bars + 23;      // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 26);
-  float* sx = reinterpret_cast<float*>(bars + 32);   // per group: [2 parity][2 halves][128] row max | [2 halves][128] row sums
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * (2 * kBQ);
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
-  const int ntiles = (p.Nk + BKV - 1) / BKV;
-  constexpr int KS = (DVP + 15) / 16;              // K16 steps of QK^T that can hold non-zero channels (d_head <= DVP)
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmQ);
-    tma_prefetch_desc(&p.tmK);
-    tma_prefetch_desc(&p.tmV);
-  }
-  if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
-    for (int s = 0; s < KV_STAGES; ++s) {
-      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
-      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
-    }
-    for (int g = 0; g < 2; ++g) {
-      mbar_init(&s_full[g], 1);
-      mbar_init(&s_free[g], 8);
-      mbar_init(&p_full[g], 8);
-      mbar_init(&pv_done[g], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc<512>(tmem_holder);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_holder;
-  pdl_launch_dependents();
-  pdl_wait();
-
-  if (warp < 4) {
-    if (warp == 0) {
-      if (lane == 0) {
-        mbar_arrive_expect_tx(q_full, 2 * kQBytes);
-        for (int g = 0; g < 2; ++g)
-          tma_load_2d(sQ + g * kQBytes, &p.tmQ, q_full, p.q_col0 + head * 64, b * p.q_bs + q0 + g * kBQ);
-        for (int j = 0; j < ntiles; ++j) {
-          const int st = j % KV_STAGES;
-          const uint32_t ph = (j / KV_STAGES) & 1;
-          mbar_wait(&k_empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&k_full[st], kKBytes);
-          tma_load_2d(sK + st * kKBytes, &p.tmK, &k_full[st], p.k_col0 + head * 64, b * p.kv_bs + j * BKV);
-          mbar_wait(&v_empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&v_full[st], kVBytes);
-          for (int a = 0; a < 2; ++a)
-            tma_load_2d(sV + st * kVBytes + a * kVAtom, &p.tmV, &v_full[st], b * p.kv_bs + j * BKV + a * 64, head * DVP);
-        }
-      }
-    } else if (warp == 1) {
-      // the whole warp runs the issue loop (convergent control flow); one elected lane issues each tcgen05 instruction.
-      // Issue order (steady state): PV_0(j), S_1(j+1), PV_1(j), S_0(j+2), ... (see attention_fa_kernel)
-      constexpr uint32_t idesc_s = make_idesc_bf16(kBQ, BKV);
-      constexpr uint32_t idesc_o = make_idesc_bf16(kBQ, DVP);
-      auto issue_S = [&](int g, int j) {
-        const int st = j % KV_STAGES;
-        mbar_wait(&k_full[st], (j / KV_STAGES) & 1);
-        tc_fence_after();
-        const uint64_t qd = make_desc_sw128(smem_u32(sQ + g * kQBytes));
-        const uint64_t kd = make_desc_sw128(smem_u32(sK + st * kKBytes));
-#pragma unroll
-        for (int k = 0; k < KS; ++k) umma_bf16_ss_w(tmem_base + g * 128, qd + 2 * k, kd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-        if (g == 1) umma_commit_w(&k_empty[st]);
-        umma_commit_w(&s_full[g]);
-      };
-      auto issue_PV = [&](int g, int j) {
-        const int st = j % KV_STAGES;
-        mbar_wait(&p_full[g], j & 1);                  // P_g(j) written, O_g rescaled
-        mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int a = 0; a < 2; ++a) {
-          const uint64_t vd = make_desc_sw128(smem_u32(sV + st * kVBytes + a * kVAtom));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ts_w(tmem_base + 256 + g * 64, tmem_base + 384 + g * 64 + a * 32 + k * 8, vd + 2 * k, idesc_o,
-                           (j > 0 || a > 0 || k > 0) ? 1u : 0u);
-        }
-        if (g == 1) umma_commit_w(&v_empty[st]);
-        umma_commit_w(&pv_done[g]);
-      };
-      auto next_S = [&](int g, int j) {                // S_g(j) once the group holds S_g(j-1) in registers
-        mbar_wait(&s_free[g], (j - 1) & 1);
-        tc_fence_after();
-        issue_S(g, j);
-      };
-      mbar_wait(q_full, 0);
-      issue_S(0, 0);
-      issue_S(1, 0);
-      if (ntiles > 1) next_S(0, 1);
-      for (int j = 0; j < ntiles; ++j) {
-        issue_PV(0, j);
-        if (j + 1 < ntiles) next_S(1, j + 1);
-        issue_PV(1, j);
-        if (j + 2 < ntiles) next_S(0, j + 2);
-      }
-    }
-  } else {
-    // ------------------------------ softmax group g, column half hw ------------------------------
-    const int g = (warp - 4) >> 3;
-    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int hw = ((warp - 4) & 7) >> 2;         // which 64 score columns / which half of the O columns
-    const int r = quarter * 32 + lane;            // query row inside the group's tile == TMEM lane
-    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const int q_idx = q0 + g * kBQ + r;
-    const uint32_t tmem_S = tmem_base + g * 128 + hw * WC + lane_off;
-    const uint32_t tmem_O = tmem_base + 256 + g * 64 + lane_off;
-    const uint32_t tmem_P = tmem_base + 384 + g * 64 + hw * (WC / 2) + lane_off;   // this half row's 32 packed bf16x2 columns
-    constexpr int OCH = DVP / 16;                 // 16-column O chunks, split between the two warps of a quarter
-    const int oc_begin = hw == 0 ? 0 : (OCH + 1) / 2;
-    const int oc_end = hw == 0 ? (OCH + 1) / 2 : OCH;
-    float* sxm = sx + g * 768;                    // [2 parity][2 halves][128 rows]
-    float* sxl = sxm + 512;                       // [2 halves][128 rows]
-    auto pair_sync = [&] { asm volatile("bar.sync %0, 64;" ::"r"(3 + g * 4 + quarter) : "memory"); };
-    auto token_wait = [&] { if (TOKEN) asm volatile("bar.sync %0, 512;" ::"r"(1 + g) : "memory"); };
-    auto token_pass = [&] { if (TOKEN) asm volatile("bar.arrive %0, 512;" ::"r"(1 + (g ^ 1)) : "memory"); };
-    if (g == 1) token_pass();                     // prime the ring: group 0 goes first
-    float m_ref = -INFINITY;
-    float l_sum = 0.f;
-    for (int j = 0; j < ntiles; ++j) {
-      mbar_wait(&s_full[g], j & 1);
-      tc_fence_after();
-      uint32_t keep[WC];
-      {
-        uint32_t v0[32], v1[32];
-        tmem_ld32(tmem_S, v0);
-        tmem_ld32(tmem_S + 32, v1);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { keep[i] = v0[i]; keep[32 + i] = v1[i]; }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[g]);     // the MMA warp may overwrite S with the next tile's scores
-      const int kv0 = j * BKV + hw * WC;
-      const bool need_mask = j * BKV + BKV > p.Nk;
-      float mx;
-      {
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-        if (need_mask) {
-#pragma unroll
-          for (int i = 0; i < WC; ++i)
-            if (kv0 + i >= p.Nk) keep[i] = 0xff800000u;   // -inf: contributes exp2 = 0 and never wins the max
-        }
-#pragma unroll
-        for (int i = 0; i < WC; i += 8) {
-          m0 = fmaxf(m0, fmaxf(__uint_as_float(keep[i]), __uint_as_float(keep[i + 1])));
-          m1 = fmaxf(m1, fmaxf(__uint_as_float(keep[i + 2]), __uint_as_float(keep[i + 3])));
-          m2 = fmaxf(m2, fmaxf(__uint_as_float(keep[i + 4]), __uint_as_float(keep[i + 5])));
-          m3 = fmaxf(m3, fmaxf(__uint_as_float(keep[i + 6]), __uint_as_float(keep[i + 7])));
-        }
-        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      }
-      sxm[((j & 1) * 2 + hw) * 128 + r] = mx;     // combine with the partner warp's half of the row
-      pair_sync();
-      mx = fmaxf(mx, sxm[((j & 1) * 2 + (hw ^ 1)) * 128 + r]);
-      // lazy rescale decision: warp-uniform (tcgen05.ld / st are warp collectives) and identical in both warps of a quarter
-      // (they see the same 32 rows)
-      const float m_new = fmaxf(m_ref, mx);
-      bool rescale = false;
-      float factor = 1.f;
-      if (j == 0) {
-        m_ref = m_new;
-      } else {
-        const bool want = (m_new - m_ref) * p.scale_log2 > kRescaleThreshold;
-        rescale = __any_sync(0xffffffffu, want);
-        if (rescale) {
-          factor = ex2_mufu((m_ref - m_new) * p.scale_log2);
-          m_ref = m_new;
-          l_sum *= factor;
-        }
-      }
-      const float m_scaled = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;
-      // PV_g(j-1) must have retired: it reads the group's only P buffer and accumulates into O
-      if (j > 0) {
-        mbar_wait(&pv_done[g], (j - 1) & 1);
-        tc_fence_after();
-        if (rescale) {
-#pragma unroll 1
-          for (int c = oc_begin; c < oc_end; ++c) {
-            uint32_t o[16];
-            tmem_ld16(tmem_O + c * 16, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-            tmem_st16(tmem_O + c * 16, o);
-          }
-          tmem_wait_st();
-        }
-      }
-      token_wait();
-      {
-        const unsigned long long sc2 = pack_f2(p.scale_log2, p.scale_log2), nm2 = pack_f2(-m_scaled, -m_scaled);
-        unsigned long long l2 = pack_f2(0.f, 0.f), l2b = pack_f2(0.f, 0.f);
-        uint32_t pk[16];
-#pragma unroll
-        for (int q = 0; q < WC / 8; ++q) {
-          float e[8];
-#pragma unroll
-          for (int i = 0; i < 8; i += 2) {
-            float xa, xb;
-            unpack_f2(fma_f2(pack_f2(__uint_as_float(keep[q * 8 + i]), __uint_as_float(keep[q * 8 + i + 1])), sc2, nm2), xa, xb);
-            // pair index inside a group of 8 pairs (two chunks): the LAST `POLY` pairs go to the FMA pipe
-            const int pair8 = (q & 1) * 4 + (i >> 1);
-            if (pair8 >= 8 - POLY) {
-              ex2_poly2(xa, xb, e[i], e[i + 1]);
-            } else {
-              e[i] = ex2_mufu(xa);
-              e[i + 1] = ex2_mufu(xb);
-            }
-            if (i & 2) l2b = add_f2(l2b, pack_f2(e[i], e[i + 1])); else l2 = add_f2(l2, pack_f2(e[i], e[i + 1]));
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) pk[(q & 3) * 4 + i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
-          if ((q & 3) == 3) tmem_st16(tmem_P + (q >> 2) * 16, pk);   // 32 probabilities = 16 packed columns per store
-        }
-        float la, lb;
-        unpack_f2(add_f2(l2, l2b), la, lb);
-        l_sum += la + lb;
-      }
-      if (!(j == ntiles - 1 && g == 1)) token_pass();   // (the ring is primed once: skip the one surplus hand-over)
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[g]);
-    }
-    sxl[hw * 128 + r] = l_sum;
-    pair_sync();
-    l_sum += sxl[(hw ^ 1) * 128 + r];
-    mbar_wait(&pv_done[g], (ntiles - 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.f / l_sum;
-    const bool row_ok = q_idx < p.Nq;
-    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.q_bs + q_idx) * p.ldo + head * p.dv;
-#pragma unroll 1
-    for (int c = oc_begin; c < oc_end; ++c) {
-      uint32_t o[16];
-      tmem_ld16(tmem_O + c * 16, o);
-      tmem_wait_ld();
-      if (row_ok) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int col = c * 16 + q * 8;
-          if (col + 8 <= p.dv) {
-            const uint4 pk = make_uint4(
-                pack_bf16x2(__uint_as_float(o[q * 8]) * inv_l, __uint_as_float(o[q * 8 + 1]) * inv_l),
-                pack_bf16x2(__uint_as_float(o[q * 8 + 2]) * inv_l, __uint_as_float(o[q * 8 + 3]) * inv_l),
-                pack_bf16x2(__uint_as_float(o[q * 8 + 4]) * inv_l, __uint_as_float(o[q * 8 + 5]) * inv_l),
-                pack_bf16x2(__uint_as_float(o[q * 8 + 6]) * inv_l, __uint_as_float(o[q * 8 + 7]) * inv_l));
-            *reinterpret_cast<uint4*>(orow + col) = pk;
-          }
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
-}
+// (A column-split variant of the kernel above — sixteen softmax warps, the two warps of a TMEM lane quarter sharing a row's 128
+// columns as in attention_kernel — was measured at 346-376 us against 329-335 us on the B = 8, N = 4096, d = 40 launch: 43 % more
+// instructions per tile (row-max exchange, twice the per-tile bookkeeping) at 60 % issue utilisation and 54 % MUFU utilisation
+// (profiles/r02_ncu_attention_fa2.txt).  Its first version also hung: setmaxnreg.inc can only hand out registers of the CTA's
+// own launch allocation (20 warps x 96), never of the rest of the SM.  Removed.)
 
 struct AttnArgs {   // what the C ABI received; the tensor maps depend on the kernel variant's kv tile
   const void *Q, *K, *Vt;
@@ -1230,11 +859,11 @@ static int launch_attention(AttnParams& p, const AttnArgs& a, cudaStream_t strea
   return VDB_OK;
 }
 
-template <int DVP, int KV_STAGES, int POLY, int TOKEN, int PT, int PH>
+template <int DVP, int KV_STAGES, int POLY, int TOKEN>
 static int launch_attention_fa(AttnParams& p, const AttnArgs& a, cudaStream_t stream) {
-  constexpr size_t smem = attention_fa_smem_bytes<DVP, KV_STAGES, PT>();
+  constexpr size_t smem = attention_fa_smem_bytes<DVP, KV_STAGES>();
   static_assert(smem <= 227 * 1024, "attention (two-tile) smem budget");
-  auto kernel = attention_fa_kernel<DVP, KV_STAGES, POLY, TOKEN, PT, PH>;
+  auto kernel = attention_fa_kernel<DVP, KV_STAGES, POLY, TOKEN>;
   static bool configured = false;
   if (!configured) {
     VDB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -1253,67 +882,22 @@ static int launch_attention_fa(AttnParams& p, const AttnArgs& a, cudaStream_t st
   return VDB_OK;
 }
 
-template <int DVP, int PT, int TOKEN, int PH>
-static int dispatch_attention_fa3(int poly, AttnParams& p, const AttnArgs& a, cudaStream_t st) {
+template <int DVP, int TOKEN>
+static int dispatch_attention_fa2(int poly, AttnParams& p, const AttnArgs& a, cudaStream_t st) {
   switch (poly) {
-    case 0: return launch_attention_fa<DVP, 3, 0, TOKEN, PT, PH>(p, a, st);
-    case 1: return launch_attention_fa<DVP, 3, 1, TOKEN, PT, PH>(p, a, st);
-    case 3: return launch_attention_fa<DVP, 3, 3, TOKEN, PT, PH>(p, a, st);
-    default: return launch_attention_fa<DVP, 3, 2, TOKEN, PT, PH>(p, a, st);
+    case 0: return launch_attention_fa<DVP, 3, 0, TOKEN>(p, a, st);
+    case 2: return launch_attention_fa<DVP, 3, 2, TOKEN>(p, a, st);
+    case 3: return launch_attention_fa<DVP, 3, 3, TOKEN>(p, a, st);
+    default: return launch_attention_fa<DVP, 3, 1, TOKEN>(p, a, st);
   }
 }
 template <int DVP>
 static int dispatch_attention_fa(int mode, AttnParams& p, const AttnArgs& a, cudaStream_t st) {
-  // mode digits "[H][S]PT": P = exp2 pairs of every 8 on the FMA pipe (0..3); T = 1 MUFU token / 0 free-running; S = 1 keeps P in
-  // shared memory (SS product) instead of tensor memory (TS); H = 1 the round-2a tile body (exp2 interleaved with its pack / store
-  // work) instead of the phase-split one.  Kept variants: the default and the ones the profiles under profiles/ compare against.
-  const int poly = (mode / 10) % 10, token = mode % 10 ? 1 : 0, smem_p = (mode / 100) % 10, legacy = (mode / 1000) % 10;
-  if (legacy) return token ? dispatch_attention_fa3<DVP, 1, 1, 0>(poly, p, a, st) : dispatch_attention_fa3<DVP, 1, 0, 0>(poly, p, a, st);
-  if (smem_p) return dispatch_attention_fa3<DVP, 0, 1, 1>(poly, p, a, st);
-  return token ? dispatch_attention_fa3<DVP, 1, 1, 1>(poly, p, a, st) : dispatch_attention_fa3<DVP, 1, 0, 1>(poly, p, a, st);
-}
-
-
-template <int DVP, int KV_STAGES, int POLY, int TOKEN>
-static int launch_attention_fa2(AttnParams& p, const AttnArgs& a, cudaStream_t stream) {
-  constexpr size_t smem = attention_fa2_smem_bytes<DVP, KV_STAGES>();
-  static_assert(smem <= 227 * 1024, "attention (two-tile, column-split) smem budget");
-  auto kernel = attention_fa2_kernel<DVP, KV_STAGES, POLY, TOKEN>;
-  static bool configured = false;
-  if (!configured) {
-    VDB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    prefer_max_smem(kernel);
-    configured = true;
-  }
-  int rc = make_tmap_2d(&p.tmQ, a.Q, static_cast<uint64_t>(a.ldq), static_cast<uint64_t>(a.B) * a.q_bstride, a.ldq * 2, 64, kBQ);
-  if (rc) return rc;
-  rc = make_tmap_2d(&p.tmK, a.K, static_cast<uint64_t>(a.ldk), static_cast<uint64_t>(a.B) * a.kv_bstride, a.ldk * 2, 64, 128);
-  if (rc) return rc;
-  rc = make_tmap_2d(&p.tmV, a.Vt, static_cast<uint64_t>(a.B) * a.kv_bstride, static_cast<uint64_t>(a.H) * DVP, a.ldv * 2, 64, DVP);
-  if (rc) return rc;
-  dim3 grid((p.Nq + 2 * kBQ - 1) / (2 * kBQ), a.H, a.B);
-  VDB_CUDA_CHECK(launch_pdl(kernel, grid, dim3(640), smem, stream, p));
-  count_launch();
-  return VDB_OK;
-}
-template <int DVP>
-static int dispatch_attention_fa2(int mode, AttnParams& p, const AttnArgs& a, cudaStream_t st) {
+  // mode digits "PT": P = exp2 pairs of every 8 on the FMA pipe (0..3), T = 1 MUFU token between the two groups / 0 free-running
   const int poly = (mode / 10) % 10, token = mode % 10 ? 1 : 0;
-  if (token) {
-    switch (poly) {
-      case 0: return launch_attention_fa2<DVP, 4, 0, 1>(p, a, st);
-      case 1: return launch_attention_fa2<DVP, 4, 1, 1>(p, a, st);
-      case 3: return launch_attention_fa2<DVP, 4, 3, 1>(p, a, st);
-      default: return launch_attention_fa2<DVP, 4, 2, 1>(p, a, st);
-    }
-  }
-  switch (poly) {
-    case 0: return launch_attention_fa2<DVP, 4, 0, 0>(p, a, st);
-    case 1: return launch_attention_fa2<DVP, 4, 1, 0>(p, a, st);
-    case 3: return launch_attention_fa2<DVP, 4, 3, 0>(p, a, st);
-    default: return launch_attention_fa2<DVP, 4, 2, 0>(p, a, st);
-  }
+  return token ? dispatch_attention_fa2<DVP, 1>(poly, p, a, st) : dispatch_attention_fa2<DVP, 0>(poly, p, a, st);
 }
+
 }  // namespace vdb
 
 using namespace vdb;
@@ -1367,16 +951,12 @@ int vdb_attention_bf16(const void* Q, long long ldq, int q_col0, const void* K, 
   //                    of a 128-column tile are masked padding)
   //   VDB_ATT_BKV=128  the 128-column kernel everywhere
   // default: the three-CTA kernel for short contexts (65..512 keys), the 128-column kernel otherwise
-  // VDB_ATT_FA2: the column-split two-tile kernel (attention_fa2_kernel, default): digits "PT" as below; 0 = off (falls to VDB_ATT_FA)
-  static const int fa2 = [] { const char* e = getenv("VDB_ATT_FA2"); return e ? atoi(e) : -1; }();
-  if (fa2 != 0 && DK == 64 && !causal && Nk >= 512 && Nq >= 256 && (Nq % 256) == 0 && !getenv("VDB_ATT_FA")) {
-    const int mode = fa2 < 0 ? 21 : fa2;
-    if (DVP == 48) return dispatch_attention_fa2<48>(mode, p, a, st);
-    if (DVP == 64) return dispatch_attention_fa2<64>(mode, p, a, st);
-  }
+  // VDB_ATT_FA: the two-tile kernel (attention_fa_kernel).  0 = off; otherwise digits "PT": P = exp2 pairs of every 8 on the FMA
+  // pipe (0..3), T = 1 MUFU token / 0 free-running.  Default 11 (measured best: 329 us on the B = 8, N = 4096, d = 40 launch;
+  // 1 -> 358, 21 -> 334, 31 -> 334, 10 -> 340: profiles/r02_visit_f_summary.log).
   static const int fa = [] { const char* e = getenv("VDB_ATT_FA"); return e ? atoi(e) : -1; }();
   if (fa != 0 && DK == 64 && !causal && Nk >= 512 && Nq >= 256 && (Nq % 256) == 0) {
-    const int mode = fa < 0 ? 21 : fa;
+    const int mode = fa < 0 ? 11 : fa;
     if (DVP == 48) return dispatch_attention_fa<48>(mode, p, a, st);
     if (DVP == 64) return dispatch_attention_fa<64>(mode, p, a, st);
   }
