@@ -177,6 +177,11 @@ int vdb_scale_by_row_norm(const void* z, const int* idx, const float* row_scale,
 /* ---- row softmax (VAE AttnBlock, autokl_modules.py:186-188) ------------------------------------- */
 int vdb_softmax_rows(const void* x, long long rows, int n, long long ld, float scale, void* y, void* stream);
 
+/* ---- per-position affine + activation (text-latent flow): y[r,i] = act(x[r,i] * gamma[i] + beta[i]) on bf16
+ *      rows with fp32 parameters — the affine half of FCBlock's GroupNorm32 (openaimodel.py:2100-2112), whose gamma / beta are
+ *      indexed by the FLATTENED channel c*sdim + s while vdb_groupnorm_nhwc normalises per channel c.  act 0 none, 1 SiLU. ---- */
+int vdb_affine_act_rows(const void* x, long long rows, int n, const float* gamma, const float* beta, int act, void* y, void* stream);
+
 /* ---- load-time weight repack (SURVEY §8b `vdb_pack_conv_weight`): checkpoint tensors in the reference's layouts (fp32,
  *      contiguous: Conv2d [Cout,Cin,kh,kw], Linear [out,in]) -> the bf16 K-major layouts the kernels above consume, so a
  *      binder that keeps the reference's own nn.Modules needs none of this repo's Python.  All device pointers. ------------ */

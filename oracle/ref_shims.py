@@ -97,7 +97,7 @@ def load():
     return ns
 
 
-def build_vd(unet_overrides=None, vae_overrides=None, with_text_ctx=True, with_vae=True):
+def build_vd(unet_overrides=None, vae_overrides=None, with_text_ctx=True, with_vae=True, text_parts="c"):
     """The reference VD_v2_0 with diffuser.image (global+data+context), diffuser.text (context blocks
     only, configs/model/openai_unet.yaml:78-81) and vae.image — no CLIP, no Optimus, no 0D data blocks."""
     ns = load()
@@ -107,7 +107,7 @@ def build_vd(unet_overrides=None, vae_overrides=None, with_text_ctx=True, with_v
         if vae_overrides:
             ak.args.ddconfig.update(vae_overrides)
         u2 = bank("openai_unet_2d_v1")
-        u0 = bank("openai_unet_0d_v1_c")
+        u0 = bank("openai_unet_0d_v1_" + text_parts)     # "c": context blocks only (image sampling); "dc": + the text-latent data blocks
         if unet_overrides:
             u2.args.update(unet_overrides)
             u0.args.update({k: v for k, v in unet_overrides.items() if k in ("model_channels", "channel_mult", "num_heads", "context_dim")})

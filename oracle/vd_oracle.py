@@ -168,6 +168,97 @@ def unet_layout(model_channels=320, channel_mult=(1, 2, 4, 4), num_res_blocks=(2
     return ops
 
 
+def fcblock(sd, p, x, emb):
+    """FCBlock_MultiDim.forward -> FCBlock._forward, openaimodel.py:2134-2141, 2344-2354: the [B, C, s, 1] feature is flattened
+    to C*s*1 channels of a 1x1 "image" (index c*s + si), GroupNorm32 (eps 1e-5) -> SiLU -> 1x1 conv, + SiLU->Linear(emb),
+    GroupNorm32 -> SiLU -> 1x1 conv, + skip (identity or 1x1 conv); the result is viewed back as [B, Cout, s, 1]."""
+    b, _, sdim, _ = x.shape
+    xf = x.reshape(b, -1, 1, 1)
+    h = F.conv2d(F.silu(_gn(xf, sd, p + ".in_layers.0", 1e-5)), sd[p + ".in_layers.2.weight"], sd[p + ".in_layers.2.bias"])
+    e = F.linear(F.silu(emb), sd[p + ".emb_layers.1.weight"], sd[p + ".emb_layers.1.bias"])
+    h = h + e[:, :, None, None]
+    h = F.conv2d(F.silu(_gn(h, sd, p + ".out_layers.0", 1e-5)), sd[p + ".out_layers.3.weight"], sd[p + ".out_layers.3.bias"])
+    if (p + ".skip_connection.weight") in sd:
+        xf = F.conv2d(xf, sd[p + ".skip_connection.weight"], sd[p + ".skip_connection.bias"])
+    y = xf + h
+    return y.reshape(b, y.shape[1] // sdim, sdim, 1)
+
+
+def unet0d_layout(channel_mult=(1, 2, 4, 4), num_noattn_blocks=(2, 2, 2, 2), with_attn=(True, True, True, False)):
+    """The layer walk of UNetModel0D_Next.__init__, openaimodel.py:2885-2962: ('lin_in'|'fc'|'ctx'|'lin'|'out'|'save'|'load',
+    data_idx / ctx_idx) in execution order."""
+    ops, d, c = [], 0, 0
+    ops.append(("lin_in", d)); d += 1
+    ops.append(("save", None))
+    for level in range(len(channel_mult)):
+        for _ in range(num_noattn_blocks[level]):
+            ops.append(("fc", d)); d += 1
+            if with_attn[level]:
+                ops.append(("ctx", c)); c += 1
+            ops.append(("save", None))
+        if level != len(channel_mult) - 1:
+            ops.append(("lin", d)); d += 1
+            ops.append(("save", None))
+    ops.append(("fc", d)); d += 1
+    ops.append(("ctx", c)); c += 1
+    ops.append(("fc", d)); d += 1
+    for level in list(range(len(channel_mult)))[::-1]:
+        for _ in range(num_noattn_blocks[level] + 1):
+            ops.append(("load", None))
+            ops.append(("fc", d)); d += 1
+            if with_attn[level]:
+                ops.append(("ctx", c)); c += 1
+        if level != 0:
+            ops.append(("lin", d)); d += 1
+    ops.append(("out", d)); d += 1
+    return ops
+
+
+def apply_model_text(sd, x, timesteps, contexts, ratios=None, c_types=("text",), layout=None, model_channels=320,
+                     second_dim=4, num_heads=8, time_from="image"):
+    """VD_v2_0.apply_model / apply_model_multicontext (vd.py:330-455) for x_type = 'text': the 0-D diffuser's data blocks
+    (Linear_MultiDim / FCBlock_MultiDim, openaimodel.py:2275-2354, 2885-2962) on a [B, 768] text latent, context blocks of
+    diffuser[c_type] on the [B, C, second_dim, 1] feature (four "pixels").  time_embed comes from diffuser[global_layer_ptr]
+    (= 'image' in vd_four_flow) for apply_model and from diffuser['text'] for the multicontext variant (vd.py:339, 415)."""
+    layout = layout or unet0d_layout()
+    D = "diffuser.text"
+    T = f"diffuser.{time_from}"
+    t_emb = timestep_embedding(timesteps, model_channels)
+    emb = F.linear(F.silu(F.linear(t_emb, sd[T + ".time_embed.0.weight"], sd[T + ".time_embed.0.bias"])),
+                   sd[T + ".time_embed.2.weight"], sd[T + ".time_embed.2.bias"])
+    if ratios is None:
+        ratios = [1.0] * len(contexts)
+    r = np.array(ratios, dtype=np.float64)
+    r = r / r.sum()
+    b = x.shape[0]
+    hs, h = [], x
+    for kind, idx in layout:
+        p = f"{D}.data_blocks.{idx}.0"
+        if kind == "lin_in":       # Linear_MultiDim([768] -> [C, s, 1])
+            h = F.linear(h, sd[p + ".weight"], sd[p + ".bias"]).view(b, -1, second_dim, 1)
+        elif kind == "lin":        # Linear_MultiDim([C, s, 1] -> [C, s, 1])
+            h = F.linear(h.reshape(b, -1), sd[p + ".weight"], sd[p + ".bias"]).view(b, -1, second_dim, 1)
+        elif kind == "fc":
+            h = fcblock(sd, p, h, emb)
+        elif kind == "out":        # GroupNorm32(C) -> SiLU -> Linear_MultiDim([C, s, 1] -> [768])
+            h = F.silu(_gn(h, sd, p + ".0", 1e-5))
+            h = F.linear(h.reshape(b, -1), sd[p + ".2.weight"], sd[p + ".2.bias"])
+        elif kind == "ctx":
+            if len(contexts) == 1:
+                h = spatial_transformer(sd, f"diffuser.{c_types[0]}.context_blocks.{idx}.0", h, contexts[0], num_heads)
+            else:
+                acc = None
+                for ct, c, ri in zip(c_types, contexts, r):
+                    hi = spatial_transformer(sd, f"diffuser.{ct}.context_blocks.{idx}.0", h, c, num_heads) * ri
+                    acc = hi if acc is None else acc + hi
+                h = acc
+        elif kind == "save":
+            hs.append(h)
+        elif kind == "load":
+            h = torch.cat([h, hs.pop()], dim=1)
+    return h
+
+
 def apply_model(sd, x, timesteps, contexts, ratios=None, x_type="image", c_types=("text",), layout=None,
                 model_channels=320, num_heads=8):
     """VD_v2_0.apply_model (vd.py:330-381) when len(contexts)==1 and apply_model_multicontext +

@@ -157,3 +157,23 @@ print('LIVE-OK')
 """ % ROOT
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert "LIVE-OK" in out.stdout, out.stderr[-2000:]
+
+
+def test_oracle_text_latent_diffuser_vs_reference_golden():
+    """the 0-D diffuser restatement (Linear_MultiDim / FCBlock_MultiDim walk) against goldens produced by the
+    unmodified reference's apply_model on a [B, 768] text latent (tests/golden/mini_text.npz)."""
+    import json
+    import numpy as np
+    from oracle import vd_oracle as O, weights
+    from oracle.make_golden import golden_inputs, WEIGHT_SEED
+    gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    shapes = {k: tuple(v) for k, v in json.load(open(os.path.join(gold_dir, "keys_mini_text.json"))).items()}
+    sd = weights.synth_state_dict(shapes, seed=WEIGHT_SEED)
+    gold = dict(np.load(os.path.join(gold_dir, "mini_text.npz")))
+    gt = golden_inputs("text")
+    with torch.no_grad():
+        t2t = O.apply_model_text(sd, gt["x"], gt["t"], [gt["c_text"]], c_types=("text",), model_channels=64)
+        i2t = O.apply_model_text(sd, gt["x"], gt["t"], [gt["c_img"]], c_types=("image",), model_channels=64)
+    for out, key in ((t2t, "eps_t2t"), (i2t, "eps_i2t")):
+        ref = torch.as_tensor(gold[key])
+        assert (out - ref).abs().max().item() <= 2e-4 * ref.abs().max().item(), key

@@ -32,12 +32,14 @@ def _cmp(out, ref, cos_min=0.999, tol=3e-2, what=""):
     assert cos >= cos_min and err <= tol * scale, f"{what}: cos {cos:.6f}, max err {err:.4g} vs scale {scale:.4g}"
 
 
-def build_net(mini=True, with_vae=True):
+def build_net(mini=True, with_vae=True, text_flows=False):
     from lib.cfg_helper import model_cfg_bank
     from lib.model_zoo import get_model
     from oracle import weights
     from oracle.make_golden import MINI_UNET, MINI_VAE, WEIGHT_SEED
     cfg = model_cfg_bank()('vd_four_flow_v1-0')
+    if text_flows:      # the reference's own text diffuser config: data + context blocks (VDB_TEXT_FLOWS=1 selects it in cfg_helper)
+        cfg.args.diffuser_cfg_list[1][1] = model_cfg_bank()('openai_unet_0d_v1_dc')
     cfg.args.ctx_cfg_list = []
     if not with_vae:
         cfg.args.vae_cfg_list = []
@@ -414,3 +416,34 @@ def test_images_to_uint8_matches_topilimage(mini):
     out = net.images_to_uint8(x.to(DEV)).cpu().numpy()
     ref = np.stack([np.asarray(tvtrans.ToPILImage()(xi)) for xi in x])
     assert np.array_equal(out, ref)
+
+
+# ---- text-latent flows: the 0-D diffuser's data blocks (Linear_MultiDim / FCBlock_MultiDim) on a [B, 768] latent
+def test_text_latent_apply_model_vs_reference_golden():
+    """i2t / t2t diffusion: VD_v2_0.apply_model with x_type = 'text' (reference vd.py:330-381 over openaimodel.py:2275-2354,
+    2814-2975) against goldens produced by the unmodified reference (tests/golden/mini_text.npz), and the checkpoint ABI of the
+    0-D diffuser's data blocks (keys_mini_text.json)."""
+    from oracle import weights
+    from oracle.make_golden import golden_inputs
+    net, sd = build_net(mini=True, with_vae=False, text_flows=True)
+    ref_keys = {k: tuple(v) for k, v in json.load(open(os.path.join(GOLD, "keys_mini_text.json"))).items()}
+    ours = weights.param_shapes(net)
+    assert set(ours) == set(ref_keys) and all(ours[k] == ref_keys[k] for k in ref_keys)
+    gold = dict(np.load(os.path.join(GOLD, "mini_text.npz")))
+    gt = golden_inputs("text")
+    with torch.no_grad():
+        t2t = net.apply_model({"type": "text", "x": gt["x"].to(DEV)}, gt["t"].to(DEV), {"type": "text", "c": gt["c_text"].to(DEV)})
+        i2t = net.apply_model({"type": "text", "x": gt["x"].to(DEV)}, gt["t"].to(DEV), {"type": "image", "c": gt["c_img"].to(DEV)})
+    assert t2t.shape == (3, 768)
+    _cmp(t2t, gold["eps_t2t"], what="text-latent apply_model, text context (reference golden)")
+    _cmp(i2t, gold["eps_i2t"], what="text-latent apply_model, image context (reference golden)")
+    # dual context on the text latent (apply_model_multicontext) against the oracle
+    from oracle import vd_oracle as O
+    with torch.no_grad():
+        ref = O.apply_model_text(sd, gt["x"], gt["t"], [gt["c_text"], gt["c_img"]], ratios=[0.4, 0.6], c_types=("text", "image"),
+                                 model_channels=64, time_from="text") if ("diffuser.text.time_embed.0.weight" in sd) else None
+    if ref is not None:
+        out = net.apply_model_multicontext({"type": "text", "x": gt["x"].to(DEV)}, gt["t"].to(DEV),
+                                           [{"type": "text", "c": gt["c_text"].to(DEV), "ratio": 0.4},
+                                            {"type": "image", "c": gt["c_img"].to(DEV), "ratio": 0.6}])
+        _cmp(out, ref, what="text-latent apply_model_multicontext vs oracle")

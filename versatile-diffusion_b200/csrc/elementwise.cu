@@ -1297,6 +1297,32 @@ __global__ void __launch_bounds__(256) scale_by_row_norm_kernel(const __nv_bfloa
   }
 }
 
+// y[r, i] = act(x[r, i] * gamma[i] + beta[i]) on bf16 rows (fp32 parameters): the position-dependent GroupNorm affine of the
+// 0-D diffuser's FCBlock (gamma / beta per flattened channel c*sdim + s, openaimodel.py:2100-2112) after the statistics pass
+__global__ void affine_act_rows_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int n, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, int act, __nv_bfloat16* __restrict__ y) {
+  const long long total = rows * (n / 8);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(i % (n / 8)) * 8;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x) + i);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16x2(w[k]);
+      float a = f.x * gg[2 * k] + bb[2 * k], c = f.y * gg[2 * k + 1] + bb[2 * k + 1];
+      if (act == 1) { a = silu_bf16_f(a); c = silu_bf16_f(c); }
+      o[k] = pack_bf16x2(a, c);
+    }
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ---- load-time weight repack (fp32 checkpoint layouts -> bf16 kernel layouts) ----
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int kh, int kw,
                                         __nv_bfloat16* __restrict__ out, long long ldo, long long col0) {
@@ -1565,6 +1591,15 @@ int vdb_layernorm(const void* x, long long rows, int C, const float* gamma, cons
     VDB_CUDA_CHECK(launch_pdl(layernorm_kernel<5, 2>, dim3(blocks), dim3(threads), 0, st, xp, rows, C, gamma, beta, eps, yp));
   else
     VDB_CUDA_CHECK(launch_pdl(layernorm_kernel<8, 1>, dim3(blocks), dim3(threads), 0, st, xp, rows, C, gamma, beta, eps, yp));
+  count_launch();
+  return VDB_OK;
+}
+
+int vdb_affine_act_rows(const void* x, long long rows, int n, const float* gamma, const float* beta, int act, void* y, void* stream) {
+  if (!x || !gamma || !beta || !y || rows <= 0 || n <= 0 || (n % 8)) return set_error(VDB_ERR_INVALID, "affine_act_rows: bad argument (n %% 8 == 0)");
+  affine_act_rows_kernel<<<ew_blocks(rows * (n / 8), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), rows, n, gamma, beta, act, reinterpret_cast<__nv_bfloat16*>(y));
+  VDB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return VDB_OK;
 }

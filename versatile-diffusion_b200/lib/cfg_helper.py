@@ -6,6 +6,7 @@ Text-latent flows (Optimus VAE, 0D data blocks) are outside the hot path: 'vd_fo
 carries the image VAE, both CLIP context encoders, the 2D diffuser and the 0D diffuser's context blocks.
 """
 import copy
+import os
 
 
 class CfgDict(dict):
@@ -88,8 +89,10 @@ class model_cfg_bank(object):
             cfg.args.update(dict(
                 vae_cfg_list=[["image", self("autokl_v1")]],
                 ctx_cfg_list=[["image", self("clip_image_context_encoder")], ["text", self("clip_text_context_encoder")]],
-                # the 0D (text-latent) diffuser contributes only its context blocks to image sampling
-                diffuser_cfg_list=[["image", self("openai_unet_2d_v1")], ["text", self("openai_unet_0d_v1_c")]],
+                # the 0D (text-latent) diffuser contributes only its context blocks to image sampling; VDB_TEXT_FLOWS=1 builds its
+                # data blocks too (the reference's 'openai_unet_0d_v1_dc': +1.7 G parameters) for the i2t / t2t diffusion
+                diffuser_cfg_list=[["image", self("openai_unet_2d_v1")],
+                                   ["text", self("openai_unet_0d_v1_dc" if os.environ.get("VDB_TEXT_FLOWS") == "1" else "openai_unet_0d_v1_c")]],
                 global_layer_ptr="image", latent_scale_factor={"image": 0.18215}))
             return cfg
         if name not in _BANK:

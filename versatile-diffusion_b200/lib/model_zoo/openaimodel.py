@@ -16,6 +16,7 @@ Kernel schedule of a ResBlock (reference _forward, :254-274):
 import copy
 from functools import partial
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -464,11 +465,166 @@ def unet_walk(data_unet, ctx_unets, h, emb, contexts, ratios):
     return h
 
 
+def _md_perm(C, sdim, device):
+    """Index map between the reference's flattening of a [C, sdim, 1] multi-dim feature (index c*sdim + s, openaimodel.py:2287-2293)
+    and this build's NHWC order (index s*C + c): ours[i] = ref[perm[i]]."""
+    idx = torch.arange(C * sdim, device=device)
+    s, c = idx // C, idx % C
+    return c * sdim + s
+
+
+class Linear_MultiDim(PackedMixin, nn.Linear):
+    """nn.Linear over a flattened multi-dim feature (reference openaimodel.py:2275-2293); same parameter names / shapes.
+    Here the [B, C, sdim, 1] features of the 0-D diffuser live as NHWC bf16 [B, sdim, 1, C]; the rows / columns of the weight
+    are permuted once at pack time so that the GEMM reads and writes that order directly."""
+
+    def __init__(self, in_features, out_features, *args, **kwargs):
+        in_features = [in_features] if isinstance(in_features, int) else list(in_features)
+        out_features = [out_features] if isinstance(out_features, int) else list(out_features)
+        self.in_features_multidim = in_features
+        self.out_features_multidim = out_features
+        nn.Linear.__init__(self, int(np.prod(in_features)), int(np.prod(out_features)), *args, **kwargs)
+
+    def _pack(self):
+        w, b = self.weight.detach(), self.bias.detach()
+        if len(self.out_features_multidim) == 3:
+            po = _md_perm(self.out_features_multidim[0], self.out_features_multidim[1], w.device)
+            w, b = w[po], b[po]
+        if len(self.in_features_multidim) == 3:
+            pi = _md_perm(self.in_features_multidim[0], self.in_features_multidim[1], w.device)
+            w = w[:, pi]
+        return {"w": bf16(w), "b": f32(b)}
+
+    def forward(self, x):
+        """x: [B, K] (flat input, bf16 or fp32) or NHWC bf16 [B, sdim, 1, C]; returns NHWC bf16 [B, sdim, 1, C] for a
+        multi-dim output, fp32 [B, N] for a flat one (the output head)."""
+        ops = _ops()
+        p = self.packed()
+        B = x.shape[0]
+        a = x.reshape(B, -1)
+        a = a if a.dtype == torch.bfloat16 else ops.to_bf16(a.float().contiguous())
+        if len(self.out_features_multidim) == 3:
+            C, sdim = self.out_features_multidim[0], self.out_features_multidim[1]
+            return ops.gemm(a, p["w"], bias=p["b"]).view(B, sdim, 1, C)
+        return ops.gemm(a, p["w"], bias=p["b"], out_dtype=torch.float32)
+
+
+class FCBlock_MultiDim(PackedModule, TimestepBlock):
+    """The 0-D diffuser's residual block (reference FCBlock / FCBlock_MultiDim, openaimodel.py:2084-2141, 2295-2354): the
+    [C, sdim, 1] feature flattened to C*sdim channels of a 1x1 image, GroupNorm32 -> SiLU -> 1x1 conv (+ SiLU->Linear(emb)),
+    GroupNorm32 -> SiLU -> 1x1 conv, + skip (identity / 1x1 conv).  Parameter names / shapes as in the reference.
+    Kernels: GroupNorm over the NHWC [B, sdim, 1, C] view (the reference's 32 groups of the flattened index c*sdim + s are
+    exactly 32 channel groups over all sdim positions), the three 1x1 convs as GEMMs over the flattened feature with rows /
+    columns permuted to NHWC order; the skip conv runs as extra K columns of the second GEMM.  M = batch rows: these GEMMs
+    stream weights (0.2 GB per block at full size) — HBM-bound by construction."""
+
+    def __init__(self, channels, emb_channels, dropout, out_channels=None, use_checkpoint=False):
+        super().__init__()
+        channels = [channels] if isinstance(channels, int) else list(channels)
+        self.channels_multidim = channels
+        self.out_channels_multidim = channels if out_channels is None else \
+            ([out_channels] if isinstance(out_channels, int) else list(out_channels))
+        self.channels = int(np.prod(self.channels_multidim))
+        self.out_channels = int(np.prod(self.out_channels_multidim))
+        self.emb_channels = emb_channels
+        self.dropout = dropout
+        self.use_checkpoint = use_checkpoint
+        self.in_layers = nn.Sequential(normalization(self.channels), nn.SiLU(), nn.Conv2d(self.channels, self.out_channels, 1, padding=0))
+        self.emb_layers = nn.Sequential(nn.SiLU(), linear(emb_channels, self.out_channels))
+        self.out_layers = nn.Sequential(normalization(self.out_channels), nn.SiLU(), nn.Dropout(p=dropout),
+                                        zero_module(nn.Conv2d(self.out_channels, self.out_channels, 1, padding=0)))
+        if self.out_channels == self.channels:
+            self.skip_connection = nn.Identity()
+        else:
+            self.skip_connection = nn.Conv2d(self.channels, self.out_channels, 1, padding=0)
+
+    def _pack(self):
+        dev = self.in_layers[2].weight.device
+        Cin, sdim = self.channels_multidim[0], self.channels_multidim[1]
+        Cout = self.out_channels_multidim[0]
+        pi, po = _md_perm(Cin, sdim, dev), _md_perm(Cout, sdim, dev)
+        w1 = self.in_layers[2].weight.detach().reshape(self.out_channels, self.channels)[po][:, pi]
+        w2 = self.out_layers[3].weight.detach().reshape(self.out_channels, self.out_channels)[po][:, po]
+        b2 = self.out_layers[3].bias.detach()[po].float()
+        has_skip = not isinstance(self.skip_connection, nn.Identity)
+        if has_skip:
+            ws = self.skip_connection.weight.detach().reshape(self.out_channels, self.channels)[po][:, pi]
+            w2 = torch.cat([w2, ws], dim=1)
+            b2 = b2 + self.skip_connection.bias.detach()[po].float()
+        # GroupNorm parameters are per flattened channel (c*sdim + s): gathered into NHWC order -> [sdim, C] tables; the kernel
+        # takes per-channel gamma / beta, so position-dependent parameters are applied as sdim separate channel vectors only when
+        # they differ across s (synthetic weights do; a trained checkpoint does too)
+        g1 = self.in_layers[0].weight.detach()[pi].float().view(sdim, Cin)
+        be1 = self.in_layers[0].bias.detach()[pi].float().view(sdim, Cin)
+        g2 = self.out_layers[0].weight.detach()[po].float().view(sdim, Cout)
+        be2 = self.out_layers[0].bias.detach()[po].float().view(sdim, Cout)
+        return {"w1": bf16(w1), "b1": self.in_layers[2].bias.detach()[po].float().contiguous(),
+                "we": bf16(self.emb_layers[1].weight.detach()[po]), "be": self.emb_layers[1].bias.detach()[po].float().contiguous(),
+                "w2": bf16(w2), "b2": b2.contiguous(), "has_skip": has_skip, "sdim": sdim,
+                "g1": g1.contiguous(), "be1": be1.contiguous(), "g2": g2.contiguous(), "be2": be2.contiguous()}
+
+    @staticmethod
+    def _gn_silu(x, gamma, beta, eps, x2=None):
+        """GroupNorm32 + SiLU over the flattened channels of [B, sdim, 1, C] (+ concat): statistics per (image, channel group) over
+        all sdim positions == the reference's groups of the flattened index; gamma / beta differ per position, so the affine
+        part is applied with identity parameters by the kernel's statistics pass and finished per position."""
+        ops = _ops()
+        B, sdim, _, C1 = x.shape
+        C = C1 + (x2.shape[-1] if x2 is not None else 0)
+        ones = torch.ones(C, dtype=torch.float32, device=x.device)
+        zeros = torch.zeros(C, dtype=torch.float32, device=x.device)
+        xn = ops.groupnorm(x, ones, zeros, eps, act=ops.ACT_NONE, x2=x2)            # (x - mean) * rstd, bf16 [B, sdim, 1, C]
+        return ops.affine_silu_rows(xn.view(B, sdim * C), gamma.view(-1), beta.view(-1))
+
+    def forward(self, x, emb):
+        """x: NHWC bf16 [B, sdim, 1, C] or a pair (h, skip) == cat along C.  emb: fp32 [B, emb_channels] (SiLU applied here)."""
+        ops = _ops()
+        p = self.packed()
+        x1, x2 = x if isinstance(x, tuple) else (x, None)
+        require_cuda(x1, "FCBlock_MultiDim")
+        B, sdim = x1.shape[0], x1.shape[1]
+        eps = self.in_layers[0].eps
+        a1 = self._gn_silu(x1, p["g1"], p["be1"], eps, x2=x2)                      # [B, sdim*Cin] bf16
+        e = ops.linear_small(emb.float().contiguous(), p["we"], (p["be"] + p["b1"]).contiguous(), act_in=ops.ACT_SILU)
+        h = ops.gemm(a1, p["w1"], bias=e, bias_bstride=self.out_channels, rows_per_batch=1)
+        Cout = self.out_channels_multidim[0]
+        a2 = self._gn_silu(h.view(B, sdim, 1, Cout), p["g2"], p["be2"], self.out_layers[0].eps)
+        raw = x1 if x2 is None else torch.cat([x1, x2], dim=-1)                     # (data movement only: 4 positions per row)
+        raw = raw.reshape(B, -1)
+        if p["has_skip"]:
+            out = ops.gemm(a2, p["w2"], bias=p["b2"], a2=raw)
+        else:
+            out = ops.gemm(a2, p["w2"], bias=p["b2"], resid=raw)
+        return out.view(B, sdim, 1, Cout)
+
+
+class OutHead0D(PackedModule):
+    """GroupNorm32(C) -> SiLU -> Linear_MultiDim([C, sdim, 1] -> [output_channels]) (reference openaimodel.py:2957-2962),
+    registered under the reference's Sequential indices 0 (norm) and 2 (linear)."""
+
+    def __init__(self, current_channel, output_channels):
+        super().__init__()
+        self.add_module("0", normalization(current_channel[0]))
+        self.add_module("1", nn.SiLU())
+        self.add_module("2", zero_module(Linear_MultiDim(current_channel, [output_channels], bias=True)))
+
+    def _pack(self):
+        norm = getattr(self, "0")
+        return {"g": f32(norm.weight), "b": f32(norm.bias)}
+
+    def forward(self, x):
+        ops = _ops()
+        p = self.packed()
+        a = ops.groupnorm(x, p["g"], p["b"], getattr(self, "0").eps, act=ops.ACT_SILU)
+        return getattr(self, "2")(a)
+
+
 @register('openai_unet_0d_next')
 class UNetModel0D_Next(UNetModel2D_Next):
-    """Only the context blocks of the 0-D (text-latent) diffuser are on the image-sampling path: they supply
-    the text-context SpatialTransformers (vd.py:345; configs/model/openai_unet.yaml:78-81).  Constructing it
-    with 'data' or 'global' parts raises: the text-latent flows are out of scope (SURVEY.md §2.1 #3)."""
+    """The 0-D (text-latent) diffuser (reference openaimodel.py:2814-2975).  Image sampling only needs its context blocks (the
+    text-context SpatialTransformers, vd.py:345; configs/model/openai_unet.yaml:78-81) — that is what 'vd_four_flow_v1-0' builds
+    by default here.  With 'data' in parts (round 2) the data blocks of the text-latent flows are built too:
+    Linear_MultiDim / FCBlock_MultiDim on a [B, 768] latent expanded to [C, second_dim, 1] features (NHWC bf16 [B, sdim, 1, C] here)."""
 
     def __init__(self, input_channels, model_channels, output_channels, context_dim=788,
                  num_noattn_blocks=(2, 2, 2, 2), channel_mult=(1, 2, 4, 8), second_dim=(4, 4, 4, 4),
@@ -476,9 +632,6 @@ class UNetModel0D_Next(UNetModel2D_Next):
                  parts=['global', 'data', 'context']):
         nn.Module.__init__(self)
         self.parts = parts if isinstance(parts, list) else [parts]
-        if self.parts != ['context']:
-            raise NotImplementedError("UNetModel0D_Next: only parts=['context'] is built for the B200 hot path "
-                                      "(text-latent data blocks belong to the i2t/t2t flows)")
         self.input_channels = input_channels
         self.model_channels = model_channels
         self.output_channels = output_channels
@@ -488,50 +641,83 @@ class UNetModel0D_Next(UNetModel2D_Next):
         self.with_attn = with_attn
         self.num_heads = num_heads
         self.num_head_channels = num_head_channels
-        self.glayer_included, self.dlayer_included, self.clayer_included = False, False, True
+        self.glayer_included = 'global' in self.parts
+        self.dlayer_included = 'data' in self.parts
+        self.clayer_included = 'context' in self.parts
+        if len(set(second_dim)) != 1:
+            raise NotImplementedError("UNetModel0D_Next: one second_dim for all levels (as in every VD config)")
         self.layer_sequence_ordering = []
-        self.context_blocks = nn.ModuleList([])
-        CrossAttnDefault = partial(SpatialTransformer, context_dim=context_dim, disable_self_attn=False)
+        time_embed_dim = model_channels * 4
+        if self.glayer_included:
+            self.time_embed = nn.Sequential(linear(model_channels, time_embed_dim), nn.SiLU(), linear(time_embed_dim, time_embed_dim))
+        if self.dlayer_included:
+            self.data_blocks = nn.ModuleList([])
+            FCBlockDefault = partial(FCBlock_MultiDim, dropout=0, use_checkpoint=use_checkpoint)
+            Lin = lambda i, o: Linear_MultiDim(i, o, bias=True)
+        else:
+            FCBlockDefault = lambda *a, **k: None
+            Lin = lambda i, o: None
+        if self.clayer_included:
+            self.context_blocks = nn.ModuleList([])
+        CrossAttnDefault = partial(SpatialTransformer, context_dim=context_dim, disable_self_attn=False) if self.clayer_included \
+            else (lambda *a, **k: None)
 
         def ctx(ch):
             d_head, n_heads = self.get_d_head_n_heads(ch)
             self.add_context_layer(CrossAttnDefault(in_channels=ch, d_head=d_head, n_heads=n_heads))
 
-        self.add_data_layer(None)
+        sdim = second_dim[0]
+        cur = [model_channels, sdim, 1]
+        self.add_data_layer(Lin([input_channels], cur))
         self.layer_sequence_ordering.append('save_hidden_feature')
-        ch = model_channels
-        for level_idx, mult in enumerate(channel_mult):
+        input_block_channels = [cur]
+        for level_idx, (mult, sdim) in enumerate(zip(channel_mult, second_dim)):
             for _ in range(num_noattn_blocks[level_idx]):
-                self.add_data_layer(None)
-                ch = mult * model_channels
+                self.add_data_layer(FCBlockDefault(cur, time_embed_dim, out_channels=[mult * model_channels, sdim, 1]))
+                cur = [mult * model_channels, sdim, 1]
                 if with_attn[level_idx]:
-                    ctx(ch)
+                    ctx(cur[0])
+                input_block_channels.append(cur)
                 self.layer_sequence_ordering.append('save_hidden_feature')
             if level_idx != len(channel_mult) - 1:
-                self.add_data_layer(None)
+                self.add_data_layer(Lin(cur, cur))
+                input_block_channels.append(cur)
                 self.layer_sequence_ordering.append('save_hidden_feature')
         self.i_order = copy.deepcopy(self.layer_sequence_ordering)
         self.layer_sequence_ordering = []
-        self.add_data_layer(None)
-        ctx(ch)
-        self.add_data_layer(None)
+        self.add_data_layer(FCBlockDefault(cur, time_embed_dim))
+        ctx(cur[0])
+        self.add_data_layer(FCBlockDefault(cur, time_embed_dim))
         self.m_order = copy.deepcopy(self.layer_sequence_ordering)
         self.layer_sequence_ordering = []
-        for level_idx, mult in list(enumerate(channel_mult))[::-1]:
+        for level_idx, (mult, sdim) in list(enumerate(zip(channel_mult, second_dim)))[::-1]:
             for _ in range(num_noattn_blocks[level_idx] + 1):
                 self.layer_sequence_ordering.append('load_hidden_feature')
-                self.add_data_layer(None)
-                ch = mult * model_channels
+                extra = input_block_channels.pop()
+                self.add_data_layer(FCBlockDefault([cur[0] + extra[0]] + cur[1:], time_embed_dim,
+                                                   out_channels=[mult * model_channels, sdim, 1]))
+                cur = [mult * model_channels, sdim, 1]
                 if with_attn[level_idx]:
-                    ctx(ch)
+                    ctx(cur[0])
             if level_idx != 0:
-                self.add_data_layer(None)
-        self.add_data_layer(None)
+                self.add_data_layer(Lin(cur, cur))
+        self.add_data_layer(OutHead0D(cur, output_channels) if self.dlayer_included else None)
         self.o_order = copy.deepcopy(self.layer_sequence_ordering)
         self.layer_order = copy.deepcopy(self.i_order + self.m_order + self.o_order)
         del self.layer_sequence_ordering
-        self.parameter_group = {'context': self.context_blocks}
+        self.parameter_group = {}
+        if self.glayer_included:
+            self.parameter_group['global'] = self.time_embed
+        if self.dlayer_included:
+            self.parameter_group['data'] = self.data_blocks
+        if self.clayer_included:
+            self.parameter_group['context'] = self.context_blocks
         self._emb_packed = None
 
+    def embed_table(self, t_emb, time_owner=None):
+        """Sinusoid [B, model_channels] fp32 -> the raw time embedding fp32 [B, 4*model_channels]; every FCBlock applies its own
+        SiLU -> Linear (the per-block projections are 1280 x (C*sdim): streamed once per call either way)."""
+        return (time_owner or self).time_embedding(t_emb)
+
     def forward(self, *a, **k):
-        raise NotImplementedError("context-only diffuser: used through VD_v2_0.apply_model")
+        raise NotImplementedError("the 0-D diffuser is driven by VD_v2_0.apply_model (data blocks of diffuser[x_type], context blocks of diffuser[c_type])")

@@ -180,8 +180,15 @@ class VD_v2_0(nn.Module):
     def _apply_model(self, x_type, x, timesteps, c_types, contexts, ratios, time_from):
         require_cuda(x, "VD_v2_0.apply_model")
         ops = _ops()
-        xh = ops.nchw_to_nhwc(x.float().contiguous())
         t_emb = timestep_embedding(timesteps, self.diffuser[time_from].model_channels, repeat_only=False)
+        if x.dim() == 2:
+            # text latent [B, 768] (i2t / t2t flows): the 0-D diffuser's data blocks take the flat latent
+            if not getattr(self.diffuser[x_type], "dlayer_included", False):
+                raise RuntimeError(f"diffuser['{x_type}'] was built without its data blocks: construct the model with the "
+                                   "'openai_unet_0d_v1_dc' text diffuser (VDB_TEXT_FLOWS=1) for the text-latent flows")
+            eps = self.eps_nhwc(x.float().contiguous(), x_type, t_emb, c_types, contexts, ratios, time_from)
+            return eps.to(x.dtype)
+        xh = ops.nchw_to_nhwc(x.float().contiguous())
         eps = self.eps_nhwc(xh, x_type, t_emb, c_types, contexts, ratios, time_from)
         return ops.nhwc_to_nchw(eps).to(x.dtype)
 

@@ -56,6 +56,7 @@ SIGNATURES = {
     "vdb_patchify": (i, [p, i, i, i, i, i, p, p]),
     "vdb_vit_assemble": (i, [p, p, p, p, i, i, i, i, p, p]),
     "vdb_scale_by_row_norm": (i, [p, p, p, i, i, i, i, p, p]),
+    "vdb_affine_act_rows": (i, [p, ll, i, p, p, i, p, p]),
     "vdb_pack_conv_weight": (i, [p, i, i, i, i, p, ll, ll, p]),
     "vdb_pack_geglu": (i, [p, p, i, i, p, p, p]),
     "vdb_pad_heads": (i, [p, i, i, i, i, p, p]),

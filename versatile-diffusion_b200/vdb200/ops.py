@@ -314,6 +314,16 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
     return out
 
 
+def affine_silu_rows(x, gamma, beta, act=ACT_SILU, out=None):
+    """y[r, i] = act(x[r, i] * gamma[i] + beta[i]); x bf16 [rows, n], gamma / beta fp32 [n] (FCBlock's per-position GroupNorm affine)."""
+    _need(x, BF16, "x"); _need(gamma, torch.float32, "gamma"); _need(beta, torch.float32, "beta")
+    rows, n = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.vdb_affine_act_rows(_ptr(x), rows, n, _ptr(gamma), _ptr(beta), int(act), _ptr(out), _stream()), "affine_act_rows")
+    return out
+
+
 def pack_conv_weight(w, out=None, col0=0):
     """Conv2d weight fp32 [Cout, Cin, kh, kw] -> bf16 [Cout, ldo] with column col0 + (ky*kw + kx)*Cin + ci (C ABI repack)."""
     _need(w, torch.float32, "w")
