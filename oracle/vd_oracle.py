@@ -325,6 +325,26 @@ def p_sample_ddim(sd, x, conds, unconds, t, index, sched, scale, c_types=("text"
     return x_prev, pred_x0, e_t
 
 
+def ddim_sample_text(sd, x_T, conds, unconds, steps, scale=7.5, c_types=("text",), num_ddpm=1000, **kw):
+    """DDIMSampler.sample (ddim.py:58-171) on a [n, 768] text latent: the same loop as ddim_sample with apply_model_text inside
+    (app.py:384-434: inference_i2t / inference_t2t before the Optimus decode).  eta = 0."""
+    sched = ddim_schedule(ddpm_schedule(num_ddpm)["alphas_cumprod"], steps)
+    x = x_T
+    b = x.shape[0]
+    for i in range(steps):
+        index = steps - i - 1
+        t = torch.full((b,), int(sched["timesteps"][index]), dtype=torch.long)
+        x_in, t_in = torch.cat([x] * 2), torch.cat([t] * 2)
+        c_in = [torch.cat([u, c]) for u, c in zip(unconds, conds)]
+        e_u, e_c = apply_model_text(sd, x_in, t_in, c_in, c_types=c_types, **kw).chunk(2)
+        e_t = e_u + scale * (e_c - e_u)
+        a_t, a_prev = float(sched["alphas"][index]), float(sched["alphas_prev"][index])
+        s1m = float(sched["sqrt_one_minus_alphas"][index])
+        pred_x0 = (x - s1m * e_t) / a_t ** 0.5
+        x = a_prev ** 0.5 * pred_x0 + (1.0 - a_prev) ** 0.5 * e_t
+    return x
+
+
 def q_sample(x_start, t, noise, num_ddpm=1000):
     """VD_v2_0.q_sample, vd.py:221-224: sqrt(ac_t) * x0 + sqrt(1 - ac_t) * noise (per-row t)."""
     sch = ddpm_schedule(num_ddpm)     # sqrt taken in fp64, stored fp32 — as the reference's registered buffers

@@ -153,6 +153,29 @@ finally:
 with torch.no_grad():
     xo = O.ddim_sample(sd, xT, [ct, ci], [ut, ui], 4, 7.5, c_types=('text', 'image'), ratios=[0.7, 0.3], model_channels=64)
 assert (xm - xo).abs().max() <= 5e-4 * xm.abs().max(), (xm - xo).abs().max()
+# text-latent flows (SURVEY 8f rank 4): the 0-D diffuser with its data blocks, apply_model + the 4-step CFG DDIM walk on [n, 768]
+net_t = ref_shims.build_vd(unet_overrides=dict(model_channels=64), with_vae=False, text_parts='dc')
+sd_t = weights.synth_state_dict(weights.param_shapes(net_t), seed=6)
+net_t.load_state_dict(sd_t, strict=False)
+xt = torch.randn(2, 768, generator=g)
+ci2, ui2 = torch.randn(2, 40, 768, generator=g) * 0.5, torch.zeros(2, 40, 768)
+with torch.no_grad():
+    ea = net_t.apply_model({'type': 'text', 'x': xt}, torch.tensor([5, 900]), {'type': 'image', 'c': ci2})
+    eb = O.apply_model_text(sd_t, xt, torch.tensor([5, 900]), [ci2], c_types=('image',), model_channels=64)
+assert (ea - eb).abs().max() <= 2e-4 * ea.abs().max(), (ea - eb).abs().max()
+St = rd.DDIMSampler(net_t)
+orig = torch.randn
+torch.randn = lambda *a, **k: xt.clone() if (len(a) > 0 and list(a[0]) == [2, 768]) else orig(*a, **k)
+try:
+    with torch.no_grad():
+        xs, _ = St.sample(steps=4, shape=[2, 768], x_info={'type': 'text'},
+                          c_info={'type': 'image', 'conditioning': ci2, 'unconditional_conditioning': ui2,
+                                  'unconditional_guidance_scale': 7.5}, verbose=False, eta=0.)
+finally:
+    torch.randn = orig
+with torch.no_grad():
+    xr = O.ddim_sample_text(sd_t, xt, [ci2], [ui2], 4, 7.5, c_types=('image',), model_channels=64)
+assert (xs - xr).abs().max() <= 5e-4 * xs.abs().max(), (xs - xr).abs().max()
 print('LIVE-OK')
 """ % ROOT
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)

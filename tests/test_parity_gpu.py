@@ -447,3 +447,27 @@ def test_text_latent_apply_model_vs_reference_golden():
                                            [{"type": "text", "c": gt["c_text"].to(DEV), "ratio": 0.4},
                                             {"type": "image", "c": gt["c_img"].to(DEV), "ratio": 0.6}])
         _cmp(out, ref, what="text-latent apply_model_multicontext vs oracle")
+
+
+def test_text_latent_ddim_sampler_vs_oracle():
+    """inference_i2t / inference_t2t up to the Optimus decode (app.py:384-434): DDIMSampler.sample on a [n, 768] latent with CFG,
+    eager and through the captured step graph, against the oracle's DDIM walk over apply_model_text."""
+    from lib.model_zoo.ddim import DDIMSampler
+    from oracle import vd_oracle as O
+    net, sd = build_net(mini=True, with_vae=False, text_flows=True)
+    g = torch.Generator().manual_seed(41)
+    xT = torch.randn(2, 768, generator=g)
+    c, u = torch.randn(2, 257, 768, generator=g) * 0.5, torch.zeros(2, 257, 768)
+    outs = []
+    for graph in (False, True):
+        with torch.no_grad():
+            x, _ = DDIMSampler(net, use_cuda_graph=graph).sample(
+                steps=4, shape=[2, 768], x_info={"type": "text", "xt": xT.clone()},
+                c_info={"type": "image", "conditioning": c.to(DEV), "unconditional_conditioning": u.to(DEV),
+                        "unconditional_guidance_scale": 7.5}, verbose=False, eta=0.)
+        assert x.shape == (2, 768)
+        outs.append(x)
+    assert torch.equal(outs[0], outs[1]), "graph path must equal the eager path"
+    with torch.no_grad():
+        ref = O.ddim_sample_text(sd, xT, [c], [u], 4, 7.5, c_types=("image",), model_channels=64)
+    _cmp(outs[0], ref, cos_min=0.995, tol=0.1, what="4-step DDIM on a text latent (i2t) vs oracle")

@@ -142,7 +142,12 @@ class DDIMSampler(object):
         time_from = model.time_source(x_type, multi)
         mch = model.diffuser[time_from].model_channels
         B = 2 * bs if cfg else bs
-        H, W = shape[2], shape[3]
+        # text latents ([n, 768], the i2t / t2t flows: app.py:384-434) walk the same loop as a 1x1 "image" of 768 channels: the
+        # NCHW <-> NHWC conversions are identities and the 0-D diffuser takes the flat view
+        flat = len(shape) == 2
+        H, W = (1, 1) if flat else (shape[2], shape[3])
+        if flat:
+            x = x.reshape(bs, shape[1], 1, 1)
 
         # device-side per-step tables, indexed by the DDIM index (total_steps-1 ... 0)
         coef = torch.tensor(np.stack([np.asarray(self.ddim_alphas.cpu() if isinstance(self.ddim_alphas, torch.Tensor) else self.ddim_alphas, dtype=np.float32)[:total_steps],
@@ -162,7 +167,9 @@ class DDIMSampler(object):
 
         def step(noise=None):
             t_emb = ops.timestep_embedding(st['ts'], mch, step_idx=st['idx'], batch=B)
-            eps = model.eps_nhwc(st['x_in'], x_type, t_emb, c_types, ctxs, ratios, time_from)
+            eps = model.eps_nhwc(st['x_in'].view(B, -1) if flat else st['x_in'], x_type, t_emb, c_types, ctxs, ratios, time_from)
+            if flat:
+                eps = eps.view(B, 1, 1, -1)
             e_u, e_c = (eps[:bs], eps[bs:]) if cfg else (None, eps)
             ops.ddim_cfg_step(e_u, e_c, st['x_in'][:bs], st['coef'], scale, x_prev=st['x_in'][:bs],
                               x_prev_dup=st['x_in'][bs:] if cfg else None, pred_x0=st['pred_x0'], noise=noise,
@@ -219,6 +226,9 @@ class DDIMSampler(object):
                     log(total_steps - i - 1)
 
         pred_xt = ops.nhwc_to_nchw(st['x_in'][:bs].contiguous()).to(dtype)
+        if flat:
+            pred_xt = pred_xt.reshape(bs, -1)
+            intermediates = {k: [v.reshape(bs, -1) for v in vs] for k, vs in intermediates.items()}
         x_info['x'] = pred_xt
         return pred_xt, intermediates
 

@@ -563,16 +563,25 @@ class FCBlock_MultiDim(PackedModule, TimestepBlock):
                 "w2": bf16(w2), "b2": b2.contiguous(), "has_skip": has_skip, "sdim": sdim,
                 "g1": g1.contiguous(), "be1": be1.contiguous(), "g2": g2.contiguous(), "be2": be2.contiguous()}
 
-    @staticmethod
-    def _gn_silu(x, gamma, beta, eps, x2=None):
+    _unit = {}
+
+    @classmethod
+    def _unit_affine(cls, C, device):
+        """persistent (1, 0) GroupNorm parameters per channel count (no allocation / fill inside a captured step)"""
+        key = (C, str(device))
+        if key not in cls._unit:
+            cls._unit[key] = (torch.ones(C, dtype=torch.float32, device=device), torch.zeros(C, dtype=torch.float32, device=device))
+        return cls._unit[key]
+
+    @classmethod
+    def _gn_silu(cls, x, gamma, beta, eps, x2=None):
         """GroupNorm32 + SiLU over the flattened channels of [B, sdim, 1, C] (+ concat): statistics per (image, channel group) over
         all sdim positions == the reference's groups of the flattened index; gamma / beta differ per position, so the affine
         part is applied with identity parameters by the kernel's statistics pass and finished per position."""
         ops = _ops()
         B, sdim, _, C1 = x.shape
         C = C1 + (x2.shape[-1] if x2 is not None else 0)
-        ones = torch.ones(C, dtype=torch.float32, device=x.device)
-        zeros = torch.zeros(C, dtype=torch.float32, device=x.device)
+        ones, zeros = cls._unit_affine(C, x.device)
         xn = ops.groupnorm(x, ones, zeros, eps, act=ops.ACT_NONE, x2=x2)            # (x - mean) * rstd, bf16 [B, sdim, 1, C]
         return ops.affine_silu_rows(xn.view(B, sdim * C), gamma.view(-1), beta.view(-1))
 
