@@ -81,8 +81,16 @@ def test_config_bank_and_registry_surface():
     with pytest.raises(KeyError):
         bank("optimus_v1")                               # text-latent flows are out of the hot-path build
     assert get_model() is get_model()                    # singleton like the reference
-    with pytest.raises(NotImplementedError):
-        get_model()(bank("openai_unet_0d_v1"))           # 0-D data blocks: out of scope, fails loudly
+    # the 0-D diffuser's data blocks (text-latent flows, round 2) build from the reference's config keys; every FCBlock gets a
+    # column slot of the diffuser-level fused embedding projection
+    cfg0 = bank("openai_unet_0d_v1")
+    assert cfg0.args.parts == ["global", "data", "context"] or "data" in cfg0.args.parts
+    cfg0.args.model_channels, cfg0.args.input_channels, cfg0.args.output_channels = 32, 24, 24
+    cfg0.args.context_dim, cfg0.args.num_heads = 16, 2
+    u0 = get_model()(cfg0)
+    fcs = u0._fc_blocks()
+    assert len(fcs) > 0 and fcs[0].emb_slot == (0, None) and u0._emb_total == sum(f.out_channels for f in fcs)
+    assert [f.emb_slot[0] for f in fcs] == sorted(f.emb_slot[0] for f in fcs)
 
 
 def test_to_returns_none_and_no_cpu_path():

@@ -18,27 +18,54 @@ from collections import OrderedDict
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "versatile-diffusion_b200"))
+TEXT = "--text" in sys.argv                      # the text-latent (i2t) step of the full-size 0-D diffuser instead of the C2 image step
+if TEXT:
+    os.environ["VDB_TEXT_FLOWS"] = "1"
+_pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+REPS = int(_pos[0]) if _pos else 10
 import torch  # noqa: E402
-import bench  # noqa: E402
+if not TEXT:
+    import bench  # noqa: E402
 from lib.model_zoo.ddim import DDIMSampler  # noqa: E402
 from vdb200 import _lib, ops  # noqa: E402
 
-REPS = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 # torch.cuda.graph() calls torch.cuda.empty_cache() on entry: the cached blocks the recorded pointers live in would be
 # unmapped before the replay (first GPU run of this tool: "illegal memory access" on every replay).  Keep them mapped.
 torch.cuda.empty_cache = lambda: None
 dev = torch.device("cuda", 0)
-net = bench.build_net(dev)
 g = torch.Generator().manual_seed(0)
-xT = torch.randn(4, 4, 64, 64, generator=g).to(dev)
-c = (torch.randn(4, 77, 768, generator=g) * 0.5).to(dev)
-u = (torch.randn(4, 77, 768, generator=g) * 0.5).to(dev)
+if TEXT:
+    from lib.cfg_helper import model_cfg_bank  # noqa: E402
+    from lib.model_zoo import get_model  # noqa: E402
+    cfg = model_cfg_bank()('vd_four_flow_v1-0')
+    cfg.args.ctx_cfg_list = []
+    cfg.args.vae_cfg_list = []
+    torch.manual_seed(0)
+    with torch.device(dev):
+        net = get_model()(cfg, verbose=False)
+    gd = torch.Generator(device=dev).manual_seed(1)
+    with torch.no_grad():
+        for _, p_ in net.named_parameters():
+            if (p_.ndim == 1 and not bool((p_ == 1).all())) or not bool(p_.any()):
+                p_.normal_(0.0, 0.02, generator=gd)
+    net.eval()
+    net.to(dev)
+    xT = torch.randn(4, 768, generator=g).to(dev)
+    c = (torch.randn(4, 257, 768, generator=g) * 0.5).to(dev)
+    u = torch.zeros(4, 257, 768, device=dev)
+    SHAPE, XT, CT = [4, 768], "text", "image"
+else:
+    net = bench.build_net(dev)
+    xT = torch.randn(4, 4, 64, 64, generator=g).to(dev)
+    c = (torch.randn(4, 77, 768, generator=g) * 0.5).to(dev)
+    u = (torch.randn(4, 77, 768, generator=g) * 0.5).to(dev)
+    SHAPE, XT, CT = [4, 4, 64, 64], "image", "text"
 
 
 def sample(sampler, steps):
     with torch.no_grad():
-        return sampler.sample(steps=steps, shape=[4, 4, 64, 64], x_info={"type": "image", "xt": xT},
-                              c_info={"type": "text", "conditioning": c, "unconditional_conditioning": u,
+        return sampler.sample(steps=steps, shape=SHAPE, x_info={"type": XT, "xt": xT},
+                              c_info={"type": CT, "conditioning": c, "unconditional_conditioning": u,
                                       "unconditional_guidance_scale": 7.5}, verbose=False, eta=0.)[0]
 
 
@@ -120,6 +147,26 @@ def time_one(fn, args):
     return best
 
 
+def time_family(items):
+    """all launches of one family, recorded order, ONE pass per replay: weights arrive from HBM as in the real step (a launch
+    replayed alone keeps its weights in the 126 MB L2, which flatters the weight-streaming GEMMs of the 0-D diffuser)"""
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        cs = torch.cuda.current_stream().cuda_stream
+        for _, fn, args in items:
+            a = list(args); a[-1] = cs
+            if fn(*a):
+                raise RuntimeError(_lib.lib.vdb_last_error())
+    gr.replay(); torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(3):
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(); gr.replay(); s1.record(); torch.cuda.synchronize()
+        best = min(best, s0.elapsed_time(s1) * 1000.0)
+    del gr
+    return best
+
+
 agg = OrderedDict()
 total = 0.0
 for name, fn, args in step:
@@ -149,3 +196,22 @@ for k, (n, us) in agg.items():
 print("\nby family:")
 for f, (n, us) in sorted(fam.items(), key=lambda kv: -kv[1][1]):
     print(f"  {f:20s} n={n:4d} {us:10.1f} us {100.0 * us / total:6.1f}%")
+
+print("\nby family, one pass over the family's launches per replay (cold weights, as in the step):")
+byf = OrderedDict()
+for r in step:
+    byf.setdefault(label(r[0], r[2]).split()[0], []).append(r)
+tot_f = 0.0
+for f, items in byf.items():
+    try:
+        us = time_family(items)
+    except Exception as ex:  # noqa
+        print(f"  {f}: could not replay ({str(ex)[:80]})")
+        continue
+    tot_f += us
+    print(f"  {f:20s} n={len(items):4d} {us:10.1f} us  ({us / len(items):7.2f} us per launch)")
+print(f"  sum {tot_f:10.1f} us of the {step_us:.1f} us step")
+try:
+    print(f"  whole step's launches in one graph, recorded order: {time_family(step):10.1f} us")
+except Exception as ex:  # noqa
+    print(f"  whole step: could not replay ({str(ex)[:80]})")

@@ -529,6 +529,7 @@ class FCBlock_MultiDim(PackedModule, TimestepBlock):
         self.emb_channels = emb_channels
         self.dropout = dropout
         self.use_checkpoint = use_checkpoint
+        self.emb_slot = None  # (offset, total) into the diffuser-level fused emb projection, set by the owner
         self.in_layers = nn.Sequential(normalization(self.channels), nn.SiLU(), nn.Conv2d(self.channels, self.out_channels, 1, padding=0))
         self.emb_layers = nn.Sequential(nn.SiLU(), linear(emb_channels, self.out_channels))
         self.out_layers = nn.Sequential(normalization(self.out_channels), nn.SiLU(), nn.Dropout(p=dropout),
@@ -594,8 +595,12 @@ class FCBlock_MultiDim(PackedModule, TimestepBlock):
         B, sdim = x1.shape[0], x1.shape[1]
         eps = self.in_layers[0].eps
         a1 = self._gn_silu(x1, p["g1"], p["be1"], eps, x2=x2)                      # [B, sdim*Cin] bf16
-        e = ops.linear_small(emb.float().contiguous(), p["we"], (p["be"] + p["b1"]).contiguous(), act_in=ops.ACT_SILU)
-        h = ops.gemm(a1, p["w1"], bias=e, bias_bstride=self.out_channels, rows_per_batch=1)
+        if isinstance(emb, EmbTable):
+            e, bstride = emb.slot(self.emb_slot[0]), emb.total
+        else:
+            e = ops.linear_small(emb.float().contiguous(), p["we"], (p["be"] + p["b1"]).contiguous(), act_in=ops.ACT_SILU)
+            bstride = self.out_channels
+        h = ops.gemm(a1, p["w1"], bias=e, bias_bstride=bstride, rows_per_batch=1)
         Cout = self.out_channels_multidim[0]
         a2 = self._gn_silu(h.view(B, sdim, 1, Cout), p["g2"], p["be2"], self.out_layers[0].eps)
         raw = x1 if x2 is None else torch.cat([x1, x2], dim=-1)                     # (data movement only: 4 positions per row)
@@ -722,11 +727,39 @@ class UNetModel0D_Next(UNetModel2D_Next):
         if self.clayer_included:
             self.parameter_group['context'] = self.context_blocks
         self._emb_packed = None
+        self._assign_emb_slots()
+
+    def _fc_blocks(self):
+        return [layer for blk in self.data_blocks for layer in blk if isinstance(layer, FCBlock_MultiDim)] if self.dlayer_included else []
+
+    def _assign_emb_slots(self):
+        off = 0
+        for layer in self._fc_blocks():
+            layer.emb_slot = (off, None)
+            off += layer.out_channels
+        self._emb_total = off
+
+    def _pack_emb(self):
+        if self._emb_packed is None:
+            with torch.no_grad():
+                ps = [layer.packed() for layer in self._fc_blocks()]
+                self._emb_packed = {"w": torch.cat([q["we"] for q in ps], 0).contiguous(),
+                                    "b": torch.cat([q["be"] + q["b1"] for q in ps], 0).contiguous()}
+        return self._emb_packed
 
     def embed_table(self, t_emb, time_owner=None):
-        """Sinusoid [B, model_channels] fp32 -> the raw time embedding fp32 [B, 4*model_channels]; every FCBlock applies its own
-        SiLU -> Linear (the per-block projections are 1280 x (C*sdim): streamed once per call either way)."""
-        return (time_owner or self).time_embedding(t_emb)
+        """Sinusoid [B, model_channels] fp32 -> EmbTable: the time_embed MLP, then the SiLU -> Linear of EVERY FCBlock as one
+        [B, sum(C*sdim)] tensor-core GEMM with the first conv's bias folded in (columns in each block's NHWC order).  Per block
+        and step this was a 54 us CUDA-core launch (29 % of the text-latent step, profiles/r02_text_step_breakdown_v1.txt).
+        Without data blocks (context-only build) the raw embedding is returned."""
+        if not self.dlayer_included:
+            return (time_owner or self).time_embedding(t_emb)
+        ops = _ops()
+        w0, b0, w2, b2 = (time_owner or self).time_embed_packed()
+        p = self._pack_emb()
+        h = ops.gemm(ops.to_bf16(t_emb.contiguous()), w0, bias=b0, act=ops.ACT_SILU, ksplit=1)
+        s = ops.gemm(h, w2, bias=b2, act=ops.ACT_SILU, ksplit=1)          # SiLU(time_embed(t_emb)), bf16
+        return EmbTable(ops.gemm(s, p["w"], bias=p["b"], out_dtype=torch.float32, ksplit=1))
 
     def forward(self, *a, **k):
         raise NotImplementedError("the 0-D diffuser is driven by VD_v2_0.apply_model (data blocks of diffuser[x_type], context blocks of diffuser[c_type])")
