@@ -230,6 +230,8 @@ ATT_CASES = [
     (1, 3, 256, 1000, 40, False),      # masked tail tile (1000 = 7 * 128 + 104)
     (2, 2, 768, 520, 48, False),       # d 48; kv stride 520, five tiles, last one 8 keys
     (8, 8, 4096, 4096, 40, False),     # the benchmark's own self-attention launch (B = 8, 64x64 latent)
+    (2, 3, 512, 900, 56, False),       # d 56 in DVP 64: row sums through the ones row of V^T, masked tail
+    (1, 2, 256, 512, 32, False),       # d 32 in DVP 48: two padding swizzle groups behind the data rows
 ]
 
 

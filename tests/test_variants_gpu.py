@@ -23,7 +23,7 @@ VARIANTS = [
     ({"VDB_GN_BUNDLE": "0"}, "groupnorm"),         # single-launch pixel-range GroupNorm instead of the group-bundle kernel
     ({"VDB_LN_RG": "0"}, "layernorm"),             # warp-per-row LayerNorm instead of the row-group kernel
     ({"VDB_ATT_FA": "0"}, "attention"),            # column-split attention kernel for every shape (round-1 default)
-    ({"VDB_ATT_FA": "111"}, "attention"),          # two-tile kernel with P through shared memory (SS product)
+    ({"VDB_ATT_ONES": "0"}, "attention"),          # two-tile kernel with the row sums on the softmax threads
 ]
 
 RUN = pytest.mark.skipif(os.environ.get("VDB_TEST_VARIANTS") != "1", reason="set VDB_TEST_VARIANTS=1 to run the opt-in kernel variants")

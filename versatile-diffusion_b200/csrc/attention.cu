@@ -497,7 +497,11 @@ VDB_DEVINL void ex2_poly2(float xa, float xb, float& ea, float& eb) {
   eb = __int_as_float(__float_as_int(pb) + (__float_as_int(rb) << 23));
 }
 
-template <int DVP, int KV_STAGES, int POLY, int TOKEN>
+//   * ONES (d_head < DVP, i.e. the V^T tile has a zero-padding row): the row sums come out of the tensor core.  The TMA box
+//     of a V^T tile covers only the d_head real rows; row d_head of every stage is written ONCE with bf16 ones (the rest of
+//     the padding with zeros), so column d_head of O accumulates sum_j P (of the bf16-rounded probabilities the PV product
+//     actually uses, rescaled with O for free) and the softmax threads drop their 64 packed adds per tile (~12 % of the loop).
+template <int DVP, int KV_STAGES, int POLY, int TOKEN, int ONES>
 __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_constant__ AttnParams p) {
   constexpr int PT = 1;   // P in tensor memory (TS product).  PT = 0 (P through shared memory, SS product) measured the same: 350 vs 347 us
   constexpr int BKV = 128;
@@ -557,6 +561,18 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_holder);
+  const int vrows = ONES ? p.dv : DVP;              // rows of a V^T atom the TMA box fills
+  if (ONES && warp == 3) {
+    // static padding rows [d_head, DVP) of every V^T atom: row d_head = ones, the others zero (128-byte rows; the 16-byte-chunk
+    // swizzle permutes equal chunks, so the row can be written linearly)
+    const int prow = DVP - p.dv;                    // a multiple of 8 rows, starting on an 8-row swizzle group
+    for (int i = lane; i < KV_STAGES * 2 * prow * 8; i += 32) {
+      const int chunk = i & 7, row = (i >> 3) % prow, atom = (i >> 3) / prow;
+      const uint32_t v = (row == 0) ? 0x3F803F80u : 0u;
+      *reinterpret_cast<uint4*>(sV + atom * kVAtom + (p.dv + row) * 128 + chunk * 16) = make_uint4(v, v, v, v);
+    }
+    fence_proxy_async_smem();                       // generic-proxy stores -> visible to the tensor core's async-proxy reads
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -578,7 +594,7 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
         mbar_arrive_expect_tx(&k_full[st], kKBytes);
         tma_load_2d(sK + st * kKBytes, &p.tmK, &k_full[st], p.k_col0 + head * 64, b * p.kv_bs + j * BKV);
         mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], kVBytes);
+        mbar_arrive_expect_tx(&v_full[st], static_cast<uint32_t>(2 * vrows * 128));
         for (int a = 0; a < 2; ++a)
           tma_load_2d(sV + st * kVBytes + a * kVAtom, &p.tmV, &v_full[st], b * p.kv_bs + j * BKV + a * 64, head * DVP);
       }
@@ -766,7 +782,9 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
                 e[i] = ex2_mufu(xa);
                 e[i + 1] = ex2_mufu(xb);
               }
-              if (i & 2) l2b = add_f2(l2b, pack_f2(e[i], e[i + 1])); else l2 = add_f2(l2, pack_f2(e[i], e[i + 1]));
+              if constexpr (!ONES) {
+                if (i & 2) l2b = add_f2(l2b, pack_f2(e[i], e[i + 1])); else l2 = add_f2(l2, pack_f2(e[i], e[i + 1]));
+              }
             }
             if constexpr (PT) {
               // packed bf16 pairs -> 32-bit tensor-memory columns [4 q, 4 q + 4) of this lane's P row; stored 32 columns at a time
@@ -779,9 +797,11 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
                            "r"(v4.x), "r"(v4.y), "r"(v4.z), "r"(v4.w) : "memory");
             }
           }
-          float la, lb;
-          unpack_f2(add_f2(l2, l2b), la, lb);
-          l_sum += la + lb;
+          if constexpr (!ONES) {
+            float la, lb;
+            unpack_f2(add_f2(l2, l2b), la, lb);
+            l_sum += la + lb;
+          }
         }
         VDB_FTL(8 * g + 5, j, tlw);
         if (!(j == ntiles - 1 && g == 1)) token_pass();   // (the ring is primed once: skip the one surplus hand-over)
@@ -794,6 +814,12 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
     }
     mbar_wait(&pv_done[g], (ntiles - 1) & 1);
     tc_fence_after();
+    if constexpr (ONES) {                         // column d_head of O = sum_j P (the ones row of V^T)
+      uint32_t o[16];                             // (16 columns from d_head on: element 0 is the sum; the rest is ignored)
+      tmem_ld16(tmem_O + p.dv, o);
+      tmem_wait_ld();
+      l_sum = __uint_as_float(o[0]);
+    }
     const float inv_l = 1.f / l_sum;
     const bool row_ok = q_idx < p.Nq;
     __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.q_bs + q_idx) * p.ldo + head * p.dv;
@@ -859,11 +885,11 @@ static int launch_attention(AttnParams& p, const AttnArgs& a, cudaStream_t strea
   return VDB_OK;
 }
 
-template <int DVP, int KV_STAGES, int POLY, int TOKEN>
+template <int DVP, int KV_STAGES, int POLY, int TOKEN, int ONES>
 static int launch_attention_fa(AttnParams& p, const AttnArgs& a, cudaStream_t stream) {
   constexpr size_t smem = attention_fa_smem_bytes<DVP, KV_STAGES>();
   static_assert(smem <= 227 * 1024, "attention (two-tile) smem budget");
-  auto kernel = attention_fa_kernel<DVP, KV_STAGES, POLY, TOKEN>;
+  auto kernel = attention_fa_kernel<DVP, KV_STAGES, POLY, TOKEN, ONES>;
   static bool configured = false;
   if (!configured) {
     VDB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -874,7 +900,8 @@ static int launch_attention_fa(AttnParams& p, const AttnArgs& a, cudaStream_t st
   if (rc) return rc;
   rc = make_tmap_2d(&p.tmK, a.K, static_cast<uint64_t>(a.ldk), static_cast<uint64_t>(a.B) * a.kv_bstride, a.ldk * 2, 64, 128);
   if (rc) return rc;
-  rc = make_tmap_2d(&p.tmV, a.Vt, static_cast<uint64_t>(a.B) * a.kv_bstride, static_cast<uint64_t>(a.H) * DVP, a.ldv * 2, 64, DVP);
+  rc = make_tmap_2d(&p.tmV, a.Vt, static_cast<uint64_t>(a.B) * a.kv_bstride, static_cast<uint64_t>(a.H) * DVP, a.ldv * 2, 64,
+                    ONES ? p.dv : DVP);          // ONES: the box leaves the static padding rows of the stage alone
   if (rc) return rc;
   dim3 grid((p.Nq + 2 * kBQ - 1) / (2 * kBQ), a.H, a.B);
   VDB_CUDA_CHECK(launch_pdl(kernel, grid, dim3(384), smem, stream, p));
@@ -884,11 +911,22 @@ static int launch_attention_fa(AttnParams& p, const AttnArgs& a, cudaStream_t st
 
 template <int DVP, int TOKEN>
 static int dispatch_attention_fa2(int poly, AttnParams& p, const AttnArgs& a, cudaStream_t st) {
+  // row sums through the ones row of V^T whenever the head has a padding row (VDB_ATT_ONES=0: summed by the softmax threads)
+  static const int ones_on = [] { const char* e = getenv("VDB_ATT_ONES"); return (e && e[0] == '0') ? 0 : 1; }();
+  if (ones_on && TOKEN == 1 && p.dv < DVP) {
+    switch (poly) {
+      case 2: return launch_attention_fa<DVP, 3, 2, 1, 1>(p, a, st);
+      case 3: return launch_attention_fa<DVP, 3, 3, 1, 1>(p, a, st);
+      case 4: return launch_attention_fa<DVP, 3, 4, 1, 1>(p, a, st);
+      case 1: return launch_attention_fa<DVP, 3, 1, 1, 1>(p, a, st);
+      default: break;
+    }
+  }
   switch (poly) {
-    case 0: return launch_attention_fa<DVP, 3, 0, TOKEN>(p, a, st);
-    case 2: return launch_attention_fa<DVP, 3, 2, TOKEN>(p, a, st);
-    case 3: return launch_attention_fa<DVP, 3, 3, TOKEN>(p, a, st);
-    default: return launch_attention_fa<DVP, 3, 1, TOKEN>(p, a, st);
+    case 0: return launch_attention_fa<DVP, 3, 0, TOKEN, 0>(p, a, st);
+    case 2: return launch_attention_fa<DVP, 3, 2, TOKEN, 0>(p, a, st);
+    case 3: return launch_attention_fa<DVP, 3, 3, TOKEN, 0>(p, a, st);
+    default: return launch_attention_fa<DVP, 3, 1, TOKEN, 0>(p, a, st);
   }
 }
 template <int DVP>
@@ -952,11 +990,14 @@ int vdb_attention_bf16(const void* Q, long long ldq, int q_col0, const void* K, 
   //   VDB_ATT_BKV=128  the 128-column kernel everywhere
   // default: the three-CTA kernel for short contexts (65..512 keys), the 128-column kernel otherwise
   // VDB_ATT_FA: the two-tile kernel (attention_fa_kernel).  0 = off; otherwise digits "PT": P = exp2 pairs of every 8 on the FMA
-  // pipe (0..3), T = 1 MUFU token / 0 free-running.  Default 11 (measured best: 329 us on the B = 8, N = 4096, d = 40 launch;
+  // pipe (0..4), T = 1 MUFU token / 0 free-running.  Without the ones row 11 was best (329 us on the B = 8, N = 4096, d = 40 launch;
   // 1 -> 358, 21 -> 334, 31 -> 334, 10 -> 340: profiles/r02_visit_f_summary.log).
   static const int fa = [] { const char* e = getenv("VDB_ATT_FA"); return e ? atoi(e) : -1; }();
   if (fa != 0 && DK == 64 && !causal && Nk >= 512 && Nq >= 256 && (Nq % 256) == 0) {
-    const int mode = fa < 0 ? 11 : fa;
+    // default: 3 of 8 pairs on the FMA pipe when the row sums come out of the tensor core (ONES: 315 us; 2 -> 318, 1 -> 340),
+    // 1 of 8 otherwise (328 us; profiles/r02_visit_o_attention_ones.log)
+    static const int ones_on = [] { const char* e = getenv("VDB_ATT_ONES"); return (e && e[0] == '0') ? 0 : 1; }();
+    const int mode = fa < 0 ? ((ones_on && d_head < DVP) ? 31 : 11) : fa;
     if (DVP == 48) return dispatch_attention_fa<48>(mode, p, a, st);
     if (DVP == 64) return dispatch_attention_fa<64>(mode, p, a, st);
   }
