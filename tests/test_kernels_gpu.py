@@ -139,6 +139,123 @@ def test_gemm_geglu(M, C):
     assert_close(out, ref, what="geglu")
 
 
+# ---- LayerNorm folded into the GEMMs (vdb_gemm_ln_bf16) ------------------------------------------------------------------
+def _chunk_stats(x, width=32):
+    """[M, C] fp32 -> [C/width, M, 2] partial (sum, sum of squares) over column ranges: the kind of table a producer GEMM writes"""
+    M, C = x.shape
+    xc = x.view(M, C // width, width)
+    return torch.stack([xc.sum(-1), (xc * xc).sum(-1)], -1).permute(1, 0, 2).contiguous()
+
+
+def _ln(x, C, width=32):
+    st = _chunk_stats(x.float(), width)
+    return _ops().LnFold(st, st.shape[0], C, 1e-5)
+
+
+def _fold(w, b, gamma, beta):
+    wg = (w.float() * gamma[None, :]).to(torch.bfloat16).contiguous()
+    c = w.float() @ beta + (b if b is not None else 0)
+    return wg, wg.float().sum(1).contiguous(), c.contiguous()
+
+
+@pytest.mark.parametrize("M,N,K,resid,bn", [(1024, 320, 320, True, 0), (520, 640, 1280, True, 0), (4096, 320, 320, False, 160),
+                                            (300, 1280, 512, True, 64)])
+def test_gemm_ln_producer_writes_chunk_statistics(M, N, K, resid, bn):
+    ops = _ops()
+    a, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5)
+    b = rnd(N, seed=3, dtype=torch.float32)
+    r = rnd(M, N, seed=4) if resid else None
+    st = ops.ln_stats_buffer(M, N, a.device)
+    st.fill_(float("nan"))
+    out, parts = ops.gemm_ln(a, w, bias=b, resid=r, stats_out=st, bn=bn)
+    ref = a.float() @ w.float().t() + b + (r.float() if resid else 0)
+    assert_close(out, ref, what=f"gemm_ln producer {M}x{N}x{K}")
+    assert 2 <= parts <= st.shape[0] and torch.isfinite(st[:parts]).all()
+    tot = st[:parts].sum(0)                                       # [M, 2]: the partials add up to the row sums
+    ref_tot = torch.stack([ref.sum(1), (ref * ref).sum(1)], -1)
+    err = (tot - ref_tot).abs().max().item()
+    assert err <= 2e-3 * ref_tot.abs().max().item() + 1e-3, f"row statistics off by {err}"
+
+
+@pytest.mark.parametrize("M,N,C,bias,mean", [(1024, 1024, 320, False, 0.0), (2048, 512, 640, True, 1.5), (384, 2048, 1280, True, -0.7),
+                                             (100, 320, 320, True, 4.0)])
+def test_gemm_ln_consumer_rows(M, N, C, bias, mean):
+    """Linear(LayerNorm(x)) from the raw x + per-chunk statistics; `mean` shifts the rows (the rank-1 term must cancel it)"""
+    ops = _ops()
+    x = (rnd(M, C, seed=1).float() * 1.3 + mean).to(torch.bfloat16)
+    w0 = rnd(N, C, seed=2, scale=C ** -0.5)
+    b0 = rnd(N, seed=3, dtype=torch.float32) if bias else None
+    gamma = 1.0 + 0.3 * rnd(C, seed=4, dtype=torch.float32)
+    beta = 0.2 * rnd(C, seed=5, dtype=torch.float32)
+    wg, s, c = _fold(w0, b0, gamma, beta)
+    out = ops.gemm_ln(x, wg, bias=c, ln=_ln(x, C, 32 if C > 320 else 160), colsum=s)     # 2 .. 40 partials per row
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5) @ w0.float().t() + (b0 if bias else 0)
+    assert_close(out, ref, what=f"gemm_ln rows {M}x{N}x{C} mean {mean}")
+
+
+@pytest.mark.parametrize("T,R,C", [(4096, 384, 320), (992, 384, 640), (256, 640, 1280)])
+def test_gemm_ln_consumer_columns(T, R, C):
+    """the transposed projection: out^T [R, T] = W0 LayerNorm(x)^T, statistics per output COLUMN (token)"""
+    ops = _ops()
+    x = (rnd(T, C, seed=1).float() + 0.8).to(torch.bfloat16)
+    w0 = rnd(R, C, seed=2, scale=C ** -0.5)
+    gamma = 1.0 + 0.3 * rnd(C, seed=4, dtype=torch.float32)
+    beta = 0.2 * rnd(C, seed=5, dtype=torch.float32)
+    wg, s, c = _fold(w0, None, gamma, beta)
+    out = ops.gemm_ln(wg, x, ln=_ln(x, C, 64), colsum=s, on_cols=True, rowbias=c)
+    ref = w0.float() @ F.layer_norm(x.float(), (C,), gamma, beta, 1e-5).t()
+    assert out.shape == (R, T)
+    assert_close(out, ref, what=f"gemm_ln columns {R}x{T}x{C}")
+
+
+@pytest.mark.parametrize("M,C", [(512, 320), (1024, 640)])
+def test_gemm_ln_consumer_geglu(M, C):
+    ops = _ops()
+    x = (rnd(M, C, seed=1).float() * 0.9 - 0.4).to(torch.bfloat16)
+    w0 = rnd(8 * C, C, seed=2, scale=C ** -0.5)
+    b0 = rnd(8 * C, seed=3, dtype=torch.float32)
+    gamma = 1.0 + 0.3 * rnd(C, seed=4, dtype=torch.float32)
+    beta = 0.2 * rnd(C, seed=5, dtype=torch.float32)
+    wg, s, c = _fold(w0, b0, gamma, beta)
+    wp, cp = pack_geglu(wg, c)
+    _, sp = pack_geglu(wg, s)
+    out = ops.gemm_ln(x, wp, bias=cp, act=ops.ACT_GEGLU, ln=_ln(x, C, 80), colsum=sp)
+    h = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5) @ w0.float().t() + b0
+    val, gate = h.chunk(2, dim=-1)
+    assert out.shape == (M, 4 * C)
+    assert_close(out, val * F.gelu(gate), what="gemm_ln geglu")
+
+
+def test_gemm_ln_rejects_what_the_tma_store_epilogue_cannot_do():
+    from vdb200._lib import VdbError
+    ops = _ops()
+    x, w = rnd(1000, 320, seed=1), rnd(384, 320, seed=2)
+    s = torch.zeros(384, device=DEV)
+    with pytest.raises(VdbError):        # 1000 output columns: not a multiple of 32
+        ops.gemm_ln(w, x, ln=_ln(x, 320), colsum=s, on_cols=True)
+    with pytest.raises(VdbError):        # neither consumer nor producer
+        ops.gemm_ln(x, w)
+
+
+def test_gemm_ln_producer_feeds_consumer():
+    """the real chain: producer GEMM (+resid) writes the statistics of ITS bf16 output rows, the consumer normalises with them"""
+    ops = _ops()
+    M, C, N = 2048, 320, 1024
+    a, w = rnd(M, C, seed=1), rnd(C, C, seed=2, scale=C ** -0.5)
+    r = rnd(M, C, seed=3)
+    st = ops.ln_stats_buffer(M, C, a.device)
+    x, parts = ops.gemm_ln(a, w, resid=r, stats_out=st)
+    w0 = rnd(N, C, seed=4, scale=C ** -0.5)
+    gamma = 1.0 + 0.3 * rnd(C, seed=5, dtype=torch.float32)
+    beta = 0.2 * rnd(C, seed=6, dtype=torch.float32)
+    wg, s, c = _fold(w0, None, gamma, beta)
+    out = ops.gemm_ln(x, wg, bias=c, ln=ops.LnFold(st, parts, C, 1e-5), colsum=s)
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5) @ w0.float().t()
+    assert_close(out, ref, what="gemm_ln chain")
+    via_kernel = ops.gemm(ops.layernorm(x, gamma, beta, eps=1e-5), w0)
+    assert_close(out, via_kernel.float(), what="gemm_ln chain vs LayerNorm kernel + GEMM")
+
+
 def pack_conv_w(w, skip_ws=()):
     """[N,C,3,3] -> [N, (ky,kx,c)] (+ 1x1 skip columns)"""
     cols = [w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)]

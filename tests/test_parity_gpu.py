@@ -122,6 +122,29 @@ def test_unet_forward_matches_oracle_fresh_inputs(mini):
     _cmp(out, ref, what="apply_model vs oracle (24x24, B=3, L=50)")
 
 
+def test_layernorm_fold_equals_the_layernorm_kernels(mini, monkeypatch):
+    """The three LayerNorms of every transformer block run inside the neighbouring GEMMs' epilogues by default (vdb_gemm_ln_bf16);
+    VDB_LN_FOLD=0 runs them as kernels.  Same eps prediction (both are checked against the reference golden), fewer launches."""
+    from vdb200 import ops
+    net, sd, gi, gold = mini
+    args = ({"type": "image", "x": gi["x"].to(DEV)}, gi["t"].to(DEV), {"type": "text", "c": gi["c_text"].to(DEV)})
+    with torch.no_grad():
+        net.apply_model(*args)
+        ops.reset_launch_count()
+        out_fold = net.apply_model(*args)
+        n_fold = ops.launch_count()
+        monkeypatch.setenv("VDB_LN_FOLD", "0")
+        ops.reset_launch_count()
+        out_ln = net.apply_model(*args)
+        n_ln = ops.launch_count()
+    _cmp(out_ln, gold["eps_text"], what="apply_model with LayerNorm kernels (reference golden)")
+    _cmp(out_fold, gold["eps_text"], what="apply_model with folded LayerNorms (reference golden)")
+    # (two bf16 schedules of the same arithmetic: they differ from each other by about what each differs from the fp32 reference)
+    _cmp(out_fold, out_ln, cos_min=0.9998, tol=3e-2, what="folded LayerNorms vs LayerNorm kernels")
+    print(f"[parity] launches per UNet evaluation: {n_ln} with LayerNorm kernels, {n_fold} folded")
+    assert n_fold < n_ln
+
+
 def test_fresh_context_tensors_never_hit_a_stale_kv_cache(mini):
     """K / V^T of the context are cached per CrossAttention; a NEW context tensor that the allocator places at the
     address of a freed one (same shape, same version) must not be served the old projections."""

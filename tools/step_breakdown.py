@@ -83,10 +83,16 @@ records = []
 real = {}
 
 
+_PARTS = ctypes.c_int(0)      # vdb_gemm_ln_bf16 producers report their partial count through a host int*: the caller's is gone at replay
+
+
 def make_wrapper(name, fn):
     def wrapper(*args):
+        rc = fn(*args)
+        if name == "vdb_gemm_ln_bf16" and args[22]:
+            args = args[:22] + (ctypes.addressof(_PARTS),) + args[23:]
         records.append((name, fn, args))
-        return fn(*args)
+        return rc
     return wrapper
 
 
@@ -115,6 +121,8 @@ def label(name, a):
     """family + the shape arguments that identify the launch (positions follow include/vdb200.h)."""
     if name == "vdb_gemm_bf16":
         return f"gemm M{a[1]} N{a[8]} K{a[2] + a[5]} act{a[18]}{' +res' if a[13] else ''}"
+    if name == "vdb_gemm_ln_bf16":
+        return f"gemm M{a[1]} N{a[5]} K{a[2]} act{a[12]}{' +res' if a[8] else ''}{' ln-in' if a[13] else ''}{'-cols' if a[19] else ''}{' stats-out' if a[21] else ''}"
     if name == "vdb_conv3x3_bf16":
         return f"conv3x3 B{a[1]} {a[2]}x{a[3]} C{a[4]}+{a[10]}+{a[12]} -> N{a[7]} mode{a[5]}"
     if name == "vdb_attention_bf16":

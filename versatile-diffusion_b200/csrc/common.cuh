@@ -21,6 +21,14 @@ enum : int {
   VDB_ERR_UNSUPPORTED = 3, // shape outside what the kernels implement
 };
 
+// 16-byte shared-memory load through a 32-bit shared address (a pointer derived from the aligned dynamic window has lost its
+// address space: the compiler emits generic LD.E instead of LDS)
+VDB_DEVINL float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 VDB_DEVINL uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

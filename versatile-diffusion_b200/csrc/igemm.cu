@@ -61,9 +61,20 @@ struct alignas(64) IgemmParams {
   int act;                    // 0 none, 1 silu, 2 gelu(erf), 3 quick_gelu, 4 geglu (packed halves)
   float alpha;                // out = act(alpha * (acc + bias)) + resid
   float* partial;             // split-K: [ksplit, M, N] fp32
+  // LayerNorm folded into the GEMM (modes 5 / 6 consume, mode 7 produces; see the epilogue):
+  const float* ln_stats;      // [ln_parts][ln_mstat][2] fp32: partial (sum, sum of squares) over column ranges of the normalised rows
+  long long ln_mstat;         // rows of the statistics table
+  int ln_parts;               // partials per row (what the producer launch reported)
+  int ln_on_cols;             // 0: the statistics belong to the OUTPUT ROWS (x is the A operand); 1: to the output COLUMNS (x is B)
+  float ln_inv_dim, ln_eps;   // 1 / normalised width, epsilon
+  const float* ln_colsum;     // on_cols 0: [N] sum_k W'[n, k];  on_cols 1: [M] (per output row)
+  const float* ln_rowbias;    // on_cols 1: [M] beta-term of the output row (null = 0); on_cols 0 the beta term lives in `bias`
+  float* stats_out;           // mode 7: [2 * tilesN][M][2] fp32: (sum, sum of squares) of the columns each of the two epilogue
+                              // warps of a TMEM lane quarter handled in each N tile, for every OUTPUT row
   int epi_alt;                // 1: the two warps of a TMEM quarter swap chunk parity every tile (odd chunk counts)
   int nfast;                  // 1: N is the fast tile index (tile t -> n = t % tilesN, m = t / tilesN); needs ksplit == 1
   unsigned long long* timeline; // debug: per-tile role timestamps of CTA 0 (null = off)
+  unsigned smem_bytes;        // dynamic shared memory of the launch (LN modes check their carve-up against it)
 };
 
 enum { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_QGELU = 3, ACT_GEGLU = 4 };
@@ -112,8 +123,18 @@ VDB_DEVINL float apply_act(float v, int act) {
 // NEXT chunk prefetched, 2 = only GEGLU.  The generic kernel is ~6300 SASS instructions; ncu's source view of the
 // K = 320 GEMMs showed 9 % instruction-fetch stalls and 10 % branch-resolve stalls in the epilogue warps, and the
 // residual's first use exposed its full load latency (hot lines of the current build: profiles/r01_ncu_hot_lines_v7.txt).
+// Modes 3 / 4 are modes 1 / 2 with the tile leaving through shared memory + TMA stores.  Modes 5 / 6 are modes 3 / 4 for a GEMM whose
+// input is a LayerNorm: the operand is the RAW activation x and the weights carry gamma (W' = W * gamma), so with the row's mean mu
+// and rstd r       LN(x) W^T + b  =  r * (x W'^T  -  mu * s) + c,     s[n] = sum_k W'[n,k],  c[n] = sum_k beta_k W[n,k] + b[n]
+// is a rank-1 correction in the epilogue (2 FMAs per element) — the normalised tensor is never written or read.  mu and r come
+// from per-32-channel partial sums that the PRODUCER of x wrote from its own epilogue (mode 7 = mode 3 + those sums).  When x is
+// the B operand (the transposed V^T projection) the statistics belong to the output columns instead (ln_on_cols).
 template <int BN, int STAGES, int CTAS, int EW, int MODE>
 __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+  constexpr bool kTmaEpi = MODE >= 3;                 // TMA-store epilogues
+  constexpr bool kGegluEpi = MODE == 4 || MODE == 6;
+  constexpr bool kLnIn = MODE == 5 || MODE == 6;
+  constexpr bool kStatsOut = MODE == 7;
   constexpr int kNumEpiWarps = EW;
   constexpr int kNumEpiThreads = EW * 32;
   constexpr int kWPQ = EW / 4;           // epilogue warps per TMEM lane quarter
@@ -137,6 +158,13 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* sbias = reinterpret_cast<float*>(tmem_holder + 4);   // [BN] bias of the current output tile
+  float* slnx = sbias + BN;                                   // [BN] LN modes: colsum s (on_cols 0) / column mean (on_cols 1)
+  const uint32_t sbias_s = smem_u32(sbias), slnx_s = smem_u32(slnx);   // (shared-space addresses: LDS, not generic LD)
+  (void)slnx_s;
+  if constexpr (kLnIn) {
+    // (BN 256 leaves 912 instead of 1024 bytes of alignment slack; the dynamic window starts 1024-aligned in practice)
+    if (reinterpret_cast<uint8_t*>(slnx + BN) > smem_raw + p.smem_bytes) __trap();
+  }
   auto epi_bar_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory"); };   // the epilogue warps only
 
   const int warp = threadIdx.x >> 5;
@@ -314,6 +342,21 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
     int unit_m = t_first % unitsM, rest = t_first / unitsM;
     const int nf_step_n = p.nfast ? t_step % p.tilesN : 0, nf_step_m = p.nfast ? t_step / p.tilesN : 0;   // (see the producer)
     int nf_n = p.nfast ? t_first % p.tilesN : 0, nf_m = p.nfast ? t_first / p.tilesN : 0;
+    // folded LayerNorm, row statistics: partial sums of the row this thread owns in the NEXT tile, requested a tile ahead
+    constexpr int kLnPre = 16;
+    float2 ln_pre[kLnIn ? kLnPre : 1];
+    auto ln_prefetch = [&](int row) {
+      if constexpr (kLnIn) {
+        const bool ok = row < p.Wo;
+#pragma unroll
+        for (int i = 0; i < kLnPre; ++i)
+          ln_pre[i] = (ok && i < p.ln_parts) ? __ldg(reinterpret_cast<const float2*>(p.ln_stats) + static_cast<long long>(i) * p.ln_mstat + row)
+                                              : make_float2(0.f, 0.f);
+      }
+    };
+    if constexpr (kLnIn) {
+      if (!p.ln_on_cols && p.ln_parts <= kLnPre && t_first < num_tiles) ln_prefetch((t_first % unitsM) * kBlockM + r);
+    }
     for (int t = t_first; t < num_tiles; t += t_step, ++it) {
       const int m_idx = (p.nfast ? nf_m : unit_m) * CTAS + static_cast<int>(cta_rank);
       int n_idx = p.nfast ? nf_n : rest, ks = 0;
@@ -355,7 +398,38 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
       const bool bias_uniform = (MODE != 0) ? (p.bias != nullptr)    // host: a tile never straddles two bias rows
                                             : (p.bias && p.ksplit == 1 &&
                                                (p.bias_bstride == 0 || gp_first / p.rows_per_batch == gp_last / p.rows_per_batch));
-      if (bias_uniform) {
+      if constexpr (kLnIn) {
+        // folded-LayerNorm tiles: sbias = c[n] (beta term + bias), slnx = s[n]; or, when the statistics belong to the
+        // columns, sbias = rstd[n], slnx = mean[n] computed here from the producer's partial sums (one column per thread)
+        const float* key = reinterpret_cast<const float*>(static_cast<uintptr_t>(n0) + 1);
+        if (key != sbias_src) {
+          epi_bar_sync();
+          for (int i = threadIdx.x - 64; i < BN; i += kNumEpiThreads) {
+            const int n = n0 + i;
+            float a = 0.f, b = 0.f;
+            if (n < p.N) {
+              if (p.ln_on_cols) {
+                float su = 0.f, sq = 0.f;
+#pragma unroll 8
+                for (int ch = 0; ch < p.ln_parts; ++ch) {
+                  const float2 v = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + static_cast<long long>(ch) * p.ln_mstat + n);
+                  su += v.x; sq += v.y;
+                }
+                const float mu = su * p.ln_inv_dim;
+                a = mu;
+                b = rsqrtf(fmaxf(sq * p.ln_inv_dim - mu * mu, 0.f) + p.ln_eps);
+              } else {
+                a = __ldg(p.ln_colsum + n);
+                b = p.bias ? __ldg(p.bias + n) : 0.f;
+              }
+            }
+            slnx[i] = a;
+            sbias[i] = b;
+          }
+          epi_bar_sync();
+          sbias_src = key;
+        }
+      } else if (bias_uniform) {
         // consecutive tiles of a CTA usually share the N tile (M is the fast tile index): reload only on change,
         // otherwise the ~0.7 us global-load latency + two barriers sit between every two tiles
         const float* brow = p.bias + (p.bias_bstride ? static_cast<long long>(gp_first / p.rows_per_batch) * p.bias_bstride : 0) + n0;
@@ -383,6 +457,34 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
         if (has_resid && f_first < f_nchunks) load_resid_fast(f_first, rr_first);
       }
 
+      // folded LayerNorm: this thread's row scalars (requested before the accumulator wait)
+      float ln_a0 = 0.f, ln_a1 = 1.f;     // on_cols 0: (mean, rstd) of the row;  on_cols 1: (s[m], c[m]) of the output row
+      if constexpr (kLnIn) {
+        if (row_ok) {
+          if (p.ln_on_cols) {
+            ln_a0 = __ldg(p.ln_colsum + gp);
+            ln_a1 = p.ln_rowbias ? __ldg(p.ln_rowbias + gp) : 0.f;
+          } else {
+            float su = 0.f, sq = 0.f;
+            if (p.ln_parts <= kLnPre) {
+              // the partials of THIS tile's row were requested one tile ago (ln_pre): a tile's own request would sit on the
+              // critical path of every epilogue-bound tile (first version: +75 % on the K = 320 GEMMs)
+#pragma unroll
+              for (int i = 0; i < kLnPre; ++i) { su += ln_pre[i].x; sq += ln_pre[i].y; }
+            } else {
+#pragma unroll 8
+              for (int ch = 0; ch < p.ln_parts; ++ch) {
+                const float2 v = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + static_cast<long long>(ch) * p.ln_mstat + gp);
+                su += v.x; sq += v.y;
+              }
+            }
+            ln_a0 = su * p.ln_inv_dim;
+            ln_a1 = rsqrtf(fmaxf(sq * p.ln_inv_dim - ln_a0 * ln_a0, 0.f) + p.ln_eps);
+          }
+        }
+        // request the next tile's row partials (GEMM view, M-fast order: unit_m already points at the next tile)
+        if (!p.ln_on_cols && p.ln_parts <= kLnPre && t + t_step < num_tiles) ln_prefetch(unit_m * kBlockM + r);
+      }
       VDB_TLE(4, it);   // epilogue: waiting for the accumulator
       if constexpr (CTAS == 2) mbar_wait_wd(&tmem_full[as], aphase, 3); else mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
@@ -430,7 +532,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
           __syncwarp();
         }
       };
-      if constexpr (MODE == 3 || MODE == 4) {
+      if constexpr (kTmaEpi) {
         // ---- TMA-store epilogues (round 2).  Everything stays in the tcgen05.ld layout (one ROW of 32 columns per thread):
         // bias from shared memory (broadcast reads), residual as this row's own 64 contiguous bytes, bf16 pack, four 16-byte
         // shared-memory stores into this warp's 32 x 32 staging tile (64-byte rows, SWIZZLE_64B pattern: conflict-free),
@@ -442,8 +544,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
         uint8_t* stg = reinterpret_cast<uint8_t*>(sstage) + (warp - 2) * 4096;
         const int qrow = quarter * 32;                                   // first tile row of this warp's TMEM lane quarter
         const int ow = wt * p.TW + (qrow % p.TW), oh = ht * p.TH + ((qrow / p.TW) % p.TH), ob = bt * p.TB + qrow / (p.TW * p.TH);
-        constexpr int OUTC = (MODE == 4) ? BN / 2 : BN;                  // output columns per tile
-        const int ochunks = (MODE == 4) ? OUTC / 32 : f_nchunks;
+        constexpr int OUTC = kGegluEpi ? BN / 2 : BN;                    // output columns per tile
+        const int ochunks = kGegluEpi ? OUTC / 32 : f_nchunks;
         const int ocol0 = n_idx * OUTC;
         const int o_first = (((OUTC / 32) % kWPQ) != 0) ? ((half + it) % kWPQ) : half;
         auto load_resid_row = [&](int c, uint4 (&rr)[4]) {
@@ -452,20 +554,64 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
           for (int k = 0; k < 4; ++k) rr[k] = __ldg(src + k);
         };
         uint4 rr[4];
-        const bool do_resid = (MODE == 3) && has_resid && row_ok;
+        float st_su = 0.f, st_sq = 0.f;                                  // mode 7: partial LayerNorm sums of this thread's columns
+        (void)st_su; (void)st_sq;
+        const bool do_resid = (MODE == 3 || MODE == 7) && has_resid && row_ok;
         if (do_resid && o_first < ochunks) load_resid_row(o_first, rr);
 #pragma unroll 1
         for (int c = o_first; c < ochunks; c += kWPQ) {
           float o[32];
-          if constexpr (MODE == 4) {
+          if constexpr (MODE == 6) {
+            // GEGLU over a folded LayerNorm (row statistics only): value and gate both get the rank-1 correction
+            uint32_t va[32], vg[32];
+            tmem_ld32(trow + c * 32, va);
+            tmem_ld32(trow + OUTC + c * 32, vg);
+            tmem_wait_ld();
+            // r * (acc - mu * s) + c  ==  fma(r, acc, fma(-r mu, s, c)); the tables are read as 16-byte broadcasts
+            const float nrm = -ln_a1 * ln_a0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 sa = lds_f4(slnx_s + 4 * (c * 32 + j)), ca = lds_f4(sbias_s + 4 * (c * 32 + j));
+              const float4 sg = lds_f4(slnx_s + 4 * (OUTC + c * 32 + j)), cg = lds_f4(sbias_s + 4 * (OUTC + c * 32 + j));
+              o[j] = fmaf(ln_a1, __uint_as_float(va[j]), fmaf(nrm, sa.x, ca.x)) * gelu_fast_f(fmaf(ln_a1, __uint_as_float(vg[j]), fmaf(nrm, sg.x, cg.x)));
+              o[j + 1] = fmaf(ln_a1, __uint_as_float(va[j + 1]), fmaf(nrm, sa.y, ca.y)) * gelu_fast_f(fmaf(ln_a1, __uint_as_float(vg[j + 1]), fmaf(nrm, sg.y, cg.y)));
+              o[j + 2] = fmaf(ln_a1, __uint_as_float(va[j + 2]), fmaf(nrm, sa.z, ca.z)) * gelu_fast_f(fmaf(ln_a1, __uint_as_float(vg[j + 2]), fmaf(nrm, sg.z, cg.z)));
+              o[j + 3] = fmaf(ln_a1, __uint_as_float(va[j + 3]), fmaf(nrm, sa.w, ca.w)) * gelu_fast_f(fmaf(ln_a1, __uint_as_float(vg[j + 3]), fmaf(nrm, sg.w, cg.w)));
+            }
+          } else if constexpr (MODE == 5) {
+            uint32_t v[32];
+            tmem_ld32(trow + c * 32, v);
+            tmem_wait_ld();
+            if (p.ln_on_cols) {          // out = rstd[n] * (acc - mean[n] * s[m]) + c[m]
+              const float ns = -ln_a0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 mu = lds_f4(slnx_s + 4 * (c * 32 + j)), rs = lds_f4(sbias_s + 4 * (c * 32 + j));
+                o[j] = fmaf(rs.x, fmaf(mu.x, ns, __uint_as_float(v[j])), ln_a1);
+                o[j + 1] = fmaf(rs.y, fmaf(mu.y, ns, __uint_as_float(v[j + 1])), ln_a1);
+                o[j + 2] = fmaf(rs.z, fmaf(mu.z, ns, __uint_as_float(v[j + 2])), ln_a1);
+                o[j + 3] = fmaf(rs.w, fmaf(mu.w, ns, __uint_as_float(v[j + 3])), ln_a1);
+              }
+            } else {                     // out = rstd[m] * (acc - mean[m] * s[n]) + c[n] == fma(r, acc, fma(-r mu, s, c))
+              const float nrm = -ln_a1 * ln_a0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 sx = lds_f4(slnx_s + 4 * (c * 32 + j)), cx = lds_f4(sbias_s + 4 * (c * 32 + j));
+                o[j] = fmaf(ln_a1, __uint_as_float(v[j]), fmaf(nrm, sx.x, cx.x));
+                o[j + 1] = fmaf(ln_a1, __uint_as_float(v[j + 1]), fmaf(nrm, sx.y, cx.y));
+                o[j + 2] = fmaf(ln_a1, __uint_as_float(v[j + 2]), fmaf(nrm, sx.z, cx.z));
+                o[j + 3] = fmaf(ln_a1, __uint_as_float(v[j + 3]), fmaf(nrm, sx.w, cx.w));
+              }
+            }
+          } else if constexpr (MODE == 4) {
             uint32_t va[32], vg[32];
             tmem_ld32(trow + c * 32, va);
             tmem_ld32(trow + OUTC + c * 32, vg);
             tmem_wait_ld();
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 ba = p.bias ? *reinterpret_cast<const float4*>(sbias + c * 32 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-              const float4 bg = p.bias ? *reinterpret_cast<const float4*>(sbias + OUTC + c * 32 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4 ba = p.bias ? lds_f4(sbias_s + 4 * (c * 32 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4 bg = p.bias ? lds_f4(sbias_s + 4 * (OUTC + c * 32 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
               o[j] = (__uint_as_float(va[j]) + ba.x) * gelu_fast_f(__uint_as_float(vg[j]) + bg.x);
               o[j + 1] = (__uint_as_float(va[j + 1]) + ba.y) * gelu_fast_f(__uint_as_float(vg[j + 1]) + bg.y);
               o[j + 2] = (__uint_as_float(va[j + 2]) + ba.z) * gelu_fast_f(__uint_as_float(vg[j + 2]) + bg.z);
@@ -480,7 +626,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
             tmem_wait_ld();
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 bb = p.bias ? *reinterpret_cast<const float4*>(sbias + c * 32 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4 bb = p.bias ? lds_f4(sbias_s + 4 * (c * 32 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
               o[j] = __uint_as_float(v[j]) + bb.x; o[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
               o[j + 2] = __uint_as_float(v[j + 2]) + bb.z; o[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
             }
@@ -501,6 +647,13 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
               }
             }
           }
+          if constexpr (kStatsOut) {
+            // LayerNorm statistics of the rows this GEMM produces: this thread's columns of the tile (fp32, before the rounding)
+            float su = 0.f, sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { su += o[j]; sq = fmaf(o[j], o[j], sq); }
+            st_su += su; st_sq += sq;
+          }
           // the staging tile about to be rewritten was handed to the TMA unit two chunks ago: wait until it has been read
           if (lane == 0) bulk_wait_read<1>();
           __syncwarp();
@@ -520,6 +673,12 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
             bulk_commit();
           }
           st_buf ^= 1;
+        }
+        if constexpr (kStatsOut) {
+          // one partial per (N tile, warp of the lane quarter): the two warps own disjoint chunk sets (o_first = 0 / 1)
+          if (row_ok)
+            reinterpret_cast<float2*>(p.stats_out)[static_cast<long long>(n_idx * kWPQ + o_first) * (static_cast<long long>(p.Bo) * p.Ho * p.Wo) + gp] =
+                make_float2(st_su, st_sq);
         }
       } else if constexpr (MODE == 1) {
         // lean fast path: every chunk is a full 32-column bf16 chunk with one bias row; the residual rows of the
@@ -749,11 +908,17 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int kspl
 // host side
 // ----------------------------------------------------------------------------------------------
 template <int BN, int STAGES, int CTAS, int EW, int MODE>
-static int launch_igemm(const IgemmParams& p, int num_units, cudaStream_t stream) {
-  constexpr size_t smem = STAGES * (kABytes + (BN / CTAS) * kBlockK * 2) + (2 * STAGES + 4) * 8 + 16 + BN * 4 +
-                          EW * 4096 + 1024;
-  static_assert(smem <= 227 * 1024, "igemm shared-memory budget");
+static int launch_igemm(const IgemmParams& p0, int num_units, cudaStream_t stream) {
+  constexpr bool kLn = MODE == 5 || MODE == 6;       // one more [BN] fp32 table (colsum / column mean)
+  constexpr size_t need = STAGES * (kABytes + (BN / CTAS) * kBlockK * 2) + (2 * STAGES + 4) * 8 + 16 + BN * 4 +
+                          (kLn ? BN * 4 : 0) + EW * 4096;
+  // + up to 1024 bytes of slack for the 1024-byte alignment of the operand ring (the LN modes at BN 256 get 912: the dynamic
+  // window starts 1024-aligned on every driver seen so far, and the kernel traps if its carve-up would not fit)
+  constexpr size_t smem = (need + 1024 <= 227 * 1024) ? need + 1024 : 227 * 1024;
+  static_assert(need + 896 <= 227 * 1024, "igemm shared-memory budget");
   constexpr int threads = 64 + 32 * EW;
+  IgemmParams p = p0;
+  p.smem_bytes = static_cast<unsigned>(smem);
   static bool configured = false;
   if (!configured) {
     VDB_CUDA_CHECK(cudaFuncSetAttribute(igemm_kernel<BN, STAGES, CTAS, EW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -799,12 +964,26 @@ struct IgemmEpilogue {
   int out_f32 = 0;
   int act = 0;
   float alpha = 1.f;
+  // folded LayerNorm (see igemm_kernel): consumer side ...
+  const float* ln_stats = nullptr;
+  long long ln_mstat = 0;
+  int ln_parts = 0;
+  int ln_dim = 0;
+  float ln_eps = 0.f;
+  const float* ln_colsum = nullptr;
+  int ln_on_cols = 0;
+  const float* ln_rowbias = nullptr;
+  // ... and producer side
+  float* stats_out = nullptr;
+  int* stats_parts = nullptr;     // host out: partials per row the launch wrote (2 * N tiles)
 };
 
 // Finish IgemmParams (tiling, split-K, B map) and launch.
 static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot, long long ldw,
                      const IgemmEpilogue& e, int bn_forced, int ksplit_forced, void* workspace,
                      size_t ws_bytes, cudaStream_t stream) {
+  const bool ln_in = e.ln_stats != nullptr, st_out = e.stats_out != nullptr;
+  if (ln_in || st_out) ksplit_forced = 1;               // the statistics ride on the single-pass TMA-store epilogues
   int BN = pick_bn(static_cast<int>(N), e.act, bn_forced);
   // Tile-width model (round 2; VDB_BN_MODEL=0 restores the divisibility rule above): the persistent grid runs
   // waves = ceil(tiles / #SMs) rounds of one tile per CTA, a tile costs kb * c(BN) cycles of mainloop (operand fill at ~90 B/clk
@@ -866,12 +1045,16 @@ static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot
   // drop empty trailing splits
   p.ksplit = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.partial = reinterpret_cast<float*>(workspace);
+  p.ln_stats = e.ln_stats; p.ln_mstat = e.ln_mstat; p.ln_parts = e.ln_parts; p.ln_on_cols = e.ln_on_cols;
+  if (e.stats_parts) *e.stats_parts = 2 * p.tilesN;
+  p.ln_inv_dim = e.ln_dim > 0 ? 1.f / static_cast<float>(e.ln_dim) : 0.f; p.ln_eps = e.ln_eps;
+  p.ln_colsum = e.ln_colsum; p.ln_rowbias = e.ln_rowbias; p.stats_out = e.stats_out;
   p.timeline = g_timeline;
   static const int epi_alt = [] { const char* ev = getenv("VDB_EPI_ALT"); return (ev && ev[0] == '0') ? 0 : 1; }();
   p.epi_alt = epi_alt;
   // CTA pairs (cta_group::2) whenever the M tiles pair up and there is no split-K pass
   static const int pair_mode = [] { const char* ev = getenv("VDB_PAIR"); return ev ? atoi(ev) : 0; }();
-  const bool pair = pair_mode != 0 && p.ksplit == 1 && (tilesM % 2) == 0 && BN >= 128;
+  const bool pair = pair_mode != 0 && p.ksplit == 1 && (tilesM % 2) == 0 && BN >= 128 && !ln_in && !st_out;
   // N-fast tile order (VDB_NFAST=1, opt-in until measured): only when every CTA keeps its N tile from one of its tiles to
   // the next (grid % tilesN == 0: the bias tile cached in shared memory stays valid) and A is too big to survive in L2
   // between two M sweeps (FF-out at the 64x64 level re-reads its 84 MB A operand: 170.7 MB of DRAM traffic against
@@ -881,7 +1064,7 @@ static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot
     const int grid = std::min(mn_tiles * p.ksplit, num_sms());
     const double a_bytes = static_cast<double>(M) * static_cast<double>(Ktot) * 2.0;
     p.nfast = (nfast_mode != 0 && !pair && p.ksplit == 1 && p.tilesN > 1 && (grid % p.tilesN) == 0 &&
-               (nfast_mode == 2 || a_bytes > 48e6)) ? 1 : 0;
+               (nfast_mode == 2 || a_bytes > 48e6) && !ln_in) ? 1 : 0;   // (the LN modes prefetch along the M-fast order)
   }
   int rc = make_tmap_2d(&p.tmB, Wt, static_cast<uint64_t>(Ktot), static_cast<uint64_t>(N),
                         static_cast<uint64_t>(ldw) * 2, kBlockK, pair ? BN / 2 : BN);
@@ -911,12 +1094,38 @@ static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot
                           static_cast<uint64_t>(p.Ho) * p.Wo * e.ldo * 2, 32, bw, bh, bb) == 0)
       mode += 2;
   }
+  if (ln_in || st_out) {
+    // folded LayerNorm: only on the TMA-store epilogues (bf16 out, act none / GEGLU, alpha 1, N % 32 == 0, aligned pointers)
+    if (ln_in && st_out) return set_error(VDB_ERR_UNSUPPORTED, "igemm: a launch either consumes or produces LayerNorm statistics");
+    if (mode != 3 && !(mode == 4 && ln_in))
+      return set_error(VDB_ERR_UNSUPPORTED, "igemm: LayerNorm statistics need the TMA-store epilogue (bf16 out, no activation or "
+                                            "GEGLU, alpha 1, N %% 32 == 0, 16-byte aligned out / resid, VDB_EPI_TMA != 0)");
+    if (ln_in && e.resid) return set_error(VDB_ERR_UNSUPPORTED, "igemm: a folded-LayerNorm GEMM takes no residual");
+    if (ln_in && mode == 4 && e.ln_on_cols) return set_error(VDB_ERR_UNSUPPORTED, "igemm: GEGLU with column statistics");
+    mode = st_out ? 7 : mode + 2;
+  }
   if (pair) {
     ++g_pair_launches;
     switch (BN) {
       case 128: rc = launch_igemm<128, 7, 2, 8, 0>(p, num_tiles / 2, stream); break;
       case 160: rc = launch_igemm<160, 7, 2, 8, 0>(p, num_tiles / 2, stream); break;
       default: rc = launch_igemm<256, 6, 2, 8, 0>(p, num_tiles / 2, stream); break;
+    }
+  } else if (mode == 7) {
+    switch (BN) {
+      case 64: rc = launch_igemm<64, 8, 1, 8, 7>(p, num_tiles, stream); break;
+      case 128: rc = launch_igemm<128, 6, 1, 8, 7>(p, num_tiles, stream); break;
+      case 160: rc = launch_igemm<160, 5, 1, 8, 7>(p, num_tiles, stream); break;
+      default: rc = launch_igemm<256, 4, 1, 8, 7>(p, num_tiles, stream); break;
+    }
+  } else if (mode == 6) {
+    rc = launch_igemm<256, 4, 1, 8, 6>(p, num_tiles, stream);
+  } else if (mode == 5) {
+    switch (BN) {
+      case 64: rc = launch_igemm<64, 8, 1, 8, 5>(p, num_tiles, stream); break;
+      case 128: rc = launch_igemm<128, 6, 1, 8, 5>(p, num_tiles, stream); break;
+      case 160: rc = launch_igemm<160, 5, 1, 8, 5>(p, num_tiles, stream); break;
+      default: rc = launch_igemm<256, 4, 1, 8, 5>(p, num_tiles, stream); break;
     }
   } else if (mode == 4) {
     rc = launch_igemm<256, 4, 1, 8, 4>(p, num_tiles, stream);
@@ -1022,6 +1231,39 @@ int vdb_gemm_bf16(const void* A, long long M, long long K, long long lda, const 
   e.resid = resid; e.ldr = ldr; e.out = out; e.ldo = ldo; e.out_f32 = out_f32; e.act = act; e.alpha = alpha;
   return run_igemm(p, W, N, K + (A2 ? K2 : 0), ldw, e, bn, ksplit, workspace, ws_bytes,
                    reinterpret_cast<cudaStream_t>(stream));
+}
+
+// GEMM with a LayerNorm folded in (consumer) or LayerNorm statistics written out (producer); see include/vdb200.h
+int vdb_gemm_ln_bf16(const void* A, long long M, long long K, long long lda, const void* W, long long N, long long ldw,
+                     const float* bias, const void* resid, long long ldr, void* out, long long ldo, int act,
+                     const float* ln_stats, long long ln_rows, int ln_parts, int ln_dim, float ln_eps, const float* ln_colsum,
+                     int ln_on_cols, const float* ln_rowbias, float* stats_out, int* stats_parts, int bn, void* stream) {
+  if (!A || !W || !out || M <= 0 || N <= 0 || K <= 0) return set_error(VDB_ERR_INVALID, "gemm_ln: null/empty argument");
+  if ((K % 8) || (lda % 8) || (ldw % 8)) return set_error(VDB_ERR_INVALID, "gemm_ln: K, lda, ldw must be multiples of 8");
+  if (M > 0x7fffffffLL || N > 0x7fffffffLL) return set_error(VDB_ERR_INVALID, "gemm_ln: dimension too large");
+  if (!ln_stats && !stats_out) return set_error(VDB_ERR_INVALID, "gemm_ln: neither ln_stats nor stats_out given (use vdb_gemm_bf16)");
+  if (ln_stats) {
+    if (!ln_colsum || ln_dim <= 0 || ln_dim != K || ln_parts <= 0)
+      return set_error(VDB_ERR_INVALID, "gemm_ln: need ln_colsum, ln_parts > 0 and ln_dim == K");
+    if (ln_rows < (ln_on_cols ? N : M)) return set_error(VDB_ERR_INVALID, "gemm_ln: statistics table has too few rows");
+  }
+  if (stats_out && ((N % 32) || !stats_parts)) return set_error(VDB_ERR_INVALID, "gemm_ln: stats_out needs N %% 32 == 0 and stats_parts");
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.Wo = static_cast<int>(M); p.Ho = 1; p.Bo = 1;
+  p.TW = kBlockM; p.TH = 1; p.TB = 1;
+  p.tilesW = static_cast<int>((M + kBlockM - 1) / kBlockM); p.tilesH = 1; p.tilesB = 1;
+  int rc = make_tmap_4d(&p.tmA[0], A, K, M, 1, 1, lda * 2, lda * 2 * M, lda * 2 * M, kBlockK, p.TW, 1, 1);
+  if (rc) return rc;
+  p.seg[0] = ASeg{0, 0, 0, static_cast<int16_t>((K + kBlockK - 1) / kBlockK), 0};
+  p.nseg = 1;
+  p.kb_total = p.seg[0].nkb;
+  for (int i = p.nseg; i < kMaxA; ++i) p.tmA[i] = p.tmA[0];
+  IgemmEpilogue e;
+  e.bias = bias; e.resid = resid; e.ldr = ldr; e.out = out; e.ldo = ldo; e.act = act;
+  e.ln_stats = ln_stats; e.ln_mstat = ln_rows; e.ln_parts = ln_parts; e.ln_dim = ln_dim; e.ln_eps = ln_eps; e.ln_colsum = ln_colsum;
+  e.ln_on_cols = ln_on_cols; e.ln_rowbias = ln_rowbias; e.stats_out = stats_out; e.stats_parts = stats_parts;
+  return run_igemm(p, W, N, K, ldw, e, bn, 1, nullptr, 0, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // 3x3 convolution on NHWC bf16 as implicit GEMM.

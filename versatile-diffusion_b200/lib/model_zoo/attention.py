@@ -6,7 +6,12 @@ Kernel schedule of one SpatialTransformer (x: [B,H,W,C] bf16):
   GN32(eps 1e-6) -> proj_in GEMM -> [LN -> fused q|k GEMM + V^T GEMM -> flash attention -> to_out GEMM(+resid)]
   -> [LN -> q GEMM (K, V^T of the context cached across DDIM steps) -> flash attention -> to_out GEMM(+resid)]
   -> LN -> GEGLU GEMM -> FF-out GEMM(+resid) -> proj_out GEMM (+ x_in, * mixing ratio)
+The three LayerNorms are not kernels (round 2, VDB_LN_FOLD=0 restores them): gamma is folded into the weights of the GEMMs that
+consume the normalised tokens, mean / rstd arrive as per-32-channel partial sums written by the epilogue of the GEMM that PRODUCED
+the tokens (proj_in, the two to_out), and the consumer applies r * (x W'^T - mu * s) + c in its own epilogue (vdb_gemm_ln_bf16).
 """
+import os
+
 import torch
 from torch import nn
 
@@ -25,6 +30,23 @@ class PaddedContext(object):
 
     def __init__(self, data, length):
         self.data, self.length = data, length
+
+
+def ln_fold_enabled():
+    """LayerNorm folded into the neighbouring GEMMs (default on; VDB_LN_FOLD=0: LayerNorm kernels).  Needs the TMA-store
+    epilogues (VDB_EPI_TMA != 0)."""
+    return os.environ.get("VDB_LN_FOLD", "1") != "0" and os.environ.get("VDB_EPI_TMA", "1") != "0"
+
+
+def fold_layernorm(w, b, gamma, beta):
+    """Linear(LayerNorm(x)) = r * (x W'^T - mu * s) + c  ->  (W' bf16 [N,K], s fp32 [N], c fp32 [N])  (include/vdb200.h)."""
+    wf = w.detach().float()
+    wg = (wf * gamma.detach().float()[None, :]).to(torch.bfloat16).contiguous()
+    s = wg.float().sum(1).contiguous()                      # of the ROUNDED weights: what the tensor core multiplies mu with
+    c = wf @ beta.detach().float()
+    if b is not None:
+        c = c + b.detach().float()
+    return wg, s, c.contiguous()
 
 
 def Normalize(in_channels):
@@ -47,7 +69,7 @@ class GEGLU(PackedModule):
         for t in range(n2 // half):
             idx += list(range(t * half, (t + 1) * half)) + list(range(n2 + t * half, n2 + (t + 1) * half))
         idx = torch.tensor(idx, device=w.device)
-        return {"w": bf16(w.detach()[idx]), "b": f32(b.detach()[idx]), "act": ops.ACT_GEGLU}
+        return {"w": bf16(w.detach()[idx]), "b": f32(b.detach()[idx]), "act": ops.ACT_GEGLU, "idx": idx}
 
     def forward(self, x):  # x: [rows, C] bf16
         p = self.packed()
@@ -85,6 +107,26 @@ class CrossAttention(PackedModule):
         out = torch.zeros(h, dpad, w.shape[1], dtype=torch.bfloat16, device=w.device)
         out[:, :d] = w.detach().view(h, d, -1).to(torch.bfloat16)
         return out.view(h * dpad, -1).contiguous()
+
+    def _pad_head_vec(self, v, dpad):
+        h, d = self.heads, self.dim_head
+        out = torch.zeros(h, dpad, dtype=torch.float32, device=v.device)
+        out[:, :d] = v.view(h, d)
+        return out.view(-1).contiguous()
+
+    def pack_folded(self, gamma, beta):
+        """the projections that read LayerNorm(x), with that LayerNorm folded in (fold_layernorm), heads padded as in _pack"""
+        dk, dv = _ops().attention_pads(self.dim_head)
+        wq, sq, cq = fold_layernorm(self.to_q.weight, None, gamma, beta)
+        out = {"wq": self._pad_heads(wq, dk), "sq": self._pad_head_vec(sq, dk), "cq": self._pad_head_vec(cq, dk)}
+        if self.is_self:
+            wk, sk, ck = fold_layernorm(self.to_k.weight, None, gamma, beta)
+            wv, sv, cv = fold_layernorm(self.to_v.weight, None, gamma, beta)
+            out.update({"wqk": torch.cat([out["wq"], self._pad_heads(wk, dk)], 0).contiguous(),
+                        "sqk": torch.cat([out["sq"], self._pad_head_vec(sk, dk)]).contiguous(),
+                        "cqk": torch.cat([out["cq"], self._pad_head_vec(ck, dk)]).contiguous(),
+                        "wv": self._pad_heads(wv, dv), "sv": self._pad_head_vec(sv, dv), "cv": self._pad_head_vec(cv, dv)})
+        return out
 
     def _pack(self):
         dk, dv = _ops().attention_pads(self.dim_head)
@@ -175,6 +217,26 @@ class CrossAttention(PackedModule):
             ops.attention(q, k, vt, o, B, H, N, L, d, scale=self.scale, kv_bstride=Lp)
         return ops.gemm(o, p["wo"], bias=p["bo"], resid=resid)
 
+    def forward_folded(self, x, ln, fp, context=None, resid=None, B=1, stats_out=None):
+        """x: [B*N, C] bf16 RAW tokens, ln: ops.LnFold with their LayerNorm statistics, fp: pack_folded(); to_out writes the
+        statistics of ITS output rows into stats_out (the next LayerNorm's input).  Self-attention needs N % 8 == 0."""
+        ops = _ops()
+        p = self.packed()
+        H, d, dk = self.heads, self.dim_head, p["dk"]
+        N = x.shape[0] // B
+        o = torch.empty(x.shape[0], H * d, dtype=torch.bfloat16, device=x.device)
+        if context is None:
+            qk = ops.gemm_ln(x, fp["wqk"], bias=fp["cqk"], ln=ln, colsum=fp["sqk"])                       # [B*N, 2*H*dk]: q | k
+            vt = ops.gemm_ln(fp["wv"], x, ln=ln, colsum=fp["sv"], on_cols=True, rowbias=fp["cv"])       # [H*dvp, B*N]
+            ops.attention(qk, qk, vt, o, B, H, N, N, d, scale=self.scale, q_col0=0, k_col0=H * dk)
+        else:
+            q = ops.gemm_ln(x, fp["wq"], bias=fp["cq"], ln=ln, colsum=fp["sq"])
+            k, vt, L, Lp = self.context_kv(context)
+            ops.attention(q, k, vt, o, B, H, N, L, d, scale=self.scale, kv_bstride=Lp)
+        if stats_out is None:
+            return ops.gemm(o, p["wo"], bias=p["bo"], resid=resid)
+        return ops.gemm_ln(o, p["wo"], bias=p["bo"], resid=resid, stats_out=stats_out)      # -> (tokens, partials per row)
+
 
 class BasicTransformerBlock(PackedModule):
     def __init__(self, dim, n_heads, d_head, dropout=0., context_dim=None, gated_ff=True, checkpoint=True,
@@ -192,13 +254,31 @@ class BasicTransformerBlock(PackedModule):
         self.checkpoint = checkpoint
 
     def _pack(self):
-        return {n: (f32(getattr(self, n).weight), f32(getattr(self, n).bias)) for n in ("norm1", "norm2", "norm3")} | \
+        out = {n: (f32(getattr(self, n).weight), f32(getattr(self, n).bias)) for n in ("norm1", "norm2", "norm3")} | \
             {"w2": bf16(self.ff.net[2].weight), "b2": f32(self.ff.net[2].bias)}
+        if ln_fold_enabled() and self.norm1.weight.shape[0] % 32 == 0:
+            g = self.ff.net[0]
+            idx = g.packed()["idx"]                          # GEGLU row order (value / gate halves per 256-column tile)
+            wf, sf, cf = fold_layernorm(g.proj.weight, g.proj.bias, self.norm3.weight, self.norm3.bias)
+            out["fold"] = {"a1": self.attn1.pack_folded(self.norm1.weight, self.norm1.bias),
+                           "a2": self.attn2.pack_folded(self.norm2.weight, self.norm2.bias),
+                           "ffw": wf[idx].contiguous(), "ffs": sf[idx].contiguous(), "ffc": cf[idx].contiguous()}
+        return out
 
-    def forward(self, x, context=None, B=1):
-        """x: [B*N, C] bf16 tokens (reference _forward, attention.py:214-218)."""
+    def forward(self, x, context=None, B=1, stats=None):
+        """x: [B*N, C] bf16 tokens (reference _forward, attention.py:214-218).  stats: (table, partials per row) — the LayerNorm
+        partial sums of x's rows written by the GEMM that produced x -> the three LayerNorms run inside the GEMM epilogues."""
         ops = _ops()
         p = self.packed()
+        C = x.shape[1]
+        if stats is not None and "fold" in p and (x.shape[0] // B) % 8 == 0 and x.shape[0] % 32 == 0:
+            f = p["fold"]
+            st1, parts1 = stats
+            st2, st3 = ops.ln_stats_buffer(x.shape[0], C, x.device), ops.ln_stats_buffer(x.shape[0], C, x.device)
+            x, parts2 = self.attn1.forward_folded(x, ops.LnFold(st1, parts1, C, self.norm1.eps), f["a1"], None, resid=x, B=B, stats_out=st2)
+            x, parts3 = self.attn2.forward_folded(x, ops.LnFold(st2, parts2, C, self.norm2.eps), f["a2"], context, resid=x, B=B, stats_out=st3)
+            h = ops.gemm_ln(x, f["ffw"], bias=f["ffc"], act=ops.ACT_GEGLU, ln=ops.LnFold(st3, parts3, C, self.norm3.eps), colsum=f["ffs"])
+            return ops.gemm(h, p["w2"], bias=p["b2"], resid=x)
         x = self.attn1(ops.layernorm(x, *p["norm1"], eps=self.norm1.eps), None, resid=x, B=B)
         x = self.attn2(ops.layernorm(x, *p["norm2"], eps=self.norm2.eps), context, resid=x, B=B)
         h = self.ff.net[0](ops.layernorm(x, *p["norm3"], eps=self.norm3.eps))
@@ -230,9 +310,17 @@ class SpatialTransformer(PackedModule):
         p = self.packed()
         B, H, W, C = x.shape
         xn = ops.groupnorm(x, p["g"], p["b"], self.norm.eps)
-        t = ops.gemm(xn.view(B * H * W, C), p["win"], bias=p["bin"])
-        for blk in self.transformer_blocks:
-            t = blk(t, context, B=B)
+        inner = p["win"].shape[0]
+        if ln_fold_enabled() and inner % 32 == 0 and (H * W) % 8 == 0 and (B * H * W) % 32 == 0:   # (tokens are the N of V^T)
+            # proj_in also writes the LayerNorm statistics of its output rows: norm1 of the first block runs inside attn1's GEMMs
+            st = ops.ln_stats_buffer(B * H * W, inner, x.device)
+            t, parts = ops.gemm_ln(xn.view(B * H * W, C), p["win"], bias=p["bin"], stats_out=st)
+            stats = (st, parts)
+        else:
+            stats = None
+            t = ops.gemm(xn.view(B * H * W, C), p["win"], bias=p["bin"])
+        for i, blk in enumerate(self.transformer_blocks):
+            t = blk(t, context, B=B, stats=stats if i == 0 else None)
         base = x if acc is None else acc
         out = ops.gemm(t, p["wout"], bias=p["bout"], resid=base.view(B * H * W, -1), alpha=float(ratio))
         return out.view(B, H, W, -1)

@@ -4,6 +4,7 @@ torch is used here for device memory, streams and allocation only; every arithme
 path is a kernel of libvdb200.so.  All functions enqueue on torch's current CUDA stream and are
 CUDA-graph capturable (no host syncs, scratch comes from the caller or torch's caching allocator).
 """
+import ctypes
 import math
 
 import torch
@@ -233,6 +234,55 @@ def gemm(a, w, bias=None, resid=None, out=None, act=ACT_NONE, a2=None, out_dtype
     if _RECORD is not None:
         _RECORD.append((lib.vdb_gemm_bf16, cargs, (a, a2, w, bias, resid, out, ws), 2.0 * M * N * (K + K2)))
     return out
+
+
+class LnFold(object):
+    """What a GEMM needs to consume a LayerNorm it never sees (vdb_gemm_ln_bf16): the producer's partial sums `stats`
+    [>= parts, rows, 2] fp32 (`parts` of them valid), the LayerNorm's width and epsilon; the weights' column sums ride with the
+    packed weights."""
+
+    def __init__(self, stats, parts, dim, eps):
+        self.stats, self.parts, self.dim, self.eps = stats, int(parts), int(dim), float(eps)
+
+
+def ln_stats_buffer(rows, width, device):
+    """statistics table a producer GEMM with N = width columns fills for its `rows` output rows (worst case: 64-column tiles)"""
+    assert width % 32 == 0
+    return torch.empty((2 * ((width + 63) // 64), rows, 2), dtype=torch.float32, device=device)
+
+
+def gemm_ln(a, w, bias=None, resid=None, out=None, act=ACT_NONE, ln=None, colsum=None, on_cols=False, rowbias=None,
+            stats_out=None, bn=0):
+    """vdb_gemm_ln_bf16: consumer (ln = LnFold, colsum) or producer (stats_out; returns (out, parts)) of folded-LayerNorm
+    statistics."""
+    _need(a, BF16, "a", True); _need(w, BF16, "w", True); _need(bias, torch.float32, "bias"); _need(resid, BF16, "resid", True)
+    _need(colsum, torch.float32, "colsum"); _need(rowbias, torch.float32, "rowbias"); _need(stats_out, torch.float32, "stats_out")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K, (w.shape, K)
+    n_out = N // 2 if act == ACT_GEGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=BF16, device=a.device)
+    _need(out, BF16, "out", True)
+    st = None
+    if ln is not None:
+        st = ln.stats
+        _need(st, torch.float32, "ln.stats")
+        assert st.dim() == 3 and st.shape[0] >= ln.parts and st.shape[2] == 2, (tuple(st.shape), ln.parts)
+    parts = ctypes.c_int(0)
+    if stats_out is not None:
+        assert stats_out.dim() == 3 and stats_out.shape[0] >= 2 * ((N + 63) // 64) and stats_out.shape[1] == M and stats_out.shape[2] == 2, \
+            (tuple(stats_out.shape), N, M)
+    cargs = (_ptr(a), M, K, a.stride(0), _ptr(w), N, w.stride(0), _ptr(bias), _ptr(resid),
+             resid.stride(0) if resid is not None else 0, _ptr(out), out.stride(0), int(act),
+             _ptr(st), st.shape[1] if st is not None else 0, ln.parts if ln is not None else 0, ln.dim if ln is not None else 0,
+             ln.eps if ln is not None else 0.0, _ptr(colsum), 1 if on_cols else 0, _ptr(rowbias), _ptr(stats_out),
+             ctypes.addressof(parts) if stats_out is not None else None, int(bn))
+    with _Span("gemm", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * n_out)):
+        check(lib.vdb_gemm_ln_bf16(*cargs, _stream()), "gemm_ln_bf16")
+    if _RECORD is not None:
+        _RECORD.append((lib.vdb_gemm_ln_bf16, cargs, (a, w, bias, resid, out, st, colsum, rowbias, stats_out, parts), 2.0 * M * N * K))
+    return (out, parts.value) if stats_out is not None else out
 
 
 def conv3x3(x, w, bias=None, resid=None, out=None, mode=0, skip1=None, skip2=None, act=ACT_NONE,
