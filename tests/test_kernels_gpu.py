@@ -6,6 +6,8 @@ fp32 elementwise kernels bit-exact or <= 1e-6 relative as stated per test.
 """
 import math
 
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -140,6 +142,21 @@ def test_gemm_geglu(M, C):
 
 
 # ---- LayerNorm folded into the GEMMs (vdb_gemm_ln_bf16) ------------------------------------------------------------------
+# (rides on the TMA-store epilogues: under the opt-in variants that switch them off the entry point refuses, which
+# test_gemm_ln_needs_the_tma_store_epilogue pins)
+_NO_TMA_EPI = os.environ.get("VDB_EPI_TMA") == "0" or os.environ.get("VDB_IGEMM_SPEC") == "0"
+needs_tma_epi = pytest.mark.skipif(_NO_TMA_EPI, reason="vdb_gemm_ln_bf16 needs the TMA-store epilogue")
+
+
+@pytest.mark.skipif(not _NO_TMA_EPI, reason="only meaningful with VDB_EPI_TMA=0 / VDB_IGEMM_SPEC=0")
+def test_gemm_ln_needs_the_tma_store_epilogue():
+    from vdb200._lib import VdbError
+    ops = _ops()
+    a, w = rnd(256, 320, seed=1), rnd(320, 320, seed=2)
+    with pytest.raises(VdbError):
+        ops.gemm_ln(a, w, stats_out=ops.ln_stats_buffer(256, 320, a.device))
+
+
 def _chunk_stats(x, width=32):
     """[M, C] fp32 -> [C/width, M, 2] partial (sum, sum of squares) over column ranges: the kind of table a producer GEMM writes"""
     M, C = x.shape
@@ -158,6 +175,7 @@ def _fold(w, b, gamma, beta):
     return wg, wg.float().sum(1).contiguous(), c.contiguous()
 
 
+@needs_tma_epi
 @pytest.mark.parametrize("M,N,K,resid,bn", [(1024, 320, 320, True, 0), (520, 640, 1280, True, 0), (4096, 320, 320, False, 160),
                                             (300, 1280, 512, True, 64)])
 def test_gemm_ln_producer_writes_chunk_statistics(M, N, K, resid, bn):
@@ -177,6 +195,7 @@ def test_gemm_ln_producer_writes_chunk_statistics(M, N, K, resid, bn):
     assert err <= 2e-3 * ref_tot.abs().max().item() + 1e-3, f"row statistics off by {err}"
 
 
+@needs_tma_epi
 @pytest.mark.parametrize("M,N,C,bias,mean", [(1024, 1024, 320, False, 0.0), (2048, 512, 640, True, 1.5), (384, 2048, 1280, True, -0.7),
                                              (100, 320, 320, True, 4.0)])
 def test_gemm_ln_consumer_rows(M, N, C, bias, mean):
@@ -193,6 +212,7 @@ def test_gemm_ln_consumer_rows(M, N, C, bias, mean):
     assert_close(out, ref, what=f"gemm_ln rows {M}x{N}x{C} mean {mean}")
 
 
+@needs_tma_epi
 @pytest.mark.parametrize("T,R,C", [(4096, 384, 320), (992, 384, 640), (256, 640, 1280)])
 def test_gemm_ln_consumer_columns(T, R, C):
     """the transposed projection: out^T [R, T] = W0 LayerNorm(x)^T, statistics per output COLUMN (token)"""
@@ -208,6 +228,7 @@ def test_gemm_ln_consumer_columns(T, R, C):
     assert_close(out, ref, what=f"gemm_ln columns {R}x{T}x{C}")
 
 
+@needs_tma_epi
 @pytest.mark.parametrize("M,C", [(512, 320), (1024, 640)])
 def test_gemm_ln_consumer_geglu(M, C):
     ops = _ops()
@@ -226,6 +247,7 @@ def test_gemm_ln_consumer_geglu(M, C):
     assert_close(out, val * F.gelu(gate), what="gemm_ln geglu")
 
 
+@needs_tma_epi
 def test_gemm_ln_rejects_what_the_tma_store_epilogue_cannot_do():
     from vdb200._lib import VdbError
     ops = _ops()
@@ -237,6 +259,7 @@ def test_gemm_ln_rejects_what_the_tma_store_epilogue_cannot_do():
         ops.gemm_ln(x, w)
 
 
+@needs_tma_epi
 def test_gemm_ln_producer_feeds_consumer():
     """the real chain: producer GEMM (+resid) writes the statistics of ITS bf16 output rows, the consumer normalises with them"""
     ops = _ops()

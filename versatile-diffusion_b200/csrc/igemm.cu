@@ -265,8 +265,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
     // ------------------------------ MMA issuer ------------------------------
     // single CTAs: the WHOLE warp runs the issue loop and one elected lane issues each tcgen05 instruction (convergent control
     // flow keeps the descriptors in uniform registers; under `if (lane == 0)` every MMA sat in an ELECT / R2UR / BRA.U.ANY
-    // loop of ~90 cycles, more than the 32-80 tensor cycles of a BN <= 160 MMA).  CTA pairs keep the single-thread form.
-    if ((CTAS == 1) || (lane == 0 && cta_rank == 0)) {
+    // loop of ~90 cycles, more than the 32-80 tensor cycles of a BN <= 160 MMA).  CTA pairs: the same, in rank 0's warp.
+    if ((CTAS == 1) || (cta_rank == 0)) {
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM * CTAS, BN);
       uint32_t stage = 0, phase = 0;
       int it = 0;
@@ -289,13 +289,13 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
-            if constexpr (CTAS == 2) umma_bf16_ss_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            if constexpr (CTAS == 2) umma_bf16_ss_pair_w(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
             else umma_bf16_ss_w(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
-          if constexpr (CTAS == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit_w(&empty_bar[stage]);
+          if constexpr (CTAS == 2) umma_commit_pair_w(&empty_bar[stage]); else umma_commit_w(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if constexpr (CTAS == 2) umma_commit_pair(&tmem_full[as]); else umma_commit_w(&tmem_full[as]);
+        if constexpr (CTAS == 2) umma_commit_pair_w(&tmem_full[as]); else umma_commit_w(&tmem_full[as]);
         VDB_TL(3, it);                             // MMA: all MMAs of the tile issued
       }
     }
@@ -1054,7 +1054,7 @@ static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot
   p.epi_alt = epi_alt;
   // CTA pairs (cta_group::2) whenever the M tiles pair up and there is no split-K pass
   static const int pair_mode = [] { const char* ev = getenv("VDB_PAIR"); return ev ? atoi(ev) : 0; }();
-  const bool pair = pair_mode != 0 && p.ksplit == 1 && (tilesM % 2) == 0 && BN >= 128 && !ln_in && !st_out;
+  const bool pair = pair_mode != 0 && p.ksplit == 1 && (tilesM % 2) == 0 && BN >= 128 && !ln_in && !st_out && e.act != ACT_GEGLU;
   // N-fast tile order (VDB_NFAST=1, opt-in until measured): only when every CTA keeps its N tile from one of its tiles to
   // the next (grid % tilesN == 0: the bias tile cached in shared memory stays valid) and A is too big to survive in L2
   // between two M sweeps (FF-out at the 64x64 level re-reads its 84 MB A operand: 170.7 MB of DRAM traffic against
@@ -1077,7 +1077,7 @@ static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot
   const bool one_bias_row = e.bias == nullptr || e.bias_bstride == 0 ||
                             (p.TB == 1 && (static_cast<long long>(p.Ho) * p.Wo == p.rows_per_batch ||
                                            (p.Ho == 1 && p.Bo == 1 && p.rows_per_batch % kBlockM == 0)));
-  if (spec && !pair && p.ksplit == 1 && !e.out_f32 && one_bias_row) {
+  if (spec && p.ksplit == 1 && !e.out_f32 && one_bias_row) {
     if (e.act == ACT_GEGLU && BN == 256) mode = 2;
     else if (e.act == ACT_NONE && e.alpha == 1.f && (N % 32) == 0) mode = 1;
   }
@@ -1104,7 +1104,14 @@ static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot
     if (ln_in && mode == 4 && e.ln_on_cols) return set_error(VDB_ERR_UNSUPPORTED, "igemm: GEGLU with column statistics");
     mode = st_out ? 7 : mode + 2;
   }
-  if (pair) {
+  if (pair && mode == 3) {
+    ++g_pair_launches;                 // CTA pairs with the TMA-store epilogue (each CTA stores its own 128 rows)
+    switch (BN) {
+      case 128: rc = launch_igemm<128, 7, 2, 8, 3>(p, num_tiles / 2, stream); break;
+      case 160: rc = launch_igemm<160, 7, 2, 8, 3>(p, num_tiles / 2, stream); break;
+      default: rc = launch_igemm<256, 6, 2, 8, 3>(p, num_tiles / 2, stream); break;
+    }
+  } else if (pair) {
     ++g_pair_launches;
     switch (BN) {
       case 128: rc = launch_igemm<128, 7, 2, 8, 0>(p, num_tiles / 2, stream); break;

@@ -35,7 +35,8 @@ class PaddedContext(object):
 def ln_fold_enabled():
     """LayerNorm folded into the neighbouring GEMMs (default on; VDB_LN_FOLD=0: LayerNorm kernels).  Needs the TMA-store
     epilogues (VDB_EPI_TMA != 0)."""
-    return os.environ.get("VDB_LN_FOLD", "1") != "0" and os.environ.get("VDB_EPI_TMA", "1") != "0"
+    return os.environ.get("VDB_LN_FOLD", "1") != "0" and os.environ.get("VDB_EPI_TMA", "1") != "0" and \
+        os.environ.get("VDB_IGEMM_SPEC", "1") != "0"
 
 
 def fold_layernorm(w, b, gamma, beta):
