@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "host_util.h"
 #include <cstdlib>
+#include <type_traits>
 
 namespace vdb {
 
@@ -234,14 +235,17 @@ attention_kernel(const __grid_constant__ AttnParams p) {
     float l_sum = 0.f;        // this thread's share of the row sum
     const bool tl_warp = (warp == 2) && (lane == 0);   // (debug timeline)
     (void)tl_warp;
-    for (int j = 0; j < ntiles; ++j) {
+    // One kv tile.  MASKED = this tile needs the validity test (columns past Nk, or the causal mask): the per-element compare /
+    // select pairs of the mask were if-converted into EVERY tile's instruction stream (329 of 895 SASS instructions per tile in the
+    // d_head 80 kernel) until the masked tile became its own instantiation of the body.
+    auto tile_body = [&](const int j, auto masked_tag) {
+      constexpr bool need_mask = decltype(masked_tag)::value;
       VDB_ATL(0, j, tl_warp);
       mbar_wait(&s_full[j % SB], (j / SB) & 1);
       tc_fence_after();
       VDB_ATL(1, j, tl_warp);
       const uint32_t ts = tmem_S + (j % SB) * BKV + lane_off;
       const int kv0 = j * kBKV;
-      const bool need_mask = (kv0 + kBKV > p.Nk) || p.causal;
       const int kv_lim = p.causal ? min(p.Nk, q_idx + 1) : p.Nk;  // valid kv indices are < kv_lim
       // pass 1: row max over this warp's columns.  With SW == 2 a thread owns only 64 columns, so the scores stay in
       // registers for pass 2 and S is read from TMEM once per tile instead of twice.
@@ -401,6 +405,11 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[j % PF]);
       VDB_ATL(6, j, tl_warp);
+    };
+#pragma unroll 1
+    for (int j = 0; j < ntiles; ++j) {
+      if ((j * kBKV + kBKV > p.Nk) || p.causal) tile_body(j, std::true_type{});
+      else tile_body(j, std::false_type{});
     }
     // epilogue: O / l -> bf16
     if (SW == 2) {
@@ -686,7 +695,11 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
     const uint32_t prow = smem_u32(sP + g * kPBytes + r * 128);   // 32-bit shared address: STS, no generic address math
     const bool tlw = (quarter == 0) && (lane == 0);   // (debug timeline: first warp of each group)
     (void)tlw;
-    for (int j = 0; j < ntiles; ++j) {
+    // One kv tile of this row.  MASKED = the tile holds columns past Nk (only ever the LAST tile): the 128 compare / select
+    // pairs of the tail mask were if-converted into EVERY tile's instruction stream (384 of 1026 SASS instructions per tile,
+    // profiles/r02_sass_attention_loop.txt) until the masked tile became its own instantiation of the body.
+    auto tile_body = [&](const int j, auto masked_tag) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
       VDB_FTL(8 * g + 7, j, tlw);
       mbar_wait(&s_full[g], j & 1);
       tc_fence_after();
@@ -707,11 +720,10 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
       if (lane == 0) mbar_arrive(&s_free[g]);     // the MMA warp may overwrite S with the next tile's scores
       VDB_FTL(8 * g + 1, j, tlw);
       const int kv0 = j * BKV;
-      const bool need_mask = kv0 + BKV > p.Nk;
       float mx;
       {
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-        if (need_mask) {
+        if constexpr (MASKED) {
 #pragma unroll
           for (int i = 0; i < BKV; ++i)
             if (kv0 + i >= p.Nk) keep[i] = 0xff800000u;   // -inf: contributes exp2 = 0 and never wins the max
@@ -811,6 +823,13 @@ __global__ void __launch_bounds__(384, 1) attention_fa_kernel(const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[g]);
       VDB_FTL(8 * g + 6, j, tlw);
+    };
+    {
+      const bool tail = (p.Nk % BKV) != 0;
+      const int nfull = tail ? ntiles - 1 : ntiles;
+#pragma unroll 1
+      for (int j = 0; j < nfull; ++j) tile_body(j, std::false_type{});
+      if (tail) tile_body(ntiles - 1, std::true_type{});
     }
     mbar_wait(&pv_done[g], (ntiles - 1) & 1);
     tc_fence_after();
