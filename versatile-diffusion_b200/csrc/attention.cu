@@ -176,6 +176,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
     {   // whole warp, one elected lane per tcgen05 instruction (see umma_bf16_ss_w)
       constexpr uint32_t idesc_s = make_idesc_bf16(kBQ, kBKV);
       constexpr uint32_t idesc_o = make_idesc_bf16(kBQ, DVP);
+      const int ksteps = (p.dv + 15) / 16;   // K16 steps of QK^T that can hold non-zero channels
       auto issue_S = [&](int j) {
         const int st = j % KV_STAGES;
         mbar_wait(&k_full[st], (j / KV_STAGES) & 1);
@@ -186,7 +187,9 @@ attention_kernel(const __grid_constant__ AttnParams p) {
           const uint64_t qd = make_desc_sw128(smem_u32(sQ + a * kBQ * 128));
           const uint64_t kd = make_desc_sw128(smem_u32(sK + st * kKBytes + a * kBKV * 128));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_ss_w(d, qd + 2 * k, kd + 2 * k, idesc_s, (a > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            if (a * 4 + k < ksteps)      // the K16 steps past d_head multiply zero padding (d 80 in DK 128: 5 of 8 steps, d 40: 3 of 4)
+              umma_bf16_ss_w(d, qd + 2 * k, kd + 2 * k, idesc_s, (a > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit_w(&k_empty[st]);
         umma_commit_w(&s_full[j % SB]);
