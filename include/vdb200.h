@@ -85,6 +85,17 @@ int vdb_gemm_ln_bf16(const void* A, long long M, long long K, long long lda, con
                      const float* ln_stats, long long ln_rows, int ln_parts, int ln_dim, float ln_eps, const float* ln_colsum,
                      int ln_on_cols, const float* ln_rowbias, float* stats_out, int* stats_parts, int bn, void* stream);
 
+/* ---- skinny GEMM on the CUDA cores for a small operand of <= 64 rows — the 0-D diffuser's Linear_MultiDim / FCBlock_MultiDim GEMMs
+ *      (openaimodel.py:2084-2141, 2275-2354; M = batch rows) and the 32-row projections of its context blocks --------------------
+ * small = [S, K1 (+K2)] bf16 rows (two sources concatenated along K, small2 may be NULL), big = [R, K1+K2] bf16 rows, fp32 accumulate.
+ * transpose_out 0:  out[s, r] = small[s] . big[r] + bias[s * bias_bstride + r] + resid[s, r]     (activations x weights^T)
+ * transpose_out 1:  out[r, s] = small[s] . big[r]                                               (no bias / residual: V^T projection)
+ * The small operand must fit shared memory: vdb_gemm_skinny_fits(S, K) != 0 (S padded to 8 / 16 / 32 / 64 rows x K x 2 B <= 200 KB). */
+int vdb_gemm_skinny_fits(int S, long long K);
+int vdb_gemm_skinny_bf16(const void* small1, int S, long long K1, long long lds1, const void* small2, long long K2, long long lds2,
+                         const void* big, long long R, long long ldb, const float* bias, long long bias_bstride,
+                         const void* resid, long long ldr, void* out, long long ldo, int transpose_out, void* stream);
+
 /* ---- tcgen05 implicit-GEMM 3x3 conv on NHWC — ResBlock convs openaimodel.py:203,229; Downsample
  *      :150-152; Upsample.conv :105; VAE autokl_modules.py:48-76,93-111 ---------------------------
  * mode 0: stride 1 pad 1; mode 1: stride 2 pad 1; mode 2: stride 2 with pad (0,1,0,1) (VAE).

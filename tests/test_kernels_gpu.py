@@ -115,6 +115,45 @@ def test_gemm_two_source_and_batched_bias():
     assert_close(out, ref, what="gemm two-source")
 
 
+@pytest.mark.parametrize("M,N,K,K2,bias,resid", [(8, 5120, 5120, 0, "row", False), (8, 1280, 768, 0, "vec", False), (8, 2560, 2560, 1280, "vec", False),
+                                                 (32, 1280, 1280, 0, "vec", True), (32, 320, 320, 0, "vec", True), (64, 1536, 1280, 0, None, False),
+                                                 (5, 1000, 328, 0, "vec", True), (24, 640, 2560, 0, "vec", True)])
+def test_gemm_skinny_small_m(M, N, K, K2, bias, resid, monkeypatch):
+    """ops.gemm routes a small operand (VDB_SKINNY rows, here 64) to the CUDA-core weight-streaming kernel (vdb_gemm_skinny_bf16)"""
+    monkeypatch.setenv("VDB_SKINNY", "64")
+    ops = _ops()
+    a = rnd(M, K, seed=1)
+    a2 = rnd(M, K2, seed=5) if K2 else None
+    w = rnd(N, K + K2, seed=2, scale=(K + K2) ** -0.5)
+    b = None if bias is None else (rnd(M, N, seed=3, dtype=torch.float32) if bias == "row" else rnd(N, seed=3, dtype=torch.float32))
+    r = rnd(M, N, seed=4) if resid else None
+    assert ops.lib.vdb_gemm_skinny_fits(M, K + K2)
+    n0 = ops.launch_count()
+    out = ops.gemm(a, w, bias=b, resid=r, a2=a2, bias_bstride=N if bias == "row" else 0, rows_per_batch=1)
+    assert ops.launch_count() - n0 == 1                     # one launch: no split-K reduction pass
+    x = torch.cat([a, a2], 1) if K2 else a
+    ref = x.float() @ w.float().t()
+    if b is not None:
+        ref = ref + b
+    if resid:
+        ref = ref + r.float()
+    assert_close(out, ref, what=f"skinny gemm {M}x{N}x{K + K2}")
+    via_tc = ops.gemm(a, w, bias=b, resid=r, a2=a2, bias_bstride=N if bias == "row" else 0, rows_per_batch=1, ksplit=1)
+    assert_close(out, via_tc.float(), tol=1e-2, what="skinny vs tensor-core kernel")
+
+
+@pytest.mark.parametrize("R,T,K", [(640, 64, 640), (384, 32, 320), (1280, 64, 1280), (100, 7, 96)])
+def test_gemm_skinny_small_n_transposed(R, T, K, monkeypatch):
+    """the transposed projection out[R, T] = W x^T with a small token operand (V^T of the 0-D context blocks)"""
+    monkeypatch.setenv("VDB_SKINNY", "64")
+    ops = _ops()
+    wv, x = rnd(R, K, seed=1, scale=K ** -0.5), rnd(T, K, seed=2)
+    n0 = ops.launch_count()
+    out = ops.gemm(wv, x)
+    assert ops.launch_count() - n0 == 1 and out.shape == (R, T)
+    assert_close(out, wv.float() @ x.float().t(), what=f"skinny transposed {R}x{T}x{K}")
+
+
 def pack_geglu(w, b, bn=256):
     """rows [0,4C) value, [4C,8C) gate -> per 256-col tile: 128 value rows then their 128 gate rows"""
     n2 = w.shape[0] // 2
@@ -372,6 +411,8 @@ ATT_CASES = [
     (8, 8, 4096, 4096, 40, False),     # the benchmark's own self-attention launch (B = 8, 64x64 latent)
     (2, 3, 512, 900, 56, False),       # d 56 in DVP 64: row sums through the ones row of V^T, masked tail
     (1, 2, 256, 512, 32, False),       # d 32 in DVP 48: two padding swizzle groups behind the data rows
+    (1, 8, 1024, 1028, 40, False),     # four token-concatenated image contexts (4 x 257 keys, app.py mcg tab): 8 full tiles + 4 keys
+    (2, 8, 256, 514, 80, False),       # two images at d_head 80 (round-1 kernel, masked tail tile)
 ]
 
 

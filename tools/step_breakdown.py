@@ -123,6 +123,8 @@ def label(name, a):
         return f"gemm M{a[1]} N{a[8]} K{a[2] + a[5]} act{a[18]}{' +res' if a[13] else ''}"
     if name == "vdb_gemm_ln_bf16":
         return f"gemm M{a[1]} N{a[5]} K{a[2]} act{a[12]}{' +res' if a[8] else ''}{' ln-in' if a[13] else ''}{'-cols' if a[19] else ''}{' stats-out' if a[21] else ''}"
+    if name == "vdb_gemm_skinny_bf16":
+        return f"gemm_skinny S{a[1]} R{a[8]} K{a[2] + a[5]}{' +res' if a[12] else ''}{' transposed' if a[16] else ''}"
     if name == "vdb_conv3x3_bf16":
         return f"conv3x3 B{a[1]} {a[2]}x{a[3]} C{a[4]}+{a[10]}+{a[12]} -> N{a[7]} mode{a[5]}"
     if name == "vdb_attention_bf16":

@@ -1176,6 +1176,127 @@ __global__ void __launch_bounds__(256) linear_small_kernel(const float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Skinny GEMM on the CUDA cores for a SMALL operand of <= 64 rows (the 0-D diffuser: M = 8 FCBlock / Linear_MultiDim GEMMs that
+// stream 3.4 GB of weights per evaluation, and the 32-row projections of its context blocks).  On the tensor-core kernel these
+// launches are a latency chain (tensor-map fetch -> TMA -> MMA -> TMEM -> epilogue, plus a split-K reduction launch): 6-10 us
+// for 3 MB of weights.  Here the small operand lives in shared memory (bf16, whole K), every warp streams RW rows of the BIG
+// operand with 16-byte loads (lanes split K) and keeps RW x S fp32 accumulators; one shuffle reduction per row group.
+//   small = [S, K1 (+K2)] bf16 rows (two sources concatenated along K), big = [R, K] bf16 rows
+//   transpose_out 0: out[s, r] = dot + bias[s * bias_bstride + r] + resid[s, r]   (small = activations, big = weights)
+//   transpose_out 1: out[r, s] = dot                                                (small = tokens, big = weights: V^T projection)
+// ---------------------------------------------------------------------------------------------
+template <int S, int RW>
+__global__ void __launch_bounds__(256) gemm_skinny_kernel(const __nv_bfloat16* __restrict__ sm1, int K1, long long lds1,
+                                                          const __nv_bfloat16* __restrict__ sm2, int K2, long long lds2, int Srows,
+                                                          const __nv_bfloat16* __restrict__ big, long long R, long long ldb,
+                                                          const float* __restrict__ bias, long long bias_bstride,
+                                                          const __nv_bfloat16* __restrict__ resid, long long ldr,
+                                                          __nv_bfloat16* __restrict__ out, long long ldo, int transpose_out) {
+  extern __shared__ __align__(16) uint8_t skinny_smem[];
+  const int K = K1 + K2;
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(skinny_smem);   // [S][K], rows >= Srows zero
+  {
+    // stage the small operand: 8 independent 16-byte loads in flight per thread (a one-load-per-iteration loop is a chain of L2
+    // round trips: 20 of them for 80 KB made this stage cost more than the whole GEMM, first GPU run of this kernel: 30 us per launch)
+    const int vec_per_row = K >> 3;
+    const int nvec = S * vec_per_row;
+    for (int i0 = threadIdx.x; i0 < nvec; i0 += blockDim.x * 8) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * blockDim.x;
+        v[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (i < nvec) {
+          const int srow = i / vec_per_row, kv = (i - srow * vec_per_row) << 3;
+          if (srow < Srows)
+            v[u] = (kv < K1) ? __ldg(reinterpret_cast<const uint4*>(sm1 + srow * lds1 + kv))
+                             : __ldg(reinterpret_cast<const uint4*>(sm2 + srow * lds2 + (kv - K1)));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < nvec) {
+          const int srow = i / vec_per_row, kv = (i - srow * vec_per_row) << 3;
+          *reinterpret_cast<uint4*>(xs + static_cast<size_t>(srow) * K + kv) = v[u];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  const uint32_t xs_s = smem_u32(xs);
+  for (long long r0 = (static_cast<long long>(blockIdx.x) * nwarps + warp) * RW; r0 < R;
+       r0 += static_cast<long long>(gridDim.x) * nwarps * RW) {
+    float acc[RW][S];
+#pragma unroll
+    for (int r = 0; r < RW; ++r)
+#pragma unroll
+      for (int q = 0; q < S; ++q) acc[r][q] = 0.f;
+    // the next k-vector of every row is requested before the current one is multiplied (two loads per row in flight: with
+    // 8-16 warps per SM a single one leaves the HBM pipe two thirds empty on the 50-150 MB weight streams)
+    uint4 nxt[RW];
+    auto fetch = [&](int k) {
+#pragma unroll
+      for (int r = 0; r < RW; ++r) {
+        nxt[r] = make_uint4(0u, 0u, 0u, 0u);
+        if (k < K && r0 + r < R) nxt[r] = __ldg(reinterpret_cast<const uint4*>(big + (r0 + r) * ldb + k));
+      }
+    };
+    fetch(lane * 8);
+    for (int k = lane * 8; k < K; k += 256) {
+      float w[RW][8];
+      uint4 cur[RW];
+#pragma unroll
+      for (int r = 0; r < RW; ++r) cur[r] = nxt[r];
+      fetch(k + 256);
+#pragma unroll
+      for (int r = 0; r < RW; ++r) {
+        const uint4 u = cur[r];
+        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float2 t = unpack_bf16x2(uu[q]); w[r][2 * q] = t.x; w[r][2 * q + 1] = t.y; }
+      }
+#pragma unroll
+      for (int q = 0; q < S; ++q) {
+        uint4 xv;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xv.x), "=r"(xv.y), "=r"(xv.z), "=r"(xv.w)
+                     : "r"(xs_s + static_cast<uint32_t>((q * K + k) * 2)));
+        const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w};
+        float xf[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 t = unpack_bf16x2(xu[i]); xf[2 * i] = t.x; xf[2 * i + 1] = t.y; }
+#pragma unroll
+        for (int r = 0; r < RW; ++r)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[r][q] = fmaf(w[r][i], xf[i], acc[r][q]);
+      }
+    }
+    // reduce over the 32 lanes; lane (r * S + q) % 32 keeps result (r, q)
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+#pragma unroll
+      for (int q = 0; q < S; ++q) {
+        float v = acc[r][q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == ((r * S + q) & 31) && q < Srows && r0 + r < R) {
+          const long long row = r0 + r;
+          if (transpose_out) {
+            out[row * ldo + q] = __float2bfloat16(v);
+          } else {
+            if (bias) v += __ldg(bias + q * bias_bstride + row);
+            if (resid) v += __bfloat162float(resid[q * ldr + row]);
+            out[q * ldo + row] = __float2bfloat16(v);
+          }
+        }
+      }
+    }
+  }
+}
+
 // row softmax over [rows, n] bf16 with scale, fp32 math, bf16 out (VAE AttnBlock, autokl_modules.py:186-188)
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const __nv_bfloat16* __restrict__ x, long long rows,
                                                            int n, long long ld, float scale,
@@ -1371,6 +1492,30 @@ static int ew_blocks(long long work_items, int threads) {
 }  // namespace vdb
 
 using namespace vdb;
+
+namespace vdb {
+template <int S, int RW>
+static int launch_gemm_skinny(const void* sm1, int K1, long long lds1, const void* sm2, int K2, long long lds2, int Srows,
+                              const void* big, long long R, long long ldb, const float* bias, long long bias_bstride,
+                              const void* resid, long long ldr, void* out, long long ldo, int transpose_out, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(S) * (K1 + K2) * 2;
+  static size_t configured = 0;
+  if (smem > configured) {
+    VDB_CUDA_CHECK(cudaFuncSetAttribute(gemm_skinny_kernel<S, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  const long long groups = (R + RW - 1) / RW;                       // one warp per group of RW rows
+  const int blocks = static_cast<int>(std::min<long long>((groups + 7) / 8, static_cast<long long>(num_sms()) * (smem > 100 * 1024 ? 1 : 2)));
+  gemm_skinny_kernel<S, RW><<<blocks, 256, smem, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(sm1), K1, lds1, reinterpret_cast<const __nv_bfloat16*>(sm2), K2, lds2, Srows,
+      reinterpret_cast<const __nv_bfloat16*>(big), R, ldb, bias, bias_bstride, reinterpret_cast<const __nv_bfloat16*>(resid), ldr,
+      reinterpret_cast<__nv_bfloat16*>(out), ldo, transpose_out);
+  VDB_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return VDB_OK;
+}
+
+}  // namespace vdb
 
 extern "C" {
 
@@ -1778,6 +1923,25 @@ int vdb_linear_small(const float* x, int M, int K, const void* Wt, int N, const 
   VDB_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return VDB_OK;
+}
+
+int vdb_gemm_skinny_fits(int S, long long K) { return S >= 1 && S <= 64 && K > 0 && (K % 8) == 0 && ((S <= 8 ? 8 : S <= 16 ? 16 : S <= 32 ? 32 : 64) * K * 2 <= 200 * 1024) ? 1 : 0; }
+
+int vdb_gemm_skinny_bf16(const void* small1, int S, long long K1, long long lds1, const void* small2, long long K2, long long lds2,
+                         const void* big, long long R, long long ldb, const float* bias, long long bias_bstride,
+                         const void* resid, long long ldr, void* out, long long ldo, int transpose_out, void* stream) {
+  if (!small1 || !big || !out || S <= 0 || R <= 0 || K1 <= 0) return set_error(VDB_ERR_INVALID, "gemm_skinny: null/empty argument");
+  const long long K = K1 + (small2 ? K2 : 0);
+  if ((K1 % 8) || (small2 && (K2 % 8)) || (lds1 % 8) || (small2 && (lds2 % 8)) || (ldb % 8))
+    return set_error(VDB_ERR_INVALID, "gemm_skinny: K and leading dimensions must be multiples of 8");
+  if (!vdb_gemm_skinny_fits(S, K)) return set_error(VDB_ERR_UNSUPPORTED, "gemm_skinny: %d rows x K %lld do not fit shared memory (use vdb_gemm_bf16)", S, K);
+  if (transpose_out && (bias || resid)) return set_error(VDB_ERR_UNSUPPORTED, "gemm_skinny: transposed output takes no bias / residual");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int k1 = static_cast<int>(K1), k2 = small2 ? static_cast<int>(K2) : 0;
+  if (S <= 8) return launch_gemm_skinny<8, 4>(small1, k1, lds1, small2, k2, lds2, S, big, R, ldb, bias, bias_bstride, resid, ldr, out, ldo, transpose_out, st);
+  if (S <= 16) return launch_gemm_skinny<16, 4>(small1, k1, lds1, small2, k2, lds2, S, big, R, ldb, bias, bias_bstride, resid, ldr, out, ldo, transpose_out, st);
+  if (S <= 32) return launch_gemm_skinny<32, 2>(small1, k1, lds1, small2, k2, lds2, S, big, R, ldb, bias, bias_bstride, resid, ldr, out, ldo, transpose_out, st);
+  return launch_gemm_skinny<64, 1>(small1, k1, lds1, small2, k2, lds2, S, big, R, ldb, bias, bias_bstride, resid, ldr, out, ldo, transpose_out, st);
 }
 
 int vdb_clip_text_embed(const long long* tokens, const float* tok_emb, const float* pos_emb, int B, int L, int Lp, int C,

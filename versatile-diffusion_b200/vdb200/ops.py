@@ -6,6 +6,7 @@ CUDA-graph capturable (no host syncs, scratch comes from the caller or torch's c
 """
 import ctypes
 import math
+import os
 
 import torch
 
@@ -208,6 +209,14 @@ def add_int(t, delta):
     check(lib.vdb_add_int(_ptr(t), int(delta), _stream()), "add_int")
 
 
+def _skinny_rows():
+    """largest small operand (rows) that ops.gemm sends to vdb_gemm_skinny_bf16 instead of the tensor-core kernel
+    (VDB_SKINNY=<rows>; default 0 = never: on the full-size 0-D diffuser the CUDA-core kernel streams weights at 1.1-1.3 TB/s
+    against 2.7-3.5 TB/s for split-K tensor-core tiles — i2t step 4.43 ms (<= 16 rows) / 7.3 ms (<= 64) vs 3.38 ms,
+    profiles/r02_visit_x_skinny_gemm.log)"""
+    return int(os.environ.get("VDB_SKINNY", "0"))
+
+
 def gemm(a, w, bias=None, resid=None, out=None, act=ACT_NONE, a2=None, out_dtype=BF16, alpha=1.0,
          bias_bstride=0, rows_per_batch=1, bn=0, ksplit=0):
     """out[M,N'] = act(alpha*[a|a2] @ w^T + bias) + resid ; a [M,K] bf16, w [N,K(+K2)] bf16."""
@@ -221,6 +230,19 @@ def gemm(a, w, bias=None, resid=None, out=None, act=ACT_NONE, a2=None, out_dtype
     if out is None:
         out = torch.empty((M, n_out), dtype=out_dtype, device=a.device)
     _need(out, out_dtype, "out", True)
+    smax = _skinny_rows()
+    if act == ACT_NONE and alpha == 1.0 and out_dtype == BF16 and bn == 0 and ksplit == 0 and smax > 0:
+        # a small operand of <= 64 rows: weight-streaming CUDA-core kernel instead of the tensor-core latency chain
+        if M <= smax and (bias_bstride == 0 or rows_per_batch == 1) and lib.vdb_gemm_skinny_fits(M, K + K2):
+            check(lib.vdb_gemm_skinny_bf16(_ptr(a), M, K, a.stride(0), _ptr(a2), K2, a2.stride(0) if a2 is not None else 0,
+                                           _ptr(w), N, w.stride(0), _ptr(bias), int(bias_bstride), _ptr(resid),
+                                           resid.stride(0) if resid is not None else 0, _ptr(out), out.stride(0), 0, _stream()),
+                  "gemm_skinny_bf16")
+            return out
+        if N <= smax and M > N and a2 is None and bias is None and resid is None and lib.vdb_gemm_skinny_fits(N, K):
+            check(lib.vdb_gemm_skinny_bf16(_ptr(w), N, K, w.stride(0), None, 0, 0, _ptr(a), M, a.stride(0), None, 0, None, 0,
+                                           _ptr(out), out.stride(0), 1, _stream()), "gemm_skinny_bf16")
+            return out
     ws, ws_bytes = None, 0
     if ksplit != 1 and M <= 8192:   # split-K only ever triggers for small MN grids
         ws, ws_bytes = workspace(a.device), WORKSPACE_BYTES
