@@ -881,16 +881,9 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int kspl
     const long long m = i / (N / 4);
     const int n = static_cast<int>(i % (N / 4)) * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    // all partials of this output requested at once (ksplit <= 16): one load per loop iteration was a chain of ksplit L2 round
-    // trips per thread (7 us per reduction at the 8x8 level, profiles/r02_launch_shares_final.txt)
-    float4 pv[16];
-#pragma unroll
-    for (int s = 0; s < 16; ++s)
-      if (s < ksplit) pv[s] = __ldg(reinterpret_cast<const float4*>(partial + (static_cast<long long>(s) * M + m) * N + n));
-#pragma unroll
-    for (int s = 0; s < 16; ++s)
-      if (s < ksplit) { acc.x += pv[s].x; acc.y += pv[s].y; acc.z += pv[s].z; acc.w += pv[s].w; }
-    for (int s = 16; s < ksplit; ++s) {
+    // (one partial per iteration on purpose: with all ksplit loads of a thread in flight at once — addresses M*N*4 bytes apart —
+    // the 8x8-level convs got 4.4 us SLOWER per launch, 26.3 -> 30.7 us; profiles/r02_visit_final_splitk_reduce_unrolled.log)
+    for (int s = 0; s < ksplit; ++s) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (static_cast<long long>(s) * M + m) * N + n));
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
