@@ -103,6 +103,9 @@ int vdb_gemm_skinny_bf16(const void* small1, int S, long long K1, long long lds1
  *      autokl_modules.py:54-58) evaluated on the SOURCE image with the 9 taps folded into 2x2: X = source [B,H,W,C],
  *      out = [B,H,W,N] (that parity sub-lattice), Wt = [N, 4*C] (ty,tx,c) pre-summed on the host; no skip inputs.
  *      vdb_interleave2x2_nhwc assembles the four parities into [B,2H,2W,N].
+ * mode 7 + 2*py + px: the same parity conv, but `out` is the full [B,2H,2W,N] tensor and the tile is stored straight into pixels
+ *      (2y+py, 2x+px) through the output tensor map (no interleave pass, no parity temporaries); bf16 out, no residual / skips /
+ *      split-K, N % 32 == 0 (needs the TMA-store epilogue).
  * Wt [N, 9*C + Cs1 + Cs2], K order (ky,kx,c) then the 1x1 skip_connection columns whose inputs
  * skip1/skip2 (raw NHWC at output resolution; the two halves of torch.cat([h, hs.pop()]),
  * vd.py:372) are accumulated into the same TMEM tile (ResBlock.skip_connection, openaimodel.py:240).

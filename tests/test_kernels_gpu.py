@@ -7,6 +7,7 @@ fp32 elementwise kernels bit-exact or <= 1e-6 relative as stated per test.
 import math
 
 import os
+import sys
 
 import pytest
 import torch
@@ -316,6 +317,30 @@ def test_gemm_ln_producer_feeds_consumer():
     assert_close(out, ref, what="gemm_ln chain")
     via_kernel = ops.gemm(ops.layernorm(x, gamma, beta, eps=1e-5), w0)
     assert_close(out, via_kernel.float(), what="gemm_ln chain vs LayerNorm kernel + GEMM")
+
+
+@pytest.mark.parametrize("B,H,W,C,N", [(2, 16, 16, 64, 64), (8, 32, 32, 640, 640), (1, 24, 40, 128, 192), (3, 8, 8, 128, 320)])
+def test_folded_upsample_conv_direct_store_equals_interleave_pass(B, H, W, C, N, monkeypatch):
+    """nearest-2x upsample + 3x3 conv as four parity convs on the source: conv modes 7..10 store every parity straight into the
+    [B,2H,2W,N] result through the output tensor map; modes 3..6 + vdb_interleave2x2_nhwc must give the same bits, and both match
+    torch's upsample + conv2d on the bf16-rounded operands (Upsample.forward, openaimodel.py:107-117)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "versatile-diffusion_b200"))
+    from lib.model_zoo.diffusion_utils import fold_upsample_conv3x3
+    ops = _ops()
+    g = torch.Generator().manual_seed(H * 7 + C)
+    x = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16).to(DEV)
+    w = torch.randn(N, C, 3, 3, generator=g) * 0.05
+    b = torch.randn(N, generator=g).to(DEV)
+    wf = fold_upsample_conv3x3(w).to(DEV)
+    if _NO_TMA_EPI:
+        pytest.skip("the direct store rides on the TMA-store epilogue")
+    direct = ops.upsample2x_conv3x3_folded(x, wf, bias=b)
+    monkeypatch.setenv("VDB_UPFOLD_DIRECT", "0")
+    via_pass = ops.upsample2x_conv3x3_folded(x, wf, bias=b)
+    assert direct.shape == (B, 2 * H, 2 * W, N) and torch.equal(direct, via_pass)
+    ref = F.conv2d(F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest"),
+                   w.to(torch.bfloat16).float().to(DEV), b, padding=1).permute(0, 2, 3, 1)
+    assert_close(direct, ref, tol=3e-2, what=f"folded upsample conv {B}x{H}x{W} {C}->{N}")
 
 
 def pack_conv_w(w, skip_ws=()):

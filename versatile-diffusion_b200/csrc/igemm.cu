@@ -978,6 +978,8 @@ struct IgemmEpilogue {
   // ... and producer side
   float* stats_out = nullptr;
   int* stats_parts = nullptr;     // host out: partials per row the launch wrote (2 * N tiles)
+  // folded upsample writing straight into the interleaved [B, 2Ho, 2Wo, N] tensor: output parity (py * 2 + px), -1 = compact output
+  int out_parity = -1;
 };
 
 // Finish IgemmParams (tiling, split-K, B map) and launch.
@@ -1090,12 +1092,21 @@ static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot
       (!e.resid || (reinterpret_cast<uintptr_t>(e.resid) & 15) == 0)) {
     const int bw = std::min(p.TW, 32), bh = std::min(p.TH, 32 / bw), bb = 32 / (bw * bh);
     const long long ncols = (mode == 2) ? N / 2 : N;
+    // out_parity >= 0: the same tile, written into every second pixel of every second row of the [B, 2Ho, 2Wo, N] tensor —
+    // only the strides and the base of the output tensor map change, the kernel does not know
+    const int py = e.out_parity >= 0 ? (e.out_parity >> 1) : 0, px = e.out_parity >= 0 ? (e.out_parity & 1) : 0;
+    const uint64_t il = e.out_parity >= 0 ? 2 : 1;
+    const void* obase = reinterpret_cast<const __nv_bfloat16*>(e.out) + (static_cast<long long>(py) * (il * p.Wo) + px) * e.ldo;
     if (bb <= p.TB &&
-        make_tmap_4d_sw64(&p.tmO, e.out, static_cast<uint64_t>(ncols), static_cast<uint64_t>(p.Wo), static_cast<uint64_t>(p.Ho),
-                          static_cast<uint64_t>(p.Bo), static_cast<uint64_t>(e.ldo) * 2, static_cast<uint64_t>(p.Wo) * e.ldo * 2,
-                          static_cast<uint64_t>(p.Ho) * p.Wo * e.ldo * 2, 32, bw, bh, bb) == 0)
+        make_tmap_4d_sw64(&p.tmO, obase, static_cast<uint64_t>(ncols), static_cast<uint64_t>(p.Wo), static_cast<uint64_t>(p.Ho),
+                          static_cast<uint64_t>(p.Bo), il * static_cast<uint64_t>(e.ldo) * 2,
+                          il * il * static_cast<uint64_t>(p.Wo) * e.ldo * 2,
+                          il * il * static_cast<uint64_t>(p.Ho) * p.Wo * e.ldo * 2, 32, bw, bh, bb) == 0)
       mode += 2;
   }
+  if (e.out_parity >= 0 && mode != 3)
+    return set_error(VDB_ERR_UNSUPPORTED, "igemm: the interleaved-output upsample modes need the TMA-store epilogue (bf16 out, no "
+                                          "activation, N %% 32 == 0, aligned out, VDB_EPI_TMA != 0)");
   if (ln_in || st_out) {
     // folded LayerNorm: only on the TMA-store epilogues (bf16 out, act none / GEGLU, alpha 1, N % 32 == 0, aligned pointers)
     if (ln_in && st_out) return set_error(VDB_ERR_UNSUPPORTED, "igemm: a launch either consumes or produces LayerNorm statistics");
@@ -1295,7 +1306,11 @@ int vdb_conv3x3_bf16(const void* X, int B, int H, int Wd, int C, int mode, const
   if ((C % kBlockK) || (ldw % 8)) return set_error(VDB_ERR_INVALID, "conv3x3: C must be a multiple of 64, ldw of 8");
   if ((skip1 && (Cs1 % kBlockK)) || (skip2 && (Cs2 % kBlockK)))
     return set_error(VDB_ERR_INVALID, "conv3x3: skip channels must be multiples of 64");
-  if (mode < 0 || mode > 6) return set_error(VDB_ERR_INVALID, "conv3x3: bad mode");
+  if (mode < 0 || mode > 10) return set_error(VDB_ERR_INVALID, "conv3x3: bad mode");
+  const int out_parity = mode >= 7 ? mode - 7 : -1;     // modes 7..10 = modes 3..6 writing into the interleaved [B, 2H, 2W, N] tensor
+  if (mode >= 7) mode -= 4;
+  if (out_parity >= 0 && (resid || out_f32 || ksplit > 1)) return set_error(VDB_ERR_INVALID, "conv3x3: modes 7..10 take no residual, bf16 out, no split-K");
+  if (out_parity >= 0) ksplit = 1;
   const bool strided = (mode == 1 || mode == 2), folded = mode >= 3;
   if (strided && ((H & 1) || (Wd & 1))) return set_error(VDB_ERR_UNSUPPORTED, "conv3x3: stride 2 needs even H, W");
   if (folded && (skip1 || skip2)) return set_error(VDB_ERR_INVALID, "conv3x3: the folded-upsample modes take no skip inputs");
@@ -1364,6 +1379,7 @@ int vdb_conv3x3_bf16(const void* X, int B, int H, int Wd, int C, int mode, const
   IgemmEpilogue e;
   e.bias = bias; e.bias_bstride = bias_bstride; e.rows_per_batch = Ho * Wo;
   e.resid = resid; e.ldr = ldr; e.out = out; e.ldo = ldo; e.out_f32 = out_f32; e.act = act; e.alpha = 1.f;
+  e.out_parity = out_parity;
   return run_igemm(p, Wt, N, static_cast<long long>(p.kb_total) * kBlockK, ldw, e, bn, ksplit, workspace, ws_bytes,
                    reinterpret_cast<cudaStream_t>(stream));
 }

@@ -317,7 +317,7 @@ def conv3x3(x, w, bias=None, resid=None, out=None, mode=0, skip1=None, skip2=Non
     Ho, Wo = (H // 2, W // 2) if mode in (1, 2) else (H, W)
     cs1 = skip1.shape[-1] if skip1 is not None else 0
     cs2 = skip2.shape[-1] if skip2 is not None else 0
-    ntaps = 4 if mode >= 3 else 9          # modes 3..6: folded nearest-2x upsample (one parity, 2x2 taps on the source)
+    ntaps = 4 if mode >= 3 else 9          # modes 3..6 (7..10: stored interleaved into `out` [B,2H,2W,N]): folded nearest-2x upsample
     assert w.shape[1] == ntaps * Cc + cs1 + cs2, (w.shape, Cc, cs1, cs2, mode)
     if out is None:
         out = torch.empty((B, Ho, Wo, N), dtype=out_dtype, device=x.device)
@@ -452,6 +452,14 @@ def upsample2x_conv3x3_folded(x, wf, bias=None):
     x bf16 [B,H,W,C]; wf bf16 [4, N, 4*C]; -> [B,2H,2W,N]."""
     B, H, W, _ = x.shape
     N = wf.shape[1]
+    if N % 32 == 0 and os.environ.get("VDB_UPFOLD_DIRECT", "1") != "0" and os.environ.get("VDB_EPI_TMA", "1") != "0" \
+            and os.environ.get("VDB_IGEMM_SPEC", "1") != "0":
+        # modes 7..10: every parity conv stores straight into its pixels of the [B,2H,2W,N] result (output tensor map with
+        # doubled strides): no interleave pass, no parity temporaries
+        out = torch.empty((B, 2 * H, 2 * W, N), dtype=BF16, device=x.device)
+        for par in range(4):
+            conv3x3(x, wf[par], bias=bias, out=out, mode=7 + par, ksplit=1)
+        return out
     parts = torch.empty((4, B, H, W, N), dtype=BF16, device=x.device)
     for par in range(4):
         conv3x3(x, wf[par], bias=bias, out=parts[par], mode=3 + par, ksplit=1)
