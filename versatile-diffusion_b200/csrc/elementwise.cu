@@ -990,24 +990,35 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int B, in
 
 // im2col for 3x3/pad-1/stride-1 convs with tiny Cin (latent 4ch, RGB 3ch): fp32 NHWC in,
 // bf16 [B*H*W, Kpad] out with column (ky*3+kx)*Cin + c, zero padded to Kpad.
+// One thread per (pixel, 16-byte chunk of the row): 32-bit index math, one 16-byte store (the first version produced one bf16 per
+// thread behind five 64-bit divisions: 18 us for the 4 MB conv_in operand of the UNet, profiles/r02_launch_shares_final.txt).
 __global__ void im2col3x3_small_kernel(const float* __restrict__ x, int B, int H, int W, int Cin, int Kpad,
                                        float in_scale, float in_shift, __nv_bfloat16* __restrict__ y) {
-  const long long total = static_cast<long long>(B) * H * W * Kpad;
+  const int chunks = Kpad >> 3;
+  const long long total = static_cast<long long>(B) * H * W * chunks;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int k = static_cast<int>(i % Kpad);
-    long long p = i / Kpad;
-    float val = 0.f;
-    if (k < 9 * Cin) {
-      const int c = k % Cin, t = k / Cin;
-      const int xo = static_cast<int>(p % W);
-      const int yo = static_cast<int>((p / W) % H);
-      const int b = static_cast<int>(p / (static_cast<long long>(W) * H));
-      const int xi = xo + t % 3 - 1, yi = yo + t / 3 - 1;
-      if (xi >= 0 && xi < W && yi >= 0 && yi < H)
-        val = x[((static_cast<long long>(b) * H + yi) * W + xi) * Cin + c] * in_scale + in_shift;
+    const int q = static_cast<int>(i % chunks);
+    const long long p = i / chunks;
+    const int xo = static_cast<int>(p % W);
+    const int yo = static_cast<int>((p / W) % H);
+    const int b = static_cast<int>(p / (static_cast<long long>(W) * H));
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = q * 8 + e;
+      float val = 0.f;
+      if (k < 9 * Cin) {
+        const int t = k / Cin, c = k - t * Cin;
+        const int ty = t / 3, tx = t - ty * 3;
+        const int xi = xo + tx - 1, yi = yo + ty - 1;
+        if (xi >= 0 && xi < W && yi >= 0 && yi < H)
+          val = __ldg(x + ((static_cast<long long>(b) * H + yi) * W + xi) * Cin + c) * in_scale + in_shift;
+      }
+      v[e] = val;
     }
-    y[i] = __float2bfloat16(val);
+    *reinterpret_cast<uint4*>(y + p * Kpad + q * 8) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
   }
 }
 
@@ -1836,7 +1847,7 @@ int vdb_interleave2x2_nhwc(const void* src, int B, int H, int W, int C, void* y,
 int vdb_im2col3x3_small(const float* x, int B, int H, int W, int Cin, int Kpad, float in_scale, float in_shift,
                         void* y, void* stream) {
   if (!x || !y || 9 * Cin > Kpad || (Kpad % 8)) return set_error(VDB_ERR_INVALID, "im2col3x3_small: bad argument");
-  const long long total = static_cast<long long>(B) * H * W * Kpad;
+  const long long total = static_cast<long long>(B) * H * W * (Kpad / 8);
   VDB_PREFER_MAX_SMEM(im2col3x3_small_kernel);
   im2col3x3_small_kernel<<<ew_blocks(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, B, H, W, Cin, Kpad, in_scale, in_shift, reinterpret_cast<__nv_bfloat16*>(y));
