@@ -148,3 +148,32 @@ def test_packed_weights_invalidate_on_load_and_cast():
     rb._packed = {"stale": True}
     net.half()
     assert rb._packed is None and rb.in_layers[2].weight.dtype == torch.float16
+
+
+def test_layernorm_fold_algebra_matches_linear_of_layernorm():
+    """What vdb_gemm_ln_bf16's consumer epilogue evaluates — r * (x W'^T - mu * s) + c with the weights packed by fold_layernorm and
+    (mu, r) rebuilt from per-chunk partial (sum, sum of squares) — is Linear(LayerNorm(x)) (attention.py:206-218); checked in
+    fp64 on the CPU with the bf16-rounded folded weights the kernel would multiply with."""
+    import torch
+    import torch.nn.functional as F
+    from lib.model_zoo.attention import fold_layernorm
+    g = torch.Generator().manual_seed(3)
+    M, C, N, eps = 37, 320, 96, 1e-5
+    x = (torch.randn(M, C, generator=g) * 1.7 + 0.9).to(torch.bfloat16).double()         # rows with a mean, as the residual stream has
+    w, b = torch.randn(N, C, generator=g) * C ** -0.5, torch.randn(N, generator=g)
+    gamma, beta = 1.0 + 0.3 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
+    wg, s, c = fold_layernorm(w, b, gamma, beta)
+    assert wg.dtype == torch.bfloat16 and torch.equal(s, wg.float().sum(1))
+    # statistics exactly as a producer GEMM writes them: partial sums over column ranges (here 4 partials of 80 columns)
+    parts = torch.stack([torch.stack([xc.sum(1), (xc * xc).sum(1)], -1) for xc in x.split(80, dim=1)])     # [4, M, 2]
+    su, sq = parts[..., 0].sum(0), parts[..., 1].sum(0)
+    mu = su / C
+    r = torch.rsqrt((sq / C - mu * mu).clamp_min(0) + eps)
+    out = r[:, None] * (x @ wg.double().t() - mu[:, None] * s.double()[None, :]) + c.double()[None, :]
+    # reference with the SAME rounded weights: LayerNorm(x) * gamma folded == (x_hat * gamma) W^T with W' = bf16(W * gamma)
+    xhat = (x - x.mean(1, keepdim=True)) * torch.rsqrt(x.var(1, unbiased=False, keepdim=True) + eps)
+    ref = xhat @ wg.double().t() + (w.double() @ beta.double() + b.double())[None, :]
+    assert (out - ref).abs().max().item() < 1e-5          # (s and c are fp32 tables)
+    # and against torch's own LayerNorm + Linear with unrounded weights: only the bf16 rounding of W * gamma separates them
+    full = F.linear(F.layer_norm(x, (C,), gamma.double(), beta.double(), eps), w.double(), b.double())
+    assert (out - full).abs().max().item() < 5e-2 and F.cosine_similarity(out.flatten(), full.flatten(), dim=0).item() > 0.99999
