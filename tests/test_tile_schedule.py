@@ -7,18 +7,20 @@ import itertools
 import pytest
 
 
-def walk(num_ctas, unitsM, tilesN, ksplit, nfast):
-    """Yields (cta, m_idx, n_idx, ks) exactly as the producer / epilogue loops of igemm_kernel compute them (CTAS == 1)."""
+def walk(num_ctas, unitsM, tilesN, ksplit, nfast, chunked=False):
+    """Yields (cta, m_idx, n_idx, ks) exactly as the producer / epilogue loops of igemm_kernel compute them (CTAS == 1).
+    chunked: every CTA walks a contiguous range of ceil(tiles / CTAs) tiles instead of the grid-strided sequence."""
     num_tiles = unitsM * tilesN * ksplit
-    t_step = num_ctas
+    per_cta = -(-num_tiles // num_ctas)
     for cta in range(num_ctas):
-        t_first = cta
+        t_first, t_step = (cta * per_cta, 1) if chunked else (cta, num_ctas)
+        t_end = min(num_tiles, t_first + per_cta) if chunked else num_tiles
         step_m, step_r = t_step % unitsM, t_step // unitsM
         unit_m, rest = t_first % unitsM, t_first // unitsM
         nf_step_n, nf_step_m = (t_step % tilesN, t_step // tilesN) if nfast else (0, 0)
         nf_n, nf_m = (t_first % tilesN, t_first // tilesN) if nfast else (0, 0)
         t = t_first
-        while t < num_tiles:
+        while t < t_end:
             m_idx = nf_m if nfast else unit_m
             n_idx, ks = (nf_n if nfast else rest), 0
             if ksplit > 1:
@@ -63,3 +65,28 @@ def test_nfast_order_covers_every_tile_once_and_pins_the_n_tile(sms, unitsM, til
         # and the N tiles of one M tile run in the same wave: neighbouring CTAs, same iteration
         first_wave = [(m, n) for cta, m, n, _ in tiles if cta < tilesN]
         assert {m for m, _ in first_wave[:1]} == {0}
+
+
+@pytest.mark.parametrize("sms,unitsM,tilesN,ksplit", [c for c in CASES if c[3] == 1])
+def test_chunked_order_covers_every_tile_once_and_rarely_changes_the_n_tile(sms, unitsM, tilesN, ksplit):
+    """p.chunked: contiguous tile ranges.  Same coverage; a CTA sees at most ceil(range / unitsM) + 1 distinct N tiles, where the
+    strided walk changes its N tile every unitsM / CTAs tiles (GEGLU at the 64x64 level: 256 M tiles x 10 N tiles on 148 CTAs)."""
+    ctas = min(sms, unitsM * tilesN)
+    tiles = list(walk(ctas, unitsM, tilesN, 1, nfast=False, chunked=True))
+    assert sorted((m, n) for _, m, n, _ in tiles) == sorted(itertools.product(range(unitsM), range(tilesN)))
+    per = -(-unitsM * tilesN // ctas)
+    changes = {}
+    last = {}
+    for cta, _, n, _ in tiles:
+        if cta in last and last[cta] != n:
+            changes[cta] = changes.get(cta, 0) + 1
+        last[cta] = n
+    assert max(changes.values(), default=0) <= -(-per // unitsM), "a contiguous range crosses at most range / unitsM N-tile boundaries"
+
+
+def test_strided_walk_changes_the_n_tile_every_other_tile_on_the_geglu_shape():
+    tiles = list(walk(148, 256, 10, 1, nfast=False))
+    seq = [n for cta, _, n, _ in tiles if cta == 0]
+    assert sum(1 for a, b in zip(seq, seq[1:]) if a != b) >= len(seq) // 2 - 1          # 18 tiles, ~9 table reloads
+    seq_c = [n for cta, _, n, _ in walk(148, 256, 10, 1, nfast=False, chunked=True) if cta == 0]
+    assert sum(1 for a, b in zip(seq_c, seq_c[1:]) if a != b) == 0

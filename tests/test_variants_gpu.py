@@ -24,6 +24,7 @@ VARIANTS = [
     ({"VDB_LN_RG": "0"}, "layernorm"),             # warp-per-row LayerNorm instead of the row-group kernel
     ({"VDB_ATT_FA": "0"}, "attention"),            # column-split attention kernel for every shape (round-1 default)
     ({"VDB_ATT_ONES": "0"}, "attention"),          # two-tile kernel with the row sums on the softmax threads
+    ({"VDB_CHUNKED": "1"}, "gemm or conv3x3"),     # contiguous tile range per CTA instead of the grid-strided walk (validated, round 2: neutral)
 ]
 
 RUN = pytest.mark.skipif(os.environ.get("VDB_TEST_VARIANTS") != "1", reason="set VDB_TEST_VARIANTS=1 to run the opt-in kernel variants")

@@ -75,6 +75,7 @@ struct alignas(64) IgemmParams {
   int nfast;                  // 1: N is the fast tile index (tile t -> n = t % tilesN, m = t / tilesN); needs ksplit == 1
   unsigned long long* timeline; // debug: per-tile role timestamps of CTA 0 (null = off)
   unsigned smem_bytes;        // dynamic shared memory of the launch (LN modes check their carve-up against it)
+  int chunked;                // 1: every CTA walks a contiguous range of tiles instead of a grid-strided one
 };
 
 enum { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_QGELU = 3, ACT_GEGLU = 4 };
@@ -200,7 +201,14 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
   const int tilesM = p.tilesW * p.tilesH * p.tilesB;
   const int unitsM = tilesM / CTAS;
   const int num_tiles = unitsM * p.tilesN * p.ksplit;
-  const int t_first = blockIdx.x / CTAS, t_step = gridDim.x / CTAS;
+  // Tile walk of this CTA (all three roles use the same bounds): strided (tile c, c + grid, ...) or, p.chunked, a contiguous range.
+  // With M as the fast tile index a strided walk changes its N tile every unitsM / grid tiles — every 1.7 tiles on the 64x64-level
+  // GEMMs with many N tiles (GEGLU: 10) — and every change reloads the bias / LayerNorm tables behind two barriers; a contiguous
+  // range changes it once or twice per launch.
+  const int n_ctas = gridDim.x / CTAS, cta_id = blockIdx.x / CTAS;
+  const int per_cta = (num_tiles + n_ctas - 1) / n_ctas;
+  const int t_first = p.chunked ? cta_id * per_cta : cta_id, t_step = p.chunked ? 1 : n_ctas;
+  const int t_end = p.chunked ? min(num_tiles, t_first + per_cta) : num_tiles;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -213,7 +221,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
       // than L2 is fetched from DRAM once instead of once per N tile
       const int nf_step_n = p.nfast ? t_step % p.tilesN : 0, nf_step_m = p.nfast ? t_step / p.tilesN : 0;
       int nf_n = p.nfast ? t_first % p.tilesN : 0, nf_m = p.nfast ? t_first / p.tilesN : 0;
-      for (int t = t_first; t < num_tiles; t += t_step) {
+      for (int t = t_first; t < t_end; t += t_step) {
         const int m_idx = (p.nfast ? nf_m : unit_m) * CTAS + static_cast<int>(cta_rank);
         int n_idx = p.nfast ? nf_n : rest, ks = 0;
         if (p.ksplit > 1) { n_idx = rest % p.tilesN; ks = rest / p.tilesN; }
@@ -270,7 +278,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM * CTAS, BN);
       uint32_t stage = 0, phase = 0;
       int it = 0;
-      for (int t = t_first; t < num_tiles; t += t_step, ++it) {
+      for (int t = t_first; t < t_end; t += t_step, ++it) {
         const int ks = (p.ksplit > 1) ? (t / unitsM) / p.tilesN : 0;
         const int kb_begin = ks * p.kb_per_split;
         const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
@@ -355,9 +363,9 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
       }
     };
     if constexpr (kLnIn) {
-      if (!p.ln_on_cols && p.ln_parts <= kLnPre && t_first < num_tiles) ln_prefetch((t_first % unitsM) * kBlockM + r);
+      if (!p.ln_on_cols && p.ln_parts <= kLnPre && t_first < t_end) ln_prefetch((t_first % unitsM) * kBlockM + r);
     }
-    for (int t = t_first; t < num_tiles; t += t_step, ++it) {
+    for (int t = t_first; t < t_end; t += t_step, ++it) {
       const int m_idx = (p.nfast ? nf_m : unit_m) * CTAS + static_cast<int>(cta_rank);
       int n_idx = p.nfast ? nf_n : rest, ks = 0;
       if (p.ksplit > 1) { n_idx = rest % p.tilesN; ks = rest / p.tilesN; }
@@ -483,7 +491,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) igemm_kernel(const __grid_con
           }
         }
         // request the next tile's row partials (GEMM view, M-fast order: unit_m already points at the next tile)
-        if (!p.ln_on_cols && p.ln_parts <= kLnPre && t + t_step < num_tiles) ln_prefetch(unit_m * kBlockM + r);
+        if (!p.ln_on_cols && p.ln_parts <= kLnPre && t + t_step < t_end) ln_prefetch(unit_m * kBlockM + r);
       }
       VDB_TLE(4, it);   // epilogue: waiting for the accumulator
       if constexpr (CTAS == 2) mbar_wait_wd(&tmem_full[as], aphase, 3); else mbar_wait(&tmem_full[as], aphase);
@@ -1069,6 +1077,16 @@ static int run_igemm(IgemmParams& p, const void* Wt, long long N, long long Ktot
     const double a_bytes = static_cast<double>(M) * static_cast<double>(Ktot) * 2.0;
     p.nfast = (nfast_mode != 0 && !pair && p.ksplit == 1 && p.tilesN > 1 && (grid % p.tilesN) == 0 &&
                (nfast_mode == 2 || a_bytes > 48e6) && !ln_in) ? 1 : 0;   // (the LN modes prefetch along the M-fast order)
+  }
+  // contiguous tile ranges (VDB_CHUNKED=1; default off) where the strided walk would change its N tile within a CTA's sequence
+  // more than a contiguous one does: several N tiles and a few tiles per CTA.  Measured neutral on every UNet shape (GEGLU 64x64:
+  // 50.4 vs 50.3 us, bench 481.96 vs 481.62 ms; profiles/r02_visit_ch_chunked_tile_walk.log): the table reloads it saves were not
+  // on the critical path.
+  {
+    static const int chunked_mode = [] { const char* ev = getenv("VDB_CHUNKED"); return ev ? atoi(ev) : 0; }();
+    const long long units = static_cast<long long>(tilesM / (pair ? 2 : 1)) * p.tilesN * p.ksplit;
+    const int grid = static_cast<int>(std::min<long long>(units, pair ? num_sms() / 2 : num_sms()));
+    p.chunked = (chunked_mode != 0 && !p.nfast && p.ksplit == 1 && p.tilesN > 1 && units >= 3LL * grid) ? 1 : 0;
   }
   int rc = make_tmap_2d(&p.tmB, Wt, static_cast<uint64_t>(Ktot), static_cast<uint64_t>(N),
                         static_cast<uint64_t>(ldw) * 2, kBlockK, pair ? BN / 2 : BN);
